@@ -1,0 +1,128 @@
+"""The C++ oracle (oracle/oracle.cpp) against the golden vectors produced by the independent Python big-int model
+(oracle/gen_golden.py).  CPU only.  This is the pin that replaces the reference's missing known-answer vectors
+(SURVEY.md §8c): two independent implementations agreeing bit-for-bit on canonical outputs."""
+import pytest
+
+import oracle
+from oracle import bn254_model as m
+
+H = bytes.fromhex
+
+
+def test_field_constants_match_survey_appendix(golden):
+    g = golden("field")
+    # Montgomery constants quoted in SURVEY.md appendix A (halo2curves layout: 4 x u64 LE limbs)
+    assert g["fq"]["inv64"] == "87d20782e4866389"
+    assert g["fr"]["inv64"] == "c2e1f593efffffff"
+    assert int.from_bytes(H(g["fq"]["mont_R"]), "little") == 0x0e0a77c19a07df2f666ea36f7879462c0a78eb28f5c70b3dd35d438dc58f0d9d
+    assert int.from_bytes(H(g["fr"]["mont_R"]), "little") == 0x0e0a77c19a07df2f666ea36f7879462e36fc76959f60cd29ac96341c4ffffffb
+    # oracle's Montgomery form of 1 is R
+    one = (1).to_bytes(32, "little")
+    assert oracle.fp_to_mont(0, one) == H(g["fq"]["mont_R"])
+    assert oracle.fp_to_mont(1, one) == H(g["fr"]["mont_R"])
+
+
+@pytest.mark.parametrize("field,name", [(0, "fq"), (1, "fr")])
+def test_field_mul_inv(golden, field, name):
+    g = golden("field")[name]
+    for a, b, c in g["mul"]:
+        assert oracle.fp_mul(field, H(a), H(b)) == H(c)
+    for a, ai in g["inv"]:
+        assert oracle.fp_inv(field, H(a)) == H(ai)
+
+
+def test_field_rejects_non_canonical(golden):
+    p = H(golden("field")["p"])
+    with pytest.raises(ValueError):
+        oracle.fp_mul(0, p, p)  # from_repr fails for values >= modulus
+
+
+def test_g1_scalar_mul_and_add(golden):
+    g = golden("g1")
+    gen = H(g["generator"])
+    for k, exp in g["mul_G"]:
+        assert oracle.g1_mul(gen, H(k)) == H(exp)
+    for a, b, c in g["add"]:
+        assert oracle.g1_add(H(a), H(b)) == H(c)
+
+
+def test_g1_rejects_off_curve():
+    bad = (1).to_bytes(32, "little") + (3).to_bytes(32, "little")
+    assert not oracle.g1_is_on_curve(bad)
+    with pytest.raises(ValueError):
+        oracle.g1_mul(bad, (5).to_bytes(32, "little"))
+
+
+def test_msm_native_fold_and_pippenger(golden):
+    for case in golden("msm"):
+        s, p, n = H(case["scalars"]), H(case["points"]), case["n"]
+        exp = H(case["expected"])
+        assert oracle.msm_native(s, p, n) == exp, case["name"]            # loader/native.rs:61-71
+        assert oracle.msm_pippenger(s, p, n, 1) == exp, case["name"]       # util/msm.rs:259-304
+        assert oracle.msm_pippenger(s, p, n, 4) == exp, case["name"]       # util/msm.rs:308-343
+
+
+def test_msm_empty_is_an_error():
+    with pytest.raises(ValueError):       # .unwrap() on an empty fold panics, native.rs:69
+        oracle.msm_native(b"", b"", 0)
+
+
+def test_synth_generators_match_python_model():
+    n = 9
+    assert oracle.synth_scalars(3, 5, n) == b"".join(m.fe_to_le(m.synth_scalar(3, 5 + i)) for i in range(n))
+    ts = [m.synth_point_scalar(3, 5 + i) for i in range(n)]
+    assert list(oracle.synth_point_scalars(3, 5, n)) == ts
+    assert oracle.synth_points(3, 5, n, 2) == b"".join(m.g1_to_bytes(m.g1_mul(m.G1_GEN, t)) for t in ts)
+
+
+def test_msm_dlog_checksum_agrees_with_pippenger():
+    n = 3000
+    s = oracle.synth_scalars(11, 0, n)
+    p = oracle.synth_points(11, 0, n, 4)
+    t = oracle.synth_point_scalars(11, 0, n)
+    assert oracle.msm_pippenger(s, p, n, 4) == oracle.msm_expected_from_dlogs(s, t, n)
+
+
+def test_pairing_gt_bytes_and_decide(golden):
+    g = golden("pairing")
+    g2, s_g2 = H(g["g2_generator"]), H(g["s_g2"])
+    assert oracle.g2_generator() == g2
+    assert oracle.g2_mul(g2, H(g["s"])) == s_g2
+    # e(G1, G2): decide(lhs=G1, rhs=identity) leaves exactly e(G1,G2) in GT
+    gen = m.g1_to_bytes(m.G1_GEN)
+    ok, gt = oracle.kzg_decide(gen, bytes(64), g2, s_g2)
+    assert not ok and gt == H(g["e_G1_G2"])
+    for c in g["checks"]:
+        ok, gt = oracle.kzg_decide(H(c["lhs"]), H(c["rhs"]), g2, s_g2)
+        assert ok == c["accept"], c["name"]
+        assert gt == H(c["gt"]), c["name"]
+
+
+def test_decide_batch_matches_single_and_hoisted(golden):
+    g = golden("pairing")
+    g2, s_g2 = H(g["g2_generator"]), H(g["s_g2"])
+    lhs = b"".join(H(c["lhs"]) for c in g["checks"])
+    rhs = b"".join(H(c["rhs"]) for c in g["checks"])
+    n = len(g["checks"])
+    for hoist in (0, 1):
+        acc, gt = oracle.kzg_decide_batch(lhs, rhs, n, g2, s_g2, threads=3, hoist=hoist, want_gt=True)
+        assert list(acc) == [int(c["accept"]) for c in g["checks"]]
+        assert gt == b"".join(H(c["gt"]) for c in g["checks"])
+
+
+def test_pairing_bilinearity_property():
+    # e(aP, bQ) e(-abP, Q) = 1   <=>  decide(lhs = a*b*G, rhs = a*G, g2, s_g2 = b*G2) accepts
+    a, b = 0x1234567890ABCDEF1234567890ABCDEF, 0xFEDCBA0987654321
+    g2 = oracle.g2_generator()
+    bg2 = oracle.g2_mul(g2, m.fe_to_le(b))
+    gen = m.g1_to_bytes(m.G1_GEN)
+    lhs = oracle.g1_mul(gen, m.fe_to_le(a * b % m.R))
+    rhs = oracle.g1_mul(gen, m.fe_to_le(a))
+    assert oracle.kzg_decide(lhs, rhs, g2, bg2, want_gt=False)[0]
+    assert not oracle.kzg_decide(lhs, oracle.g1_mul(gen, m.fe_to_le(a + 1)), g2, bg2, want_gt=False)[0]
+
+
+def test_accumulate(golden):
+    for c in golden("accumulate"):
+        a, b = oracle.kzg_accumulate(H(c["lhs"]), H(c["rhs"]), c["n"], H(c["r"]))
+        assert a == H(c["out_lhs"]) and b == H(c["out_rhs"])
