@@ -1,0 +1,154 @@
+/* snarkv_cuda.h — C ABI of libsnarkv_cuda.so: the B200-native replacement for snark-verifier's native
+ * verification hot path (BN254 G1 multi-scalar multiplication + KZG accumulator pairing check).
+ *
+ * Every entry point names the reference interface it replaces (paths relative to
+ * /root/reference/snark-verifier/src).  INTEGRATION.md shows the Rust `extern "C"` block and the
+ * `impl EcPointLoader / AccumulationDecider for CudaLoader` a maintainer would add on the reference side.
+ *
+ * There is NO CPU fallback anywhere behind this header: every compute entry point launches sm_100a kernels and
+ * returns SNARKV_ERR_CUDA if no usable device / kernel image is present.
+ *
+ * ---- Byte formats -----------------------------------------------------------------------------------------------
+ *  scalar (Fr)      32 B   SNARKV_CANONICAL : little-endian canonical integer  == `PrimeField::to_repr()`
+ *                                              (util/msm.rs:264, util/arithmetic.rs:260)
+ *                          SNARKV_MONTGOMERY: halo2curves' in-memory `Fr([u64;4])` limbs (value * 2^256 mod r)
+ *                                              == `SerdeObject::to_raw_bytes()`
+ *  G1 affine        64 B   x || y, each coordinate in the selected format; the identity is (0,0) (halo2curves)
+ *  G1 Jacobian      96 B   X || Y || Z always MONTGOMERY limbs (halo2curves `G1` layout); identity Z == 0
+ *  G2 affine       128 B   x.c0 || x.c1 || y.c0 || y.c1, CANONICAL; identity all-zero
+ *  GT (Fq12)       384 B   12 x Fq CANONICAL in tower order c0.c0.c0, c0.c0.c1, c0.c1.c0, c0.c1.c1, c0.c2.c0, c0.c2.c1,
+ *                          c1.c0.c0 ... c1.c2.c1  with Fq2 = Fq[i]/(i^2+1), Fq6 = Fq2[v]/(v^3-(9+i)), Fq12 = Fq6[w]/(w^2-v)
+ *
+ * ---- Errors -------------------------------------------------------------------------------------------------------
+ *  Return value 0 = ok, < 0 = error (see enum).  A pairing check that REJECTS is data (`accept[i] = 0`), not an error;
+ *  the Rust glue maps it to `Error::AssertionFailure("e(lhs, g2)·e(rhs, -s_g2) == O")` (pcs/kzg/decider.rs:81).
+ *  n == 0 for an MSM is SNARKV_ERR_EMPTY, mirroring the `.unwrap()` panic at loader/native.rs:69.
+ *
+ * ---- Threading ------------------------------------------------------------------------------------------------------
+ *  A context is thread-compatible, not thread-safe: one call at a time per context (it owns one stream and one grow-only
+ *  workspace).  Create one context per host thread / per GPU.  `NativeLoader` is a ZST reachable from any thread
+ *  (loader/native.rs:11-19); the Rust glue keeps one lazily created context per thread to offer the same.
+ */
+#ifndef SNARKV_CUDA_H
+#define SNARKV_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct snarkv_ctx snarkv_ctx;
+
+enum {
+    SNARKV_OK = 0,
+    SNARKV_ERR_USAGE = -1,       /* null pointer, bad enum, size overflow */
+    SNARKV_ERR_EMPTY = -2,       /* empty MSM (native.rs:69 panics) */
+    SNARKV_ERR_CUDA = -3,        /* CUDA runtime / no device / no kernel image; see snarkv_last_error */
+    SNARKV_ERR_BAD_SCALAR = -4,  /* CANONICAL scalar >= r (`from_repr` would fail) */
+    SNARKV_ERR_BAD_POINT = -5,   /* coordinate >= p, or point not on the curve (`from_xy` would fail, accumulator.rs:75-78) */
+    SNARKV_ERR_NO_KEY = -6       /* decide called before snarkv_kzg_set_deciding_key */
+};
+
+enum { SNARKV_CANONICAL = 0, SNARKV_MONTGOMERY = 1 };
+
+/* Validation of MSM inputs.  halo2curves values are valid by construction, so the Rust glue passes 0;
+ * untrusted byte sources pass SNARKV_CHECK_INPUTS to get from_repr / from_xy behaviour on the device. */
+enum { SNARKV_CHECK_INPUTS = 1 };
+
+/* ---- context ---------------------------------------------------------------------------------------------------------
+ * Replaces the global `LOADER: NativeLoader` (loader/native.rs:11-15).  `device` is a CUDA ordinal. */
+int snarkv_init(int device, snarkv_ctx** out);
+void snarkv_destroy(snarkv_ctx* ctx);
+const char* snarkv_last_error(const snarkv_ctx* ctx); /* never NULL; "" when no error */
+const char* snarkv_version(void);
+/* Launch all subsequent work of this context on an external stream (a `cudaStream_t`, e.g. torch's current stream);
+ * NULL restores the context's own stream. */
+int snarkv_set_stream(snarkv_ctx* ctx, void* cuda_stream);
+/* MSM tuning: window bits c (0 = choose from n). */
+int snarkv_set_window_bits(snarkv_ctx* ctx, int c);
+
+/* ---- a1: EcPointLoader::multi_scalar_multiplication --------------------------------------------------------------------
+ * Replaces `NativeLoader::multi_scalar_multiplication(pairs) -> C` (loader.rs:108-113, loader/native.rs:61-71):
+ *   out = to_affine( sum_i points[i] * scalars[i] ).
+ * Host buffers in (n x 32 B scalars, n x 64 B affine points, both in `format`), 64-byte affine result out (same format).
+ * The algorithm behind it is a signed-digit Pippenger (the reference's own large-n algorithm is util/msm.rs:259-343);
+ * the affine result is canonical, hence bit-identical to the reference fold. */
+int snarkv_g1_msm(snarkv_ctx* ctx, const uint8_t* scalars, const uint8_t* points, size_t n, int format, int flags,
+                  uint8_t out_affine[64]);
+
+/* Same operation on operands already resident in this device's HBM (pointers from cudaMalloc / a torch tensor's
+ * data_ptr()).  Results are written to DEVICE memory, nothing is synchronised or copied to the host:
+ *   d_out_affine   64 B  affine result in `format`            (may be NULL)
+ *   d_out_jacobian 96 B  the same point as a Jacobian partial   (may be NULL) — the unit exchanged between GPUs.
+ * `d_status` (4 B, device, may be NULL) receives 0 or the first SNARKV_ERR_BAD_* found when SNARKV_CHECK_INPUTS is set. */
+int snarkv_g1_msm_device(snarkv_ctx* ctx, const void* d_scalars, const void* d_points, size_t n, int format, int flags,
+                         void* d_out_affine, void* d_out_jacobian, void* d_status);
+
+/* Fold k Jacobian partials (k x 96 B, device memory) into one affine point (64 B, device memory, `format`):
+ * the `results.iter().fold(identity, |acc, r| acc + r)` + `.to_affine()` of util/msm.rs:333-335 across GPUs,
+ * applied after an all-gather of the per-rank partials. */
+int snarkv_g1_fold_partials_device(snarkv_ctx* ctx, const void* d_partials, size_t k, int format, void* d_out_affine);
+
+/* m independent MSMs in one launch: MSM j covers terms [offsets[j], offsets[j+1]) of the scalar/point arrays
+ * (offsets has m+1 entries, offsets[0] == 0).  out = m x 64 B.  This is PlonkVerifier running `Msm::evaluate`
+ * (util/msm.rs:81-98) for many proofs at once; every segment must be non-empty. */
+int snarkv_g1_msm_batch(snarkv_ctx* ctx, const uint8_t* scalars, const uint8_t* points, const uint64_t* offsets, size_t m,
+                        int format, int flags, uint8_t* out_affine);
+
+/* ---- a6: KzgAs::verify (accumulate) ------------------------------------------------------------------------------------
+ * Replaces pcs/kzg/accumulation.rs:41-63: powers_of_r = r.powers(n) (loader.rs:71-78);
+ *   out_lhs = sum_i r^i lhs[i], out_rhs = sum_i r^i rhs[i]   (two MSMs; a blinding pair, if any, is just the last pair).
+ * lhs/rhs: n x 64 B, r: 32 B, outputs 64 B each, all in `format`.  The powers are produced on the device. */
+int snarkv_kzg_accumulate(snarkv_ctx* ctx, const uint8_t* lhs, const uint8_t* rhs, size_t n, const uint8_t r[32], int format,
+                          uint8_t out_lhs[64], uint8_t out_rhs[64]);
+
+/* ---- a7/a8/a9: KzgDecidingKey + AccumulationDecider::{decide, decide_all} -----------------------------------------------
+ * `KzgDecidingKey::new(svk.g, g2, s_g2)` (pcs/kzg/decider.rs:6-42).  Precomputes `G2Prepared::from(g2)` and
+ * `G2Prepared::from(-s_g2)` once (the reference recomputes both inside every decide call, decider.rs:74).
+ * g1: 64 B CANONICAL, g2 / s_g2: 128 B CANONICAL. */
+int snarkv_kzg_set_deciding_key(snarkv_ctx* ctx, const uint8_t g1[64], const uint8_t g2[128], const uint8_t s_g2[128]);
+
+/* `KzgAs::decide` for N accumulators at once (decider.rs:70-93):
+ *   accept[i] = ( e(lhs_i, g2) * e(rhs_i, -s_g2) == 1 ).
+ * lhs/rhs: N x 64 B in `format`; accept: N bytes; gt_out: N x 384 B CANONICAL or NULL.
+ * `decide` is N = 1; `decide_all` is "all accept[i] == 1" (the reference stops at the first failure — callers that
+ * need that index take the first zero). */
+int snarkv_kzg_decide_batch(snarkv_ctx* ctx, const uint8_t* lhs, const uint8_t* rhs, size_t N, int format, uint8_t* accept,
+                            uint8_t* gt_out);
+/* Device-resident variant: d_lhs/d_rhs N x 64 B, d_accept N bytes, d_gt N x 384 B or NULL; no host synchronisation. */
+int snarkv_kzg_decide_batch_device(snarkv_ctx* ctx, const void* d_lhs, const void* d_rhs, size_t N, int format, void* d_accept,
+                                   void* d_gt);
+
+/* ---- synthetic workload (bench / tests) ----------------------------------------------------------------------------------
+ * Deterministic inputs (the test suite restates the same definition independently):
+ *   scalar_i: 4 x splitmix64 limbs, top limb masked to 62 bits, one conditional subtraction of r;
+ *   point_i = [t_i] G with t_i = splitmix64(...) | 1 (64-bit), G = (1, 2).
+ * Written to DEVICE memory in `format` (n x 32 B / n x 64 B), indices start .. start + n - 1. */
+int snarkv_synth_scalars_device(snarkv_ctx* ctx, uint64_t seed, uint64_t start, size_t n, int format, void* d_out);
+int snarkv_synth_points_device(snarkv_ctx* ctx, uint64_t seed, uint64_t start, size_t n, int format, void* d_out);
+
+/* ---- test support --------------------------------------------------------------------------------------------------------
+ * Element-wise field operation on n CANONICAL 32-byte values (host buffers): field 0 = Fq, 1 = Fr;
+ * op 0 = a*b, 1 = a+b, 2 = a-b, 3 = a^-1, 4 = a^2.  Exists so the parity suite can pin the device Montgomery arithmetic
+ * (fp.cuh) directly against the golden field vectors; replaces nothing in the reference. */
+int snarkv_debug_field_op(snarkv_ctx* ctx, int field, int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out);
+
+/* ---- instrumentation -----------------------------------------------------------------------------------------------------
+ * When enabled, every pipeline stage of the next MSM / decide call is bracketed by CUDA events on the context's stream.
+ * snarkv_profile_read synchronises and returns up to `cap` (name, milliseconds, launches) records of the LAST call. */
+typedef struct {
+    const char* name; /* static string, e.g. "msm_bucket_accumulate" */
+    float ms;
+    int launches;
+} snarkv_stage_time;
+int snarkv_profile_enable(snarkv_ctx* ctx, int on);
+int snarkv_profile_read(snarkv_ctx* ctx, snarkv_stage_time* out, int cap);
+/* total kernels launched by this context since creation */
+uint64_t snarkv_launch_count(const snarkv_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNARKV_CUDA_H */

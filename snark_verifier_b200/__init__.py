@@ -1,0 +1,328 @@
+"""snark_verifier_b200 — B200-native BN254 G1 MSM + KZG accumulator decision behind snark-verifier's Loader / Decider surface.
+
+The product is `libsnarkv_cuda.so` (hand-written sm_100a kernels, C ABI in include/snarkv_cuda.h).  This package is the
+thin Python host mirror used by tests/ and bench.py; the C++ mirror of the reference traits lives in host/cuda_loader.hpp and
+the Rust binding a maintainer would add is in INTEGRATION.md.
+
+Names follow the reference (paths relative to /root/reference/snark-verifier/src):
+  CudaLoader.multi_scalar_multiplication   <-> EcPointLoader::multi_scalar_multiplication   loader.rs:108-113, loader/native.rs:61-71
+  Msm                                      <-> util::msm::Msm                                util/msm.rs:20-128
+  KzgDecidingKey, KzgAs.decide/decide_all  <-> pcs/kzg/decider.rs:6-42, :70-93
+  KzgAs.verify                             <-> pcs/kzg/accumulation.rs:41-63
+  Error / AssertionFailure                 <-> lib.rs:18-28
+
+There is no CPU fallback: importing works anywhere, but constructing a CudaLoader without the built library or without a
+B200 raises immediately.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsnarkv_cuda.so")
+
+CANONICAL, MONTGOMERY = 0, 1
+CHECK_INPUTS = 1
+
+OK, ERR_USAGE, ERR_EMPTY, ERR_CUDA, ERR_BAD_SCALAR, ERR_BAD_POINT, ERR_NO_KEY = 0, -1, -2, -3, -4, -5, -6
+
+R_MODULUS = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+Q_MODULUS = 0x30644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD47
+
+
+class Error(Exception):
+    """Mirror of snark_verifier::Error (lib.rs:18-28)."""
+
+
+class AssertionFailure(Error):
+    """Error::AssertionFailure(String)"""
+
+
+class CudaError(RuntimeError):
+    """CUDA extension missing / no device / runtime failure.  Never swallowed, never replaced by a CPU path."""
+
+
+class _StageTime(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char_p), ("ms", ctypes.c_float), ("launches", ctypes.c_int)]
+
+
+_lib = None
+
+# every symbol include/snarkv_cuda.h declares: (restype, argtypes)
+_vp, _sz, _i, _u64 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint64
+C_ABI = {
+    "snarkv_init": (_i, [_i, ctypes.POINTER(_vp)]),
+    "snarkv_destroy": (None, [_vp]),
+    "snarkv_last_error": (ctypes.c_char_p, [_vp]),
+    "snarkv_version": (ctypes.c_char_p, []),
+    "snarkv_set_stream": (_i, [_vp, _vp]),
+    "snarkv_set_window_bits": (_i, [_vp, _i]),
+    "snarkv_g1_msm": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp]),
+    "snarkv_g1_msm_device": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp, _vp, _vp]),
+    "snarkv_g1_fold_partials_device": (_i, [_vp, _vp, _sz, _i, _vp]),
+    "snarkv_g1_msm_batch": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _vp]),
+    "snarkv_kzg_accumulate": (_i, [_vp, _vp, _vp, _sz, _vp, _i, _vp, _vp]),
+    "snarkv_kzg_set_deciding_key": (_i, [_vp, _vp, _vp, _vp]),
+    "snarkv_kzg_decide_batch": (_i, [_vp, _vp, _vp, _sz, _i, _vp, _vp]),
+    "snarkv_kzg_decide_batch_device": (_i, [_vp, _vp, _vp, _sz, _i, _vp, _vp]),
+    "snarkv_synth_scalars_device": (_i, [_vp, _u64, _u64, _sz, _i, _vp]),
+    "snarkv_synth_points_device": (_i, [_vp, _u64, _u64, _sz, _i, _vp]),
+    "snarkv_debug_field_op": (_i, [_vp, _i, _i, _vp, _vp, _sz, _vp]),
+    "snarkv_profile_enable": (_i, [_vp, _i]),
+    "snarkv_profile_read": (_i, [_vp, ctypes.POINTER(_StageTime), _i]),
+    "snarkv_launch_count": (_u64, [_vp]),
+}
+
+
+def load_library():
+    """dlopen libsnarkv_cuda.so and bind every symbol of include/snarkv_cuda.h.  Raises CudaError if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CudaError(f"{LIB_PATH} is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                            "there is no CPU fallback")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in C_ABI.items():
+            fn = getattr(lib, name)  # AttributeError here = header/library drift
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def _addr(buf):
+    """bytes-like / numpy array / int (device pointer) / None -> c_void_p"""
+    if buf is None:
+        return None
+    if isinstance(buf, int):
+        return ctypes.c_void_p(buf)
+    if isinstance(buf, (bytes, bytearray)):
+        return ctypes.cast(ctypes.c_char_p(bytes(buf)) if isinstance(buf, bytearray) else ctypes.c_char_p(buf), ctypes.c_void_p)
+    if hasattr(buf, "ctypes"):  # numpy
+        return ctypes.c_void_p(buf.ctypes.data)
+    if isinstance(buf, ctypes.Array):
+        return ctypes.cast(buf, ctypes.c_void_p)
+    raise TypeError(type(buf))
+
+
+class CudaLoader:
+    """The fourth interpretation of the verifier program (after Native / Evm / Halo2 loaders): values are computed on a B200.
+
+    LoadedScalar = Fr and LoadedEcPoint = G1Affine as plain byte strings (32 B / 64 B) exactly like NativeLoader keeps
+    them as plain host values (loader/native.rs:44,75); only the two hot operations are overridden.
+    """
+
+    def __init__(self, device=0, fmt=CANONICAL):
+        self.lib = load_library()
+        h = ctypes.c_void_p()
+        rc = self.lib.snarkv_init(device, ctypes.byref(h))
+        if rc != 0 or not h:
+            raise CudaError(f"snarkv_init(device={device}) failed (rc={rc}): no sm_100 GPU visible; there is no CPU fallback")
+        self.h = h
+        self.device = device
+        self.fmt = fmt
+
+    # -- plumbing -------------------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.snarkv_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc == 0:
+            return
+        msg = self.lib.snarkv_last_error(self.h).decode()
+        if rc == ERR_CUDA:
+            raise CudaError(f"{what}: {msg}")
+        raise Error(f"{what}: rc={rc} {msg}")
+
+    def set_stream(self, cuda_stream):
+        self._check(self.lib.snarkv_set_stream(self.h, ctypes.c_void_p(cuda_stream) if cuda_stream else None), "set_stream")
+
+    def set_window_bits(self, c):
+        self._check(self.lib.snarkv_set_window_bits(self.h, c), "set_window_bits")
+
+    def profile(self, on=True):
+        self._check(self.lib.snarkv_profile_enable(self.h, 1 if on else 0), "profile_enable")
+
+    def stage_times(self):
+        arr = (_StageTime * 32)()
+        k = self.lib.snarkv_profile_read(self.h, arr, 32)
+        if k < 0:
+            self._check(k, "profile_read")
+        return [(arr[i].name.decode(), arr[i].ms, arr[i].launches) for i in range(k)]
+
+    @property
+    def launch_count(self):
+        return int(self.lib.snarkv_launch_count(self.h))
+
+    # -- EcPointLoader --------------------------------------------------------------------------------------------
+    def ec_point_load_const(self, value):
+        return bytes(value)
+
+    def ec_point_assert_eq(self, annotation, lhs, rhs):
+        if bytes(lhs) != bytes(rhs):
+            raise AssertionFailure(annotation)  # loader/native.rs:50-59
+
+    def multi_scalar_multiplication(self, pairs):
+        """pairs: sequence of (scalar 32 B, point 64 B) — `&[(&LoadedScalar, &LoadedEcPoint)]` (loader.rs:108-113)."""
+        pairs = list(pairs)
+        scalars = b"".join(bytes(s) for s, _ in pairs)
+        points = b"".join(bytes(p) for _, p in pairs)
+        return self.msm(scalars, points, len(pairs))
+
+    def msm(self, scalars, points, n, flags=0):
+        """Contiguous form: n x 32 B scalars, n x 64 B points (bytes or numpy uint8) -> 64 B affine."""
+        out = ctypes.create_string_buffer(64)
+        self._check(self.lib.snarkv_g1_msm(self.h, _addr(scalars), _addr(points), n, self.fmt, flags, out), "multi_scalar_multiplication")
+        return out.raw
+
+    def msm_device(self, d_scalars, d_points, n, d_out_affine=None, d_out_jacobian=None, d_status=None, flags=0):
+        self._check(self.lib.snarkv_g1_msm_device(self.h, _addr(d_scalars), _addr(d_points), n, self.fmt, flags,
+                                                  _addr(d_out_affine), _addr(d_out_jacobian), _addr(d_status)), "msm_device")
+
+    def fold_partials_device(self, d_partials, k, d_out_affine):
+        self._check(self.lib.snarkv_g1_fold_partials_device(self.h, _addr(d_partials), k, self.fmt, _addr(d_out_affine)), "fold_partials")
+
+    def msm_batch(self, scalars, points, offsets, flags=0):
+        """m independent MSMs; offsets = m+1 cumulative term counts."""
+        m = len(offsets) - 1
+        off = (ctypes.c_uint64 * (m + 1))(*offsets)
+        out = ctypes.create_string_buffer(64 * m)
+        self._check(self.lib.snarkv_g1_msm_batch(self.h, _addr(scalars), _addr(points), ctypes.cast(off, ctypes.c_void_p), m,
+                                                 self.fmt, flags, out), "msm_batch")
+        return [out.raw[64 * j:64 * j + 64] for j in range(m)]
+
+    def field_op(self, field, op, a, b, n):
+        out = ctypes.create_string_buffer(32 * n)
+        self._check(self.lib.snarkv_debug_field_op(self.h, field, op, _addr(a), _addr(b), n, out), "field_op")
+        return out.raw
+
+    # -- synthetic workload ---------------------------------------------------------------------------------------
+    def synth_scalars_device(self, seed, start, n, d_out):
+        self._check(self.lib.snarkv_synth_scalars_device(self.h, seed, start, n, self.fmt, _addr(d_out)), "synth_scalars")
+
+    def synth_points_device(self, seed, start, n, d_out):
+        self._check(self.lib.snarkv_synth_points_device(self.h, seed, start, n, self.fmt, _addr(d_out)), "synth_points")
+
+
+class Msm:
+    """Host mirror of `util::msm::Msm` (util/msm.rs:20-128): constant + scalars + bases, evaluated by the loader's MSM.
+    Scalars are Python ints mod r here (the deferred algebra is microseconds of Fr work and stays on the host)."""
+
+    def __init__(self, loader, constant=None, scalars=None, bases=None):
+        self.loader, self.constant = loader, constant
+        self.scalars, self.bases = list(scalars or []), list(bases or [])
+
+    @classmethod
+    def constant_(cls, loader, c):
+        return cls(loader, constant=c % R_MODULUS)
+
+    @classmethod
+    def base(cls, loader, b):
+        return cls(loader, scalars=[1], bases=[bytes(b)])  # util/msm.rs:54-61
+
+    def scale(self, k):  # util/msm.rs:100-107
+        if self.constant is not None:
+            self.constant = self.constant * k % R_MODULUS
+        self.scalars = [s * k % R_MODULUS for s in self.scalars]
+        return self
+
+    def push(self, scalar, base):  # util/msm.rs:109-116 (dedupe by equality)
+        base = bytes(base)
+        if base in self.bases:
+            i = self.bases.index(base)
+            self.scalars[i] = (self.scalars[i] + scalar) % R_MODULUS
+        else:
+            self.scalars.append(scalar % R_MODULUS)
+            self.bases.append(base)
+
+    def extend(self, other):  # util/msm.rs:118-128
+        if other.constant is not None:
+            self.constant = other.constant if self.constant is None else (self.constant + other.constant) % R_MODULUS
+        for s, b in zip(other.scalars, other.bases):
+            self.push(s, b)
+        return self
+
+    def __add__(self, other):
+        r = Msm(self.loader, self.constant, self.scalars, self.bases)
+        return r.extend(other)
+
+    def __mul__(self, k):
+        return Msm(self.loader, self.constant, self.scalars, self.bases).scale(k)
+
+    def evaluate(self, gen=None):  # util/msm.rs:81-98
+        pairs = []
+        if self.constant is not None:
+            if gen is None:
+                raise ValueError("constant term needs a generator")  # the reference panics (unwrap on None)
+            pairs.append((self.constant.to_bytes(32, "little"), bytes(gen)))
+        pairs += [(s.to_bytes(32, "little"), b) for s, b in zip(self.scalars, self.bases)]
+        assert self.loader.fmt == CANONICAL, "Msm host mirror keeps canonical scalars"
+        return self.loader.multi_scalar_multiplication(pairs)
+
+
+class KzgAccumulator:
+    """pcs/kzg/accumulator.rs:6-26"""
+
+    def __init__(self, lhs, rhs):
+        self.lhs, self.rhs = bytes(lhs), bytes(rhs)
+
+
+class KzgDecidingKey:
+    """pcs/kzg/decider.rs:6-42: (svk.g, g2, s_g2).  Installing it on a loader precomputes both G2Prepared on the device."""
+
+    def __init__(self, g1, g2, s_g2):
+        self.g1, self.g2, self.s_g2 = bytes(g1), bytes(g2), bytes(s_g2)
+
+
+class KzgAs:
+    """`KzgAs<Bn256, MOS>` restricted to the hot path: AccumulationDecider::{decide, decide_all} and AccumulationScheme::verify."""
+
+    ASSERTION = "e(lhs, g2)·e(rhs, -s_g2) == O"  # decider.rs:81
+
+    def __init__(self, loader, dk):
+        self.loader, self.dk = loader, dk
+        L = loader
+        L._check(L.lib.snarkv_kzg_set_deciding_key(L.h, dk.g1, dk.g2, dk.s_g2), "KzgDecidingKey")
+
+    def decide_batch(self, lhs, rhs, n, want_gt=False):
+        """n accumulators as contiguous n x 64 B arrays -> (accept bytes, gt bytes | None)."""
+        L = self.loader
+        acc = ctypes.create_string_buffer(n)
+        gt = ctypes.create_string_buffer(384 * n) if want_gt else None
+        L._check(L.lib.snarkv_kzg_decide_batch(L.h, _addr(lhs), _addr(rhs), n, L.fmt, acc, gt), "decide")
+        return acc.raw, (gt.raw if want_gt else None)
+
+    def decide_batch_device(self, d_lhs, d_rhs, n, d_accept, d_gt=None):
+        L = self.loader
+        L._check(L.lib.snarkv_kzg_decide_batch_device(L.h, _addr(d_lhs), _addr(d_rhs), n, L.fmt, _addr(d_accept), _addr(d_gt)), "decide_device")
+
+    def decide(self, accumulator):  # decider.rs:70-82
+        acc, _ = self.decide_batch(accumulator.lhs, accumulator.rhs, 1)
+        if acc[0] != 1:
+            raise AssertionFailure(self.ASSERTION)
+
+    def decide_all(self, accumulators):  # decider.rs:84-93
+        accumulators = list(accumulators)
+        if not accumulators:
+            return
+        lhs = b"".join(a.lhs for a in accumulators)
+        rhs = b"".join(a.rhs for a in accumulators)
+        acc, _ = self.decide_batch(lhs, rhs, len(accumulators))
+        if any(b != 1 for b in acc):
+            raise AssertionFailure(self.ASSERTION)
+
+    def verify(self, instances, r, blind=None):  # accumulation.rs:41-63
+        accs = list(instances) + ([blind] if blind is not None else [])
+        L = self.loader
+        lhs = b"".join(a.lhs for a in accs)
+        rhs = b"".join(a.rhs for a in accs)
+        ol, orr = ctypes.create_string_buffer(64), ctypes.create_string_buffer(64)
+        L._check(L.lib.snarkv_kzg_accumulate(L.h, lhs, rhs, len(accs), bytes(r), L.fmt, ol, orr), "KzgAs::verify")
+        return KzgAccumulator(ol.raw, orr.raw)

@@ -1,0 +1,259 @@
+// capi.cu — the extern "C" surface declared in include/snarkv_cuda.h.
+//
+// This file is the drop-in boundary for the reference's Loader / Decider hot path: the host-buffer entry points are what
+// a Rust `impl EcPointLoader<G1Affine> for CudaLoader` (mirroring snark-verifier/src/loader/native.rs:43-72) and
+// `impl AccumulationDecider<G1Affine, CudaLoader> for KzgAs<Bn256, MOS>` (mirroring pcs/kzg/decider.rs:62-94) call; see
+// INTEGRATION.md.  There is no CPU arithmetic here — only copies, launches and status decoding.
+#include <new>
+
+#include "ctx.hpp"
+
+using namespace snarkv;
+
+#define CTX_GUARD(ctx)                            \
+    do {                                          \
+        if (!(ctx)) return SNARKV_ERR_USAGE;      \
+        (ctx)->err.clear();                       \
+        cudaError_t _g = cudaSetDevice((ctx)->device); \
+        if (_g != cudaSuccess) return (ctx)->fail(SNARKV_ERR_CUDA, "cudaSetDevice", _g); \
+    } while (0)
+
+static int bad_format(int f) { return f != SNARKV_CANONICAL && f != SNARKV_MONTGOMERY; }
+
+extern "C" {
+
+const char* snarkv_version(void) { return "snarkv-cuda 0.1 (sm_100a; BN254 G1 MSM + KZG decide)"; }
+
+int snarkv_init(int device, snarkv_ctx** out) {
+    if (!out) return SNARKV_ERR_USAGE;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t ce = cudaGetDeviceCount(&count);
+    if (ce != cudaSuccess || device < 0 || device >= count) return SNARKV_ERR_CUDA;  // no GPU: fail loudly, no fallback
+    if (cudaSetDevice(device) != cudaSuccess) return SNARKV_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SNARKV_ERR_CUDA;
+    if (prop.major != 10) return SNARKV_ERR_CUDA;  // kernels are built for sm_100a only
+    snarkv_ctx* c = new (std::nothrow) snarkv_ctx();
+    if (!c) return SNARKV_ERR_USAGE;
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming) != cudaSuccess) {
+        delete c;
+        return SNARKV_ERR_CUDA;
+    }
+    c->stream = c->own_stream;
+    *out = c;
+    return SNARKV_OK;
+}
+
+void snarkv_destroy(snarkv_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    kzg_free_key(ctx);
+    for (int i = 0; i < WS_SLOTS; ++i)
+        if (ctx->ws[i]) cudaFree(ctx->ws[i]);
+    for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
+    if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+const char* snarkv_last_error(const snarkv_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int snarkv_set_stream(snarkv_ctx* ctx, void* cuda_stream) {
+    CTX_GUARD(ctx);
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return SNARKV_OK;
+}
+
+int snarkv_set_window_bits(snarkv_ctx* ctx, int c) {
+    if (!ctx || c < 0 || c > 22) return SNARKV_ERR_USAGE;
+    ctx->window_bits = c;
+    return SNARKV_OK;
+}
+
+int snarkv_profile_enable(snarkv_ctx* ctx, int on) {
+    if (!ctx) return SNARKV_ERR_USAGE;
+    ctx->profiling = on != 0;
+    return SNARKV_OK;
+}
+
+int snarkv_profile_read(snarkv_ctx* ctx, snarkv_stage_time* out, int cap) {
+    CTX_GUARD(ctx);
+    SNARKV_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    int k = 0;
+    for (const StageRecord& r : ctx->stages) {
+        if (k >= cap) break;
+        float ms = 0.f;
+        SNARKV_CUDA_TRY(ctx, cudaEventElapsedTime(&ms, r.start, r.stop));
+        out[k].name = r.name;
+        out[k].ms = ms;
+        out[k].launches = r.launches;
+        ++k;
+    }
+    return k;
+}
+
+uint64_t snarkv_launch_count(const snarkv_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- MSM --------------------------------------------------------------------------------------------------------------
+int snarkv_g1_msm(snarkv_ctx* ctx, const uint8_t* scalars, const uint8_t* points, size_t n, int format, int flags,
+                  uint8_t out_affine[64]) {
+    CTX_GUARD(ctx);
+    if (n == 0) return ctx->fail(SNARKV_ERR_EMPTY, "multi_scalar_multiplication on an empty slice");
+    if (!scalars || !points || !out_affine || bad_format(format)) return ctx->fail(SNARKV_ERR_USAGE, "snarkv_g1_msm: bad argument");
+    ctx->profile_begin_call();
+    return msm_run_host(ctx, scalars, points, n, format, flags, out_affine);
+}
+
+int snarkv_g1_msm_device(snarkv_ctx* ctx, const void* d_scalars, const void* d_points, size_t n, int format, int flags,
+                         void* d_out_affine, void* d_out_jacobian, void* d_status) {
+    CTX_GUARD(ctx);
+    if (n == 0) return ctx->fail(SNARKV_ERR_EMPTY, "multi_scalar_multiplication on an empty slice");
+    if (!d_scalars || !d_points || bad_format(format)) return ctx->fail(SNARKV_ERR_USAGE, "snarkv_g1_msm_device: bad argument");
+    ctx->profile_begin_call();
+    return msm_run_device(ctx, d_scalars, d_points, n, format, format, format, flags, d_out_affine, d_out_jacobian, d_status);
+}
+
+int snarkv_g1_fold_partials_device(snarkv_ctx* ctx, const void* d_partials, size_t k, int format, void* d_out_affine) {
+    CTX_GUARD(ctx);
+    if (!d_partials || !d_out_affine || bad_format(format)) return ctx->fail(SNARKV_ERR_USAGE, "fold_partials: bad argument");
+    return msm_fold_partials_device(ctx, d_partials, k, format, d_out_affine);
+}
+
+int snarkv_g1_msm_batch(snarkv_ctx* ctx, const uint8_t* scalars, const uint8_t* points, const uint64_t* offsets, size_t m,
+                        int format, int flags, uint8_t* out_affine) {
+    CTX_GUARD(ctx);
+    if (!scalars || !points || !offsets || !out_affine || bad_format(format) || m == 0)
+        return ctx->fail(SNARKV_ERR_USAGE, "snarkv_g1_msm_batch: bad argument");
+    if (offsets[0] != 0) return ctx->fail(SNARKV_ERR_USAGE, "offsets[0] must be 0");
+    for (size_t j = 0; j < m; ++j)
+        if (offsets[j + 1] <= offsets[j]) return ctx->fail(SNARKV_ERR_EMPTY, "empty or decreasing MSM segment");
+    const size_t total = offsets[m];
+    ctx->profile_begin_call();
+    uint8_t* d_s = (uint8_t*)ctx->wsget(WS_IO_A, total * 32);
+    uint8_t* d_p = (uint8_t*)ctx->wsget(WS_IO_B, total * 64);
+    uint64_t* d_off = (uint64_t*)ctx->wsget(WS_IO_C, (m + 1) * 8);
+    uint8_t* d_out = (uint8_t*)ctx->wsget(WS_IO_D, m * 64);
+    int* d_status = (int*)ctx->wsget(WS_STATUS, 4);
+    if (!d_s || !d_p || !d_off || !d_out || !d_status) return SNARKV_ERR_CUDA;
+    cudaStream_t st = ctx->stream;
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_s, scalars, total * 32, cudaMemcpyHostToDevice, st));
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_p, points, total * 64, cudaMemcpyHostToDevice, st));
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_off, offsets, (m + 1) * 8, cudaMemcpyHostToDevice, st));
+    int rc = msm_batch_device(ctx, d_s, d_p, d_off, m, total, format, flags, d_out, d_status);
+    if (rc) return rc;
+    int status = 0;
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(out_affine, d_out, m * 64, cudaMemcpyDeviceToHost, st));
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(&status, d_status, 4, cudaMemcpyDeviceToHost, st));
+    SNARKV_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    if (status != 0) return ctx->fail(status, status == SNARKV_ERR_BAD_SCALAR ? "scalar is not a canonical Fr" : "point is not a valid G1Affine");
+    return SNARKV_OK;
+}
+
+// ---- KzgAs::verify -------------------------------------------------------------------------------------------------------
+int snarkv_kzg_accumulate(snarkv_ctx* ctx, const uint8_t* lhs, const uint8_t* rhs, size_t n, const uint8_t r[32], int format,
+                          uint8_t out_lhs[64], uint8_t out_rhs[64]) {
+    CTX_GUARD(ctx);
+    if (n == 0) return ctx->fail(SNARKV_ERR_EMPTY, "accumulate over zero accumulators");
+    if (!lhs || !rhs || !r || !out_lhs || !out_rhs || bad_format(format)) return ctx->fail(SNARKV_ERR_USAGE, "snarkv_kzg_accumulate: bad argument");
+    ctx->profile_begin_call();
+    uint8_t* d_l = (uint8_t*)ctx->wsget(WS_IO_A, n * 64);
+    uint8_t* d_r = (uint8_t*)ctx->wsget(WS_IO_B, n * 64);
+    uint8_t* d_pw = (uint8_t*)ctx->wsget(WS_IO_C, n * 32 + 32);  // [r | powers]
+    uint8_t* d_o = (uint8_t*)ctx->wsget(WS_OUT, 256);
+    if (!d_l || !d_r || !d_pw || !d_o) return SNARKV_ERR_CUDA;
+    cudaStream_t st = ctx->stream;
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_pw, r, 32, cudaMemcpyHostToDevice, st));
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_l, lhs, n * 64, cudaMemcpyHostToDevice, st));
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_r, rhs, n * 64, cudaMemcpyHostToDevice, st));
+    int rc = fr_powers_device(ctx, d_pw, format, n, d_pw + 32);
+    if (rc) return rc;
+    rc = msm_run_device(ctx, d_pw + 32, d_l, n, SNARKV_MONTGOMERY, format, format, 0, d_o, nullptr, nullptr);
+    if (rc) return rc;
+    rc = msm_run_device(ctx, d_pw + 32, d_r, n, SNARKV_MONTGOMERY, format, format, 0, d_o + 64, nullptr, nullptr);
+    if (rc) return rc;
+    uint8_t host[128];
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(host, d_o, 128, cudaMemcpyDeviceToHost, st));
+    SNARKV_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    memcpy(out_lhs, host, 64);
+    memcpy(out_rhs, host + 64, 64);
+    return SNARKV_OK;
+}
+
+// ---- KZG decide --------------------------------------------------------------------------------------------------------
+int snarkv_kzg_set_deciding_key(snarkv_ctx* ctx, const uint8_t g1[64], const uint8_t g2[128], const uint8_t s_g2[128]) {
+    CTX_GUARD(ctx);
+    if (!g1 || !g2 || !s_g2) return ctx->fail(SNARKV_ERR_USAGE, "snarkv_kzg_set_deciding_key: null argument");
+    return kzg_set_key(ctx, g1, g2, s_g2);
+}
+
+int snarkv_kzg_decide_batch_device(snarkv_ctx* ctx, const void* d_lhs, const void* d_rhs, size_t N, int format, void* d_accept,
+                                   void* d_gt) {
+    CTX_GUARD(ctx);
+    if (!ctx->has_key) return ctx->fail(SNARKV_ERR_NO_KEY, "decide before snarkv_kzg_set_deciding_key");
+    if (!d_lhs || !d_rhs || !d_accept || bad_format(format)) return ctx->fail(SNARKV_ERR_USAGE, "snarkv_kzg_decide_batch_device: bad argument");
+    if (N == 0) return SNARKV_OK;
+    ctx->profile_begin_call();
+    return kzg_decide_device(ctx, d_lhs, d_rhs, N, format, d_accept, d_gt);
+}
+
+int snarkv_kzg_decide_batch(snarkv_ctx* ctx, const uint8_t* lhs, const uint8_t* rhs, size_t N, int format, uint8_t* accept,
+                            uint8_t* gt_out) {
+    CTX_GUARD(ctx);
+    if (!ctx->has_key) return ctx->fail(SNARKV_ERR_NO_KEY, "decide before snarkv_kzg_set_deciding_key");
+    if (!lhs || !rhs || !accept || bad_format(format)) return ctx->fail(SNARKV_ERR_USAGE, "snarkv_kzg_decide_batch: bad argument");
+    if (N == 0) return SNARKV_OK;  // decide_all over an empty Vec is Ok(())
+    ctx->profile_begin_call();
+    uint8_t* d_l = (uint8_t*)ctx->wsget(WS_IO_A, N * 64);
+    uint8_t* d_r = (uint8_t*)ctx->wsget(WS_IO_B, N * 64);
+    uint8_t* d_acc = (uint8_t*)ctx->wsget(WS_IO_C, N);
+    uint8_t* d_gt = gt_out ? (uint8_t*)ctx->wsget(WS_IO_D, N * 384) : nullptr;
+    if (!d_l || !d_r || !d_acc || (gt_out && !d_gt)) return SNARKV_ERR_CUDA;
+    cudaStream_t st = ctx->stream;
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_l, lhs, N * 64, cudaMemcpyHostToDevice, st));
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_r, rhs, N * 64, cudaMemcpyHostToDevice, st));
+    int rc = kzg_decide_device(ctx, d_l, d_r, N, format, d_acc, d_gt);
+    if (rc) return rc;
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(accept, d_acc, N, cudaMemcpyDeviceToHost, st));
+    if (gt_out) SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(gt_out, d_gt, N * 384, cudaMemcpyDeviceToHost, st));
+    SNARKV_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return SNARKV_OK;
+}
+
+// ---- test support ---------------------------------------------------------------------------------------------------------
+int snarkv_debug_field_op(snarkv_ctx* ctx, int field, int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) {
+    CTX_GUARD(ctx);
+    if (!a || !b || !out || n == 0 || field < 0 || field > 1) return ctx->fail(SNARKV_ERR_USAGE, "snarkv_debug_field_op: bad argument");
+    uint8_t* d_a = (uint8_t*)ctx->wsget(WS_IO_A, n * 32);
+    uint8_t* d_b = (uint8_t*)ctx->wsget(WS_IO_B, n * 32);
+    uint8_t* d_o = (uint8_t*)ctx->wsget(WS_IO_C, n * 32);
+    if (!d_a || !d_b || !d_o) return SNARKV_ERR_CUDA;
+    cudaStream_t st = ctx->stream;
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_a, a, n * 32, cudaMemcpyHostToDevice, st));
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_b, b, n * 32, cudaMemcpyHostToDevice, st));
+    int rc = field_op_device(ctx, field, op, d_a, d_b, n, d_o);
+    if (rc) return rc;
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(out, d_o, n * 32, cudaMemcpyDeviceToHost, st));
+    SNARKV_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return SNARKV_OK;
+}
+
+// ---- synthetic workload ---------------------------------------------------------------------------------------------------
+int snarkv_synth_scalars_device(snarkv_ctx* ctx, uint64_t seed, uint64_t start, size_t n, int format, void* d_out) {
+    CTX_GUARD(ctx);
+    if (!d_out || bad_format(format)) return ctx->fail(SNARKV_ERR_USAGE, "snarkv_synth_scalars_device: bad argument");
+    return synth_scalars_device(ctx, seed, start, n, format, d_out);
+}
+int snarkv_synth_points_device(snarkv_ctx* ctx, uint64_t seed, uint64_t start, size_t n, int format, void* d_out) {
+    CTX_GUARD(ctx);
+    if (!d_out || bad_format(format)) return ctx->fail(SNARKV_ERR_USAGE, "snarkv_synth_points_device: bad argument");
+    return synth_points_device(ctx, seed, start, n, format, d_out);
+}
+
+}  // extern "C"

@@ -1,0 +1,163 @@
+// ctx.hpp — library-internal context: stream, grow-only device workspace, stage timers, error string.
+// The public face of this struct is the opaque `snarkv_ctx` of include/snarkv_cuda.h (it stands where the reference
+// has the global `LOADER: NativeLoader`, loader/native.rs:11-15).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/snarkv_cuda.h"
+
+namespace snarkv {
+
+struct StageRecord {
+    const char* name;
+    cudaEvent_t start, stop;
+    int launches;
+};
+
+enum WsSlot : int {
+    WS_POINTS_MONT = 0,   // n x 64 B   Montgomery copy of CANONICAL points
+    WS_COUNTS,            // W x NB u32
+    WS_OFFSETS,           // W x NB u32
+    WS_CURSOR,            // W x NB u32
+    WS_SORTED,            // W x n  u32
+    WS_BUCKETS,           // W x NB x 128 B
+    WS_SEGPART,           // W x J  x 128 B
+    WS_WINSUM,            // W x 128 B
+    WS_STATUS,            // 4 B
+    WS_OUT,               // small outputs (affine 64 + jacobian 96)
+    WS_IO_A,              // staging for host-buffer entry points
+    WS_IO_B,
+    WS_IO_C,
+    WS_IO_D,
+    WS_BATCH_TERMS,       // batch-MSM per-term XYZZ
+    WS_PAIR_A,
+    WS_PAIR_B,
+    WS_SLOTS
+};
+
+}  // namespace snarkv
+
+struct snarkv_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // second stream for host->device copies that overlap kernels
+    cudaEvent_t copy_done = nullptr;
+    std::string err;
+    int window_bits = 0;
+    uint64_t launches = 0;
+    int sm_count = 148;
+
+    void* ws[snarkv::WS_SLOTS] = {};
+    size_t ws_bytes[snarkv::WS_SLOTS] = {};
+
+    bool profiling = false;
+    std::vector<snarkv::StageRecord> stages;       // records of the call in flight / last call
+    std::vector<cudaEvent_t> event_pool;
+    size_t event_next = 0;
+
+    // KZG deciding key (pairing.cu)
+    bool has_key = false;
+    void* d_key_coeffs = nullptr;   // 2 x NUM_COEFFS x 3 x Fq2 line coefficients (Montgomery)
+    int key_num_coeffs = 0;
+    uint8_t key_g1[64] = {};
+
+    int fail(int code, const char* what, cudaError_t ce = cudaSuccess) {
+        char buf[512];
+        if (ce != cudaSuccess) snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorName(ce), cudaGetErrorString(ce));
+        else snprintf(buf, sizeof buf, "%s", what);
+        err = buf;
+        return code;
+    }
+    // grow-only workspace slot; returns nullptr (and sets err) on allocation failure
+    void* wsget(int slot, size_t bytes) {
+        if (bytes == 0) bytes = 16;
+        if (ws_bytes[slot] >= bytes) return ws[slot];
+        if (ws[slot]) {
+            cudaStreamSynchronize(stream);
+            cudaFree(ws[slot]);
+            ws[slot] = nullptr;
+            ws_bytes[slot] = 0;
+        }
+        size_t want = bytes + bytes / 8;  // slack so a sweep of growing sizes does not reallocate every call
+        cudaError_t ce = cudaMalloc(&ws[slot], want);
+        if (ce != cudaSuccess) {
+            ce = cudaMalloc(&ws[slot], bytes);
+            want = bytes;
+        }
+        if (ce != cudaSuccess) {
+            fail(SNARKV_ERR_CUDA, "cudaMalloc(workspace)", ce);
+            ws[slot] = nullptr;
+            return nullptr;
+        }
+        ws_bytes[slot] = want;
+        return ws[slot];
+    }
+    cudaEvent_t next_event() {
+        if (event_next == event_pool.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            event_pool.push_back(e);
+        }
+        return event_pool[event_next++];
+    }
+    void profile_begin_call() {
+        stages.clear();
+        event_next = 0;
+    }
+};
+
+namespace snarkv {
+
+// RAII stage bracket: records start/stop events on the context's stream when profiling is on.
+struct Stage {
+    snarkv_ctx* c;
+    int idx = -1;
+    Stage(snarkv_ctx* ctx, const char* name) : c(ctx) {
+        if (!c->profiling) return;
+        StageRecord r{name, c->next_event(), c->next_event(), 0};
+        cudaEventRecord(r.start, c->stream);
+        c->stages.push_back(r);
+        idx = (int)c->stages.size() - 1;
+    }
+    void launched(int k = 1) {
+        c->launches += (uint64_t)k;
+        if (idx >= 0) c->stages[idx].launches += k;
+    }
+    ~Stage() {
+        if (idx >= 0) cudaEventRecord(c->stages[idx].stop, c->stream);
+    }
+};
+
+#define SNARKV_CUDA_TRY(ctx, expr)                                              \
+    do {                                                                         \
+        cudaError_t _ce = (expr);                                                \
+        if (_ce != cudaSuccess) return (ctx)->fail(SNARKV_ERR_CUDA, #expr, _ce); \
+    } while (0)
+#define SNARKV_LAUNCH_CHECK(ctx, name)                                             \
+    do {                                                                            \
+        cudaError_t _ce = cudaGetLastError();                                       \
+        if (_ce != cudaSuccess) return (ctx)->fail(SNARKV_ERR_CUDA, name, _ce);     \
+    } while (0)
+
+// internal entry points shared between translation units
+int msm_run_device(snarkv_ctx* ctx, const void* d_scalars, const void* d_points, size_t n, int scalar_format, int point_format,
+                   int out_format, int flags, void* d_out_affine, void* d_out_jacobian, void* d_status);
+int msm_run_host(snarkv_ctx* ctx, const uint8_t* scalars, const uint8_t* points, size_t n, int format, int flags, uint8_t* out);
+int msm_fold_partials_device(snarkv_ctx* ctx, const void* d_partials, size_t k, int format, void* d_out_affine);
+int msm_batch_device(snarkv_ctx* ctx, const void* d_scalars, const void* d_points, const void* d_offsets, size_t m, size_t total,
+                     int format, int flags, void* d_out_affine, void* d_status);
+int fr_powers_device(snarkv_ctx* ctx, const void* d_r, int format, size_t n, void* d_out_mont);
+int field_op_device(snarkv_ctx* ctx, int field, int op, const void* d_a, const void* d_b, size_t n, void* d_out);
+int synth_scalars_device(snarkv_ctx* ctx, uint64_t seed, uint64_t start, size_t n, int format, void* d_out);
+int synth_points_device(snarkv_ctx* ctx, uint64_t seed, uint64_t start, size_t n, int format, void* d_out);
+int kzg_set_key(snarkv_ctx* ctx, const uint8_t g1[64], const uint8_t g2[128], const uint8_t s_g2[128]);
+int kzg_decide_device(snarkv_ctx* ctx, const void* d_lhs, const void* d_rhs, size_t N, int format, void* d_accept, void* d_gt);
+void kzg_free_key(snarkv_ctx* ctx);
+
+}  // namespace snarkv

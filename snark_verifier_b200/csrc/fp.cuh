@@ -1,0 +1,168 @@
+// fp.cuh — BN254 base/scalar field arithmetic for sm_100a, 8 x 32-bit limbs in Montgomery form (R = 2^256).
+//
+// Replaces (on the device) halo2curves 0.6.0 `bn256::{Fq, Fr}`, the arithmetic that the reference reaches through
+// snark-verifier/src/util/arithmetic.rs:13-23 and calls from loader/native.rs:67-70 and pcs/kzg/decider.rs:74-78.
+// In-memory layout is identical to halo2curves' `[u64; 4]` little-endian Montgomery limbs, so a `&[G1Affine]` /
+// `&[Fr]` slice from the Rust side can be handed to the kernels byte-for-byte (SNARKV_MONTGOMERY format).
+//
+// The multiply/add/sub bodies are single inline-PTX blocks generated and CPU-verified by gen_field_ptx.py: two
+// interleaved 64-bit-column accumulators so that ptxas fuses every mad.lo.cc/madc.hi.cc pair into one
+// IMAD.WIDE.U32.X (≈170 IMAD-pipe issues per Montgomery multiplication; checked with cuobjdump -sass).
+#pragma once
+#include <cstdint>
+
+#include "fp_ptx.inc"
+
+namespace snarkv {
+
+enum Field : int { FQ = 0, FR = 1 };
+
+#define SNARKV_FP_OPS(r, a, b)                                                                                   \
+    : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]),          \
+      "=r"(r.v[7])                                                                                               \
+    : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),    \
+      "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7])
+
+template <Field F>
+struct alignas(16) Fp {
+    uint32_t v[8];
+};
+typedef Fp<FQ> Fq;
+typedef Fp<FR> Fr;
+
+// ---- constants (little-endian 32-bit limbs) -------------------------------------------------------------------------
+template <Field F> __host__ __device__ __forceinline__ constexpr uint32_t fp_mod_limb(int i);
+template <> __host__ __device__ __forceinline__ constexpr uint32_t fp_mod_limb<FQ>(int i) {
+    constexpr uint32_t m[8] = SNARKV_FQ_MOD_LIMBS;
+    return m[i];
+}
+template <> __host__ __device__ __forceinline__ constexpr uint32_t fp_mod_limb<FR>(int i) {
+    constexpr uint32_t m[8] = SNARKV_FR_MOD_LIMBS;
+    return m[i];
+}
+// R = 2^256 mod m  (Montgomery one)
+template <Field F> __host__ __device__ __forceinline__ constexpr uint32_t fp_one_limb(int i);
+template <> __host__ __device__ __forceinline__ constexpr uint32_t fp_one_limb<FQ>(int i) {
+    constexpr uint32_t m[8] = SNARKV_FQ_ONE_LIMBS;
+    return m[i];
+}
+template <> __host__ __device__ __forceinline__ constexpr uint32_t fp_one_limb<FR>(int i) {
+    constexpr uint32_t m[8] = SNARKV_FR_ONE_LIMBS;
+    return m[i];
+}
+// R^2 mod m
+template <Field F> __host__ __device__ __forceinline__ constexpr uint32_t fp_r2_limb(int i);
+template <> __host__ __device__ __forceinline__ constexpr uint32_t fp_r2_limb<FQ>(int i) {
+    constexpr uint32_t m[8] = SNARKV_FQ_R2_LIMBS;
+    return m[i];
+}
+template <> __host__ __device__ __forceinline__ constexpr uint32_t fp_r2_limb<FR>(int i) {
+    constexpr uint32_t m[8] = SNARKV_FR_R2_LIMBS;
+    return m[i];
+}
+
+template <Field F> __device__ __forceinline__ Fp<F> fp_zero() {
+    Fp<F> r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.v[i] = 0;
+    return r;
+}
+template <Field F> __device__ __forceinline__ Fp<F> fp_one() {
+    Fp<F> r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.v[i] = fp_one_limb<F>(i);
+    return r;
+}
+template <Field F> __device__ __forceinline__ Fp<F> fp_r2() {
+    Fp<F> r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.v[i] = fp_r2_limb<F>(i);
+    return r;
+}
+
+// ---- core ops -----------------------------------------------------------------------------------------------------------
+template <Field F> __device__ __forceinline__ Fp<F> fp_mul(const Fp<F>& a, const Fp<F>& b) {
+    Fp<F> r;
+    if constexpr (F == FQ) asm(SNARKV_PTX_FQ_MUL SNARKV_FP_OPS(r, a, b));
+    else asm(SNARKV_PTX_FR_MUL SNARKV_FP_OPS(r, a, b));
+    return r;
+}
+template <Field F> __device__ __forceinline__ Fp<F> fp_sqr(const Fp<F>& a) { return fp_mul(a, a); }
+template <Field F> __device__ __forceinline__ Fp<F> fp_add(const Fp<F>& a, const Fp<F>& b) {
+    Fp<F> r;
+    if constexpr (F == FQ) asm(SNARKV_PTX_FQ_ADD SNARKV_FP_OPS(r, a, b));
+    else asm(SNARKV_PTX_FR_ADD SNARKV_FP_OPS(r, a, b));
+    return r;
+}
+template <Field F> __device__ __forceinline__ Fp<F> fp_sub(const Fp<F>& a, const Fp<F>& b) {
+    Fp<F> r;
+    if constexpr (F == FQ) asm(SNARKV_PTX_FQ_SUB SNARKV_FP_OPS(r, a, b));
+    else asm(SNARKV_PTX_FR_SUB SNARKV_FP_OPS(r, a, b));
+    return r;
+}
+template <Field F> __device__ __forceinline__ Fp<F> fp_dbl(const Fp<F>& a) { return fp_add(a, a); }
+template <Field F> __device__ __forceinline__ Fp<F> fp_neg(const Fp<F>& a) { return fp_sub(fp_zero<F>(), a); }
+template <Field F> __device__ __forceinline__ bool fp_is_zero(const Fp<F>& a) {
+    return (a.v[0] | a.v[1] | a.v[2] | a.v[3] | a.v[4] | a.v[5] | a.v[6] | a.v[7]) == 0;
+}
+template <Field F> __device__ __forceinline__ bool fp_eq(const Fp<F>& a, const Fp<F>& b) {
+    uint32_t d = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d |= a.v[i] ^ b.v[i];
+    return d == 0;
+}
+// canonical integer (< m) -> Montgomery form, and back
+template <Field F> __device__ __forceinline__ Fp<F> fp_to_mont(const Fp<F>& a) { return fp_mul(a, fp_r2<F>()); }
+template <Field F> __device__ __forceinline__ Fp<F> fp_from_mont(const Fp<F>& a) {
+    Fp<F> one = fp_zero<F>();
+    one.v[0] = 1;
+    return fp_mul(a, one);
+}
+// true iff the raw 256-bit value is a canonical residue (< m) — `PrimeField::from_repr` acceptance test
+template <Field F> __device__ __forceinline__ bool fp_is_canonical(const Fp<F>& a) {
+#pragma unroll
+    for (int i = 7; i >= 0; --i) {
+        if (a.v[i] < fp_mod_limb<F>(i)) return true;
+        if (a.v[i] > fp_mod_limb<F>(i)) return false;
+    }
+    return false;
+}
+
+// a^(m-2) by square-and-multiply over the constant exponent (used once per result for to_affine; not on hot loops)
+template <Field F> __device__ __noinline__ Fp<F> fp_inv(const Fp<F>& a) {
+    Fp<F> r = fp_one<F>();
+    // exponent m - 2, MSB first.  m is odd and m-2 only changes limb 0 (no borrow: low limbs are ...47 / ...01 -> need care)
+    uint32_t e[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) e[i] = fp_mod_limb<F>(i);
+    // subtract 2 with borrow
+    uint32_t borrow = 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        uint32_t t = e[i] - borrow;
+        borrow = (e[i] < borrow) ? 1u : 0u;
+        e[i] = t;
+    }
+    for (int i = 253; i >= 0; --i) {   // both moduli are 254-bit
+        r = fp_sqr(r);
+        if ((e[i >> 5] >> (i & 31)) & 1u) r = fp_mul(r, a);
+    }
+    return r;
+}
+
+// ---- 128-bit vectorised global memory access ----------------------------------------------------------------------------
+template <Field F> __device__ __forceinline__ Fp<F> fp_load(const void* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 lo = __ldg(q), hi = __ldg(q + 1);
+    Fp<F> r;
+    r.v[0] = lo.x; r.v[1] = lo.y; r.v[2] = lo.z; r.v[3] = lo.w;
+    r.v[4] = hi.x; r.v[5] = hi.y; r.v[6] = hi.z; r.v[7] = hi.w;
+    return r;
+}
+template <Field F> __device__ __forceinline__ void fp_store(void* p, const Fp<F>& a) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]);
+    q[1] = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]);
+}
+
+}  // namespace snarkv

@@ -1,0 +1,210 @@
+// g1.cuh — BN254 G1 (y^2 = x^3 + 3 over Fq, a = 0) point arithmetic for the MSM kernels.
+//
+// Device-side replacement for halo2curves 0.6.0 `bn256::{G1, G1Affine}` as used at the reference's call sites
+// snark-verifier/src/loader/native.rs:67-70 (`*base * scalar`, `acc + value`, `.to_affine()`) and
+// util/msm.rs:236-256,286,298-302 (bucket `+=`, `double`, running sums).
+//
+// Accumulators use extended Jacobian "XYZZ" coordinates (x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2): the mixed addition
+// costs 8M + 2S = 10 Montgomery multiplications versus 11 for Jacobian madd-2007-bl, and needs no field halving.
+// Identity: ZZ == 0.  Affine identity: (0, 0) — halo2curves' encoding.  Results are canonical after to_affine, so the
+// coordinate system is invisible at the C-ABI boundary.
+#pragma once
+#include "fp.cuh"
+
+namespace snarkv {
+
+struct alignas(16) G1Affine {
+    Fq x, y;
+};
+struct alignas(16) G1Xyzz {
+    Fq x, y, zz, zzz;
+};
+struct alignas(16) G1Jac {  // halo2curves' G1 layout: (X, Y, Z) with x = X/Z^2, y = Y/Z^3; identity Z == 0
+    Fq x, y, z;
+};
+
+__device__ __forceinline__ bool g1_affine_is_identity(const G1Affine& p) { return fp_is_zero(p.x) && fp_is_zero(p.y); }
+__device__ __forceinline__ bool xyzz_is_identity(const G1Xyzz& p) { return fp_is_zero(p.zz); }
+
+__device__ __forceinline__ G1Xyzz xyzz_identity() {
+    G1Xyzz r;
+    r.x = fp_zero<FQ>(); r.y = fp_one<FQ>(); r.zz = fp_zero<FQ>(); r.zzz = fp_zero<FQ>();
+    return r;
+}
+__device__ __forceinline__ G1Xyzz xyzz_from_affine(const G1Affine& p) {
+    if (g1_affine_is_identity(p)) return xyzz_identity();
+    G1Xyzz r;
+    r.x = p.x; r.y = p.y; r.zz = fp_one<FQ>(); r.zzz = fp_one<FQ>();
+    return r;
+}
+
+__device__ __forceinline__ G1Affine g1_affine_load(const void* base, size_t idx) {
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(base) + idx * 64;
+    G1Affine r;
+    r.x = fp_load<FQ>(p);
+    r.y = fp_load<FQ>(p + 32);
+    return r;
+}
+__device__ __forceinline__ void g1_affine_store(void* base, size_t idx, const G1Affine& a) {
+    uint8_t* p = reinterpret_cast<uint8_t*>(base) + idx * 64;
+    fp_store<FQ>(p, a.x);
+    fp_store<FQ>(p + 32, a.y);
+}
+__device__ __forceinline__ G1Xyzz xyzz_load(const void* base, size_t idx) {
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(base) + idx * 128;
+    G1Xyzz r;
+    r.x = fp_load<FQ>(p); r.y = fp_load<FQ>(p + 32); r.zz = fp_load<FQ>(p + 64); r.zzz = fp_load<FQ>(p + 96);
+    return r;
+}
+__device__ __forceinline__ void xyzz_store(void* base, size_t idx, const G1Xyzz& a) {
+    uint8_t* p = reinterpret_cast<uint8_t*>(base) + idx * 128;
+    fp_store<FQ>(p, a.x); fp_store<FQ>(p + 32, a.y); fp_store<FQ>(p + 64, a.zz); fp_store<FQ>(p + 96, a.zzz);
+}
+
+// 2 * (x, y) for an affine, non-identity point (mdbl-2008-s-1 with a = 0)
+static __device__ __noinline__ G1Xyzz xyzz_dbl_affine(const Fq& x, const Fq& y) {
+    G1Xyzz r;
+    if (fp_is_zero(y)) return xyzz_identity();  // order-2 points do not exist on BN254 G1; kept for totality
+    Fq u = fp_dbl(y);
+    Fq v = fp_sqr(u);
+    Fq w = fp_mul(u, v);
+    Fq s = fp_mul(x, v);
+    Fq xx = fp_sqr(x);
+    Fq m = fp_add(fp_dbl(xx), xx);
+    r.x = fp_sub(fp_sqr(m), fp_dbl(s));
+    r.y = fp_sub(fp_mul(m, fp_sub(s, r.x)), fp_mul(w, y));
+    r.zz = v;
+    r.zzz = w;
+    return r;
+}
+
+// 2 * P (dbl-2008-s-1, a = 0): 6M + 3S
+__device__ __forceinline__ G1Xyzz xyzz_dbl(const G1Xyzz& p) {
+    if (xyzz_is_identity(p)) return p;
+    G1Xyzz r;
+    Fq u = fp_dbl(p.y);
+    Fq v = fp_sqr(u);
+    Fq w = fp_mul(u, v);
+    Fq s = fp_mul(p.x, v);
+    Fq xx = fp_sqr(p.x);
+    Fq m = fp_add(fp_dbl(xx), xx);
+    r.x = fp_sub(fp_sqr(m), fp_dbl(s));
+    r.y = fp_sub(fp_mul(m, fp_sub(s, r.x)), fp_mul(w, p.y));
+    r.zz = fp_mul(v, p.zz);
+    r.zzz = fp_mul(w, p.zzz);
+    return r;
+}
+
+// acc += (x2, y2), (x2, y2) affine and NOT the identity (madd-2008-s): 8M + 2S on the common path.
+// Exceptional cases (empty accumulator, equal points, opposite points) are handled exactly.
+__device__ __forceinline__ void xyzz_madd(G1Xyzz& acc, const Fq& x2, const Fq& y2) {
+    if (xyzz_is_identity(acc)) {
+        acc.x = x2; acc.y = y2; acc.zz = fp_one<FQ>(); acc.zzz = fp_one<FQ>();
+        return;
+    }
+    Fq u2 = fp_mul(x2, acc.zz);
+    Fq s2 = fp_mul(y2, acc.zzz);
+    Fq p = fp_sub(u2, acc.x);
+    Fq r = fp_sub(s2, acc.y);
+    if (fp_is_zero(p)) {
+        if (fp_is_zero(r)) acc = xyzz_dbl_affine(x2, y2);
+        else acc = xyzz_identity();
+        return;
+    }
+    Fq pp = fp_sqr(p);
+    Fq ppp = fp_mul(p, pp);
+    Fq q = fp_mul(acc.x, pp);
+    Fq x3 = fp_sub(fp_sub(fp_sqr(r), ppp), fp_dbl(q));
+    acc.y = fp_sub(fp_mul(r, fp_sub(q, x3)), fp_mul(acc.y, ppp));
+    acc.x = x3;
+    acc.zz = fp_mul(acc.zz, pp);
+    acc.zzz = fp_mul(acc.zzz, ppp);
+}
+__device__ __forceinline__ void xyzz_madd(G1Xyzz& acc, const G1Affine& p) {
+    if (g1_affine_is_identity(p)) return;
+    xyzz_madd(acc, p.x, p.y);
+}
+
+// a + b, both XYZZ (add-2008-s): 12M + 2S
+__device__ __forceinline__ G1Xyzz xyzz_add(const G1Xyzz& a, const G1Xyzz& b) {
+    if (xyzz_is_identity(a)) return b;
+    if (xyzz_is_identity(b)) return a;
+    Fq u1 = fp_mul(a.x, b.zz);
+    Fq u2 = fp_mul(b.x, a.zz);
+    Fq s1 = fp_mul(a.y, b.zzz);
+    Fq s2 = fp_mul(b.y, a.zzz);
+    Fq p = fp_sub(u2, u1);
+    Fq r = fp_sub(s2, s1);
+    if (fp_is_zero(p)) {
+        if (fp_is_zero(r)) return xyzz_dbl(a);
+        return xyzz_identity();
+    }
+    Fq pp = fp_sqr(p);
+    Fq ppp = fp_mul(p, pp);
+    Fq q = fp_mul(u1, pp);
+    G1Xyzz o;
+    o.x = fp_sub(fp_sub(fp_sqr(r), ppp), fp_dbl(q));
+    o.y = fp_sub(fp_mul(r, fp_sub(q, o.x)), fp_mul(s1, ppp));
+    o.zz = fp_mul(fp_mul(a.zz, b.zz), pp);
+    o.zzz = fp_mul(fp_mul(a.zzz, b.zzz), ppp);
+    return o;
+}
+
+// XYZZ -> Jacobian without inversion: Z = ZZZ  =>  Z^2 = ZZ^3, Z^3 = ZZZ^3  =>  (X ZZ^2, Y ZZZ^2, ZZZ)
+__device__ __forceinline__ G1Jac xyzz_to_jacobian(const G1Xyzz& p) {
+    G1Jac r;
+    if (xyzz_is_identity(p)) {
+        r.x = fp_zero<FQ>(); r.y = fp_one<FQ>(); r.z = fp_zero<FQ>();
+        return r;
+    }
+    r.x = fp_mul(p.x, fp_sqr(p.zz));
+    r.y = fp_mul(p.y, fp_sqr(p.zzz));
+    r.z = p.zzz;
+    return r;
+}
+__device__ __forceinline__ G1Xyzz jacobian_to_xyzz(const G1Jac& p) {
+    if (fp_is_zero(p.z)) return xyzz_identity();
+    G1Xyzz r;
+    r.x = p.x; r.y = p.y;
+    r.zz = fp_sqr(p.z);
+    r.zzz = fp_mul(r.zz, p.z);
+    return r;
+}
+// `Curve::to_affine` (native.rs:70): one inversion.  (0,0) for the identity.
+__device__ __forceinline__ G1Affine xyzz_to_affine(const G1Xyzz& p) {
+    G1Affine r;
+    if (xyzz_is_identity(p)) {
+        r.x = fp_zero<FQ>(); r.y = fp_zero<FQ>();
+        return r;
+    }
+    // 1/ZZZ gives both: 1/ZZ = ZZ^2 / ZZZ^2 ... simpler: inv(ZZ * ZZZ) then split
+    Fq t = fp_inv(fp_mul(p.zz, p.zzz));
+    Fq izz = fp_mul(t, p.zzz);
+    Fq izzz = fp_mul(t, p.zz);
+    r.x = fp_mul(p.x, izz);
+    r.y = fp_mul(p.y, izzz);
+    return r;
+}
+
+// y^2 == x^3 + 3 (Montgomery-form inputs); the identity (0,0) is accepted — `CurveAffine::from_xy` semantics plus
+// halo2curves' identity encoding
+__device__ __forceinline__ bool g1_affine_is_on_curve(const G1Affine& p) {
+    if (g1_affine_is_identity(p)) return true;
+    Fq three = fp_one<FQ>();
+    three = fp_add(fp_dbl(three), three);
+    Fq rhs = fp_add(fp_mul(fp_sqr(p.x), p.x), three);
+    return fp_eq(fp_sqr(p.y), rhs);
+}
+
+// k * P for a small unsigned k (bucket-segment weights), double-and-add MSB first
+static __device__ __noinline__ G1Xyzz xyzz_mul_small(const G1Xyzz& p, uint32_t k) {
+    G1Xyzz acc = xyzz_identity();
+    if (k == 0) return acc;
+    for (int i = 31 - __clz(k); i >= 0; --i) {
+        acc = xyzz_dbl(acc);
+        if ((k >> i) & 1u) acc = xyzz_add(acc, p);
+    }
+    return acc;
+}
+
+}  // namespace snarkv

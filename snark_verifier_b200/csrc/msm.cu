@@ -1,0 +1,599 @@
+// msm.cu — BN254 G1 multi-scalar multiplication on sm_100a: a signed-digit Pippenger pipeline.
+//
+// Replaces, behind `snarkv_g1_msm*` (include/snarkv_cuda.h), the reference's
+//   NativeLoader::multi_scalar_multiplication          snark-verifier/src/loader/native.rs:61-71   (semantics: affine sum)
+//   util::msm::multi_scalar_multiplication{,_serial}   snark-verifier/src/util/msm.rs:259-343      (bucket method)
+// The reference's bucket method uses unsigned c-bit windows with c = ceil(ln n) + 2 and 2^c - 1 buckets per window,
+// processed window by window on one core (or one chunk per rayon thread).  This is a different program with the same
+// output: all windows at once, signed digits (2^(c-1) buckets per window), and a counting sort so that each bucket's
+// points are contiguous:
+//
+//   K1 digits_count       scalar -> W signed c-bit digits; histogram[w][|d|]                    (HBM-bound, 32 B/term read)
+//   K2 scan               per-window exclusive prefix sum of the histogram                      (tiny)
+//   K3 digits_scatter     recompute digits; sorted[w][pos] = term index | sign                  (HBM/L2-atomic bound)
+//   K4 bucket_accumulate  one thread per (window, bucket): XYZZ += gathered affine points       (IMAD-pipe bound: the MSM)
+//   K5 bucket_reduce      per window  sum_b b * B_b  by segment running sums                    (small)
+//   K6 window_sum / final Horner over windows with c doublings each, to_affine                  (latency, 1 thread)
+//
+// HBM layout: scalars n x 32 B and affine points n x 64 B exactly as the caller's slices (halo2curves layout), plus
+// workspace: histogram/offset/cursor W x NB x 4 B each, sorted indices W x n x 4 B, bucket sums W x NB x 128 B (XYZZ).
+#include "ctx.hpp"
+#include "g1.cuh"
+
+namespace snarkv {
+
+struct MsmPlan {
+    uint32_t c;    // window bits
+    uint32_t W;    // windows = ceil(255 / c): the top window absorbs the last signed-digit carry (scalars < 2^254)
+    uint32_t NB;   // buckets per window = 2^(c-1), bucket values 1..NB
+    uint32_t seg;  // buckets per reduce thread
+    uint32_t J;    // segments per window
+};
+
+static int choose_window_bits(size_t n) {
+    // few, long buckets keep the one-thread-per-bucket accumulate kernel balanced; enough buckets keep it occupied.
+    if (n < (1u << 6)) return 4;
+    if (n < (1u << 8)) return 5;
+    if (n < (1u << 10)) return 7;
+    if (n < (1u << 12)) return 9;
+    if (n < (1u << 14)) return 10;
+    if (n < (1u << 16)) return 11;
+    if (n < (1u << 18)) return 12;
+    if (n < (1u << 20)) return 13;
+    if (n < (1u << 22)) return 14;
+    if (n < (1u << 24)) return 15;
+    return 16;
+}
+
+static MsmPlan make_plan(size_t n, int c_override) {
+    MsmPlan p;
+    int c = c_override > 0 ? c_override : choose_window_bits(n);
+    if (c < 2) c = 2;
+    if (c > 22) c = 22;
+    p.c = (uint32_t)c;
+    p.W = (255 + p.c - 1) / p.c;
+    p.NB = 1u << (p.c - 1);
+    p.seg = p.NB < 16 ? p.NB : 16;
+    p.J = (p.NB + p.seg - 1) / p.seg;
+    return p;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// input preparation / validation
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void k_points_prepare(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, size_t n, int format, int check,
+                                 int* __restrict__ status) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        G1Affine p = g1_affine_load(in, i);
+        if (format == SNARKV_CANONICAL) {
+            if (check && (!fp_is_canonical(p.x) || !fp_is_canonical(p.y))) atomicCAS(status, 0, SNARKV_ERR_BAD_POINT);
+            p.x = fp_to_mont(p.x);
+            p.y = fp_to_mont(p.y);
+        }
+        if (check && !g1_affine_is_on_curve(p)) atomicCAS(status, 0, SNARKV_ERR_BAD_POINT);
+        if (out) g1_affine_store(out, i, p);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K1 / K3: signed-digit decomposition.  `windowed_scalar` of util/msm.rs:271-281 extracts unsigned c-bit digits from the
+// canonical little-endian repr; here each digit d in [0, 2^c) plus the carry from below is mapped to (-2^(c-1), 2^(c-1)].
+// ---------------------------------------------------------------------------------------------------------------------
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) k_digits(const uint8_t* __restrict__ scalars, size_t n, int format, int check, uint32_t c,
+                                                uint32_t W, uint32_t NB, uint32_t* __restrict__ counters,
+                                                uint32_t* __restrict__ sorted, int* __restrict__ status) {
+    const uint32_t mask = (1u << c) - 1u;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        Fr s = fp_load<FR>(scalars + i * 32);
+        if (format == SNARKV_MONTGOMERY) s = fp_from_mont(s);
+        else if (check && !SCATTER && !fp_is_canonical(s)) atomicCAS(status, 0, SNARKV_ERR_BAD_SCALAR);
+        uint32_t carry = 0;
+        for (uint32_t w = 0; w < W; ++w) {
+            uint32_t d = (s.v[0] & mask) + carry;
+            // s >>= c  (c < 32)
+#pragma unroll
+            for (int j = 0; j < 7; ++j) s.v[j] = __funnelshift_r(s.v[j], s.v[j + 1], c);
+            s.v[7] >>= c;
+            uint32_t neg = 0;
+            if (d > NB) {
+                d = (mask + 1u) - d;
+                neg = 1u;
+                carry = 1u;
+            } else carry = 0u;
+            if (d != 0) {
+                uint32_t slot = w * NB + (d - 1u);
+                if (!SCATTER) atomicAdd(&counters[slot], 1u);
+                else {
+                    uint32_t pos = atomicAdd(&counters[slot], 1u);
+                    sorted[(size_t)w * n + pos] = (uint32_t)i | (neg << 31);
+                }
+            }
+        }
+    }
+}
+
+// K2: exclusive scan of each window's histogram; one block per window.
+__global__ void __launch_bounds__(1024) k_scan(const uint32_t* __restrict__ counts, uint32_t* __restrict__ offsets,
+                                               uint32_t* __restrict__ cursor, uint32_t NB) {
+    __shared__ uint32_t warp_tot[32];
+    const uint32_t w = blockIdx.x, t = threadIdx.x, T = blockDim.x;
+    const uint32_t per = (NB + T - 1) / T;
+    const uint32_t lo = min(t * per, NB), hi = min(lo + per, NB);
+    const uint32_t* cw = counts + (size_t)w * NB;
+    uint32_t sum = 0;
+    for (uint32_t k = lo; k < hi; ++k) sum += cw[k];
+    // block-wide exclusive scan of `sum`
+    uint32_t incl = sum;
+    const uint32_t lane = t & 31, wid = t >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += v;
+    }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t v = lane < (T >> 5) ? warp_tot[lane] : 0;
+        uint32_t iv = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t u = __shfl_up_sync(0xffffffffu, iv, o);
+            if (lane >= (uint32_t)o) iv += u;
+        }
+        warp_tot[lane] = iv - v;
+    }
+    __syncthreads();
+    uint32_t running = warp_tot[wid] + incl - sum;
+    for (uint32_t k = lo; k < hi; ++k) {
+        offsets[(size_t)w * NB + k] = running;
+        cursor[(size_t)w * NB + k] = running;
+        running += cw[k];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K4: bucket accumulation — the multi-scalar multiplication proper.  `buckets[scalar - 1].add_assign(base)` of
+// util/msm.rs:291-296, with Bucket::{None, Affine, Projective} (util/msm.rs:228-246) collapsed into the XYZZ identity test.
+// One thread per (window, bucket); the next point is fetched (4 x 128-bit loads) while the current addition runs.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_bucket_accumulate(const uint8_t* __restrict__ points, const uint32_t* __restrict__ sorted,
+                                                           const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts,
+                                                           size_t n, uint32_t NB, uint32_t total, uint8_t* __restrict__ buckets) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= total) return;
+    const uint32_t w = tid / NB;
+    const uint32_t cnt = counts[tid];
+    const uint32_t* list = sorted + (size_t)w * n + offsets[tid];
+    G1Xyzz acc = xyzz_identity();
+    if (cnt > 0) {
+        uint32_t e = list[0];
+        G1Affine nxt = g1_affine_load(points, e & 0x7fffffffu);
+        for (uint32_t k = 0; k < cnt; ++k) {
+            G1Affine cur = nxt;
+            const uint32_t neg = e >> 31;
+            if (k + 1 < cnt) {
+                e = list[k + 1];
+                nxt = g1_affine_load(points, e & 0x7fffffffu);
+            }
+            if (g1_affine_is_identity(cur)) continue;
+            if (neg) cur.y = fp_neg(cur.y);
+            xyzz_madd(acc, cur.x, cur.y);
+        }
+    }
+    xyzz_store(buckets, tid, acc);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K5: per-window bucket reduction  sum_{b=1..NB} b * B_b — the running-sum loop of util/msm.rs:298-302, cut into
+// segments of `seg` buckets: a segment covering array indices [lo, hi) contributes
+//   sum (idx - lo + 1) B_idx  (running sum)  +  lo * sum B_idx  (small scalar multiple).
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_bucket_reduce(const uint8_t* __restrict__ buckets, uint32_t NB, uint32_t seg, uint32_t J,
+                                                       uint8_t* __restrict__ segpart) {
+    const uint32_t w = blockIdx.y;
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= J) return;
+    const uint32_t lo = j * seg, hi = min(lo + seg, NB);
+    G1Xyzz running = xyzz_identity(), acc = xyzz_identity();
+    for (uint32_t idx = hi; idx-- > lo;) {
+        G1Xyzz b = xyzz_load(buckets, (size_t)w * NB + idx);
+        running = xyzz_add(running, b);
+        acc = xyzz_add(acc, running);
+    }
+    if (lo > 0) acc = xyzz_add(acc, xyzz_mul_small(running, lo));
+    xyzz_store(segpart, (size_t)w * J + j, acc);
+}
+
+// K6a: sum the J segment results of one window; one block per window, shared-memory tree.
+__global__ void __launch_bounds__(128) k_window_sum(const uint8_t* __restrict__ segpart, uint32_t J, uint8_t* __restrict__ winsum) {
+    __shared__ G1Xyzz sm[128];
+    const uint32_t w = blockIdx.x, t = threadIdx.x;
+    G1Xyzz acc = xyzz_identity();
+    for (uint32_t j = t; j < J; j += blockDim.x) acc = xyzz_add(acc, xyzz_load(segpart, (size_t)w * J + j));
+    sm[t] = acc;
+    __syncthreads();
+    for (uint32_t s = blockDim.x >> 1; s > 0; s >>= 1) {
+        if (t < s) sm[t] = xyzz_add(sm[t], sm[t + s]);
+        __syncthreads();
+    }
+    if (t == 0) xyzz_store(winsum, w, sm[0]);
+}
+
+__device__ __forceinline__ void store_affine_fmt(void* out, const G1Affine& a, int format) {
+    G1Affine o = a;
+    if (format == SNARKV_CANONICAL) {
+        o.x = fp_from_mont(o.x);
+        o.y = fp_from_mont(o.y);
+    }
+    g1_affine_store(out, 0, o);
+}
+__device__ __forceinline__ void store_jacobian(void* out, const G1Jac& j) {
+    uint8_t* p = reinterpret_cast<uint8_t*>(out);
+    fp_store<FQ>(p, j.x);
+    fp_store<FQ>(p + 32, j.y);
+    fp_store<FQ>(p + 64, j.z);
+}
+
+// K6b: result = sum_w 2^(c w) * winsum[w]  (the `result.double()` x window_size loop of util/msm.rs:285-287), then the
+// caller's `.to_affine()` (native.rs:70).
+__global__ void k_msm_final(const uint8_t* __restrict__ winsum, uint32_t W, uint32_t c, int format, void* out_affine,
+                            void* out_jacobian) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    G1Xyzz acc = xyzz_load(winsum, W - 1);
+    for (uint32_t w = W - 1; w-- > 0;) {
+        for (uint32_t k = 0; k < c; ++k) acc = xyzz_dbl(acc);
+        acc = xyzz_add(acc, xyzz_load(winsum, w));
+    }
+    if (out_jacobian) store_jacobian(out_jacobian, xyzz_to_jacobian(acc));
+    if (out_affine) store_affine_fmt(out_affine, xyzz_to_affine(acc), format);
+}
+
+// fold of per-GPU Jacobian partials (util/msm.rs:333-335) + to_affine
+__global__ void k_fold_partials(const uint8_t* __restrict__ partials, uint32_t k, int format, void* out_affine) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    G1Xyzz acc = xyzz_identity();
+    for (uint32_t i = 0; i < k; ++i) {
+        G1Jac j;
+        const uint8_t* p = partials + (size_t)i * 96;
+        j.x = fp_load<FQ>(p); j.y = fp_load<FQ>(p + 32); j.z = fp_load<FQ>(p + 64);
+        acc = xyzz_add(acc, jacobian_to_xyzz(j));
+    }
+    store_affine_fmt(out_affine, xyzz_to_affine(acc), format);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host orchestration
+// ---------------------------------------------------------------------------------------------------------------------
+// Phase 1 needs only the scalars (K1-K3); phase 2 needs the points (K4-K6).  The host-buffer entry point issues the
+// points' host->device copy between the two so that it overlaps the sort.
+struct MsmWork {
+    MsmPlan pl;
+    int* status;
+    uint32_t *counts, *offsets, *cursor, *sorted;
+    uint8_t *buckets, *segpart, *winsum;
+};
+
+static int msm_alloc(snarkv_ctx* ctx, size_t n, void* d_status, MsmWork& wk) {
+    if (n == 0) return ctx->fail(SNARKV_ERR_EMPTY, "multi_scalar_multiplication on an empty slice");
+    if (n >= (1ull << 31)) return ctx->fail(SNARKV_ERR_USAGE, "n must be < 2^31");
+    wk.pl = make_plan(n, ctx->window_bits);
+    const MsmPlan& pl = wk.pl;
+    const size_t nbk = (size_t)pl.W * pl.NB;
+    wk.status = (int*)d_status;
+    if (!wk.status) wk.status = (int*)ctx->wsget(WS_STATUS, 4);
+    wk.counts = (uint32_t*)ctx->wsget(WS_COUNTS, nbk * 4);
+    wk.offsets = (uint32_t*)ctx->wsget(WS_OFFSETS, nbk * 4);
+    wk.cursor = (uint32_t*)ctx->wsget(WS_CURSOR, nbk * 4);
+    wk.sorted = (uint32_t*)ctx->wsget(WS_SORTED, (size_t)pl.W * n * 4);
+    wk.buckets = (uint8_t*)ctx->wsget(WS_BUCKETS, nbk * 128);
+    wk.segpart = (uint8_t*)ctx->wsget(WS_SEGPART, (size_t)pl.W * pl.J * 128);
+    wk.winsum = (uint8_t*)ctx->wsget(WS_WINSUM, (size_t)pl.W * 128);
+    if (!wk.status || !wk.counts || !wk.offsets || !wk.cursor || !wk.sorted || !wk.buckets || !wk.segpart || !wk.winsum)
+        return SNARKV_ERR_CUDA;
+    return SNARKV_OK;
+}
+
+static int msm_sort_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* d_scalars, size_t n, int scalar_format, int check) {
+    const MsmPlan& pl = wk.pl;
+    cudaStream_t st = ctx->stream;
+    const size_t nbk = (size_t)pl.W * pl.NB;
+    const size_t want = (n + 255) / 256, cap = (size_t)ctx->sm_count * 8;
+    const int dig_blocks = (int)(want < cap ? want : cap);
+    {
+        Stage sg(ctx, "msm_digits_count");
+        SNARKV_CUDA_TRY(ctx, cudaMemsetAsync(wk.status, 0, 4, st));
+        SNARKV_CUDA_TRY(ctx, cudaMemsetAsync(wk.counts, 0, nbk * 4, st));
+        k_digits<false><<<dig_blocks, 256, 0, st>>>((const uint8_t*)d_scalars, n, scalar_format, check, pl.c, pl.W, pl.NB, wk.counts,
+                                                    nullptr, wk.status);
+        SNARKV_LAUNCH_CHECK(ctx, "k_digits<count>");
+        sg.launched();
+    }
+    {
+        Stage sg(ctx, "msm_scan");
+        k_scan<<<pl.W, 1024, 0, st>>>(wk.counts, wk.offsets, wk.cursor, pl.NB);
+        SNARKV_LAUNCH_CHECK(ctx, "k_scan");
+        sg.launched();
+    }
+    {
+        Stage sg(ctx, "msm_digits_scatter");
+        k_digits<true><<<dig_blocks, 256, 0, st>>>((const uint8_t*)d_scalars, n, scalar_format, check, pl.c, pl.W, pl.NB, wk.cursor,
+                                                   wk.sorted, wk.status);
+        SNARKV_LAUNCH_CHECK(ctx, "k_digits<scatter>");
+        sg.launched();
+    }
+    return SNARKV_OK;
+}
+
+static int msm_point_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* d_points, size_t n, int point_format, int out_format,
+                           int check, void* d_out_affine, void* d_out_jacobian) {
+    const MsmPlan& pl = wk.pl;
+    cudaStream_t st = ctx->stream;
+    const size_t nbk = (size_t)pl.W * pl.NB;
+    const uint8_t* points = (const uint8_t*)d_points;
+    if (point_format == SNARKV_CANONICAL || check) {
+        Stage sg(ctx, "msm_points_prepare");
+        uint8_t* conv = nullptr;
+        if (point_format == SNARKV_CANONICAL) {
+            conv = (uint8_t*)ctx->wsget(WS_POINTS_MONT, n * 64);
+            if (!conv) return SNARKV_ERR_CUDA;
+        }
+        const size_t want = (n + 255) / 256, cap = (size_t)ctx->sm_count * 8;
+        k_points_prepare<<<(int)(want < cap ? want : cap), 256, 0, st>>>(points, conv, n, point_format, check, wk.status);
+        SNARKV_LAUNCH_CHECK(ctx, "k_points_prepare");
+        sg.launched();
+        if (conv) points = conv;
+    }
+    {
+        Stage sg(ctx, "msm_bucket_accumulate");
+        const uint32_t total = (uint32_t)nbk;
+        k_bucket_accumulate<<<(total + 127) / 128, 128, 0, st>>>(points, wk.sorted, wk.offsets, wk.counts, n, pl.NB, total, wk.buckets);
+        SNARKV_LAUNCH_CHECK(ctx, "k_bucket_accumulate");
+        sg.launched();
+    }
+    {
+        Stage sg(ctx, "msm_bucket_reduce");
+        dim3 grid((pl.J + 127) / 128, pl.W);
+        k_bucket_reduce<<<grid, 128, 0, st>>>(wk.buckets, pl.NB, pl.seg, pl.J, wk.segpart);
+        SNARKV_LAUNCH_CHECK(ctx, "k_bucket_reduce");
+        sg.launched();
+    }
+    {
+        Stage sg(ctx, "msm_window_combine");
+        k_window_sum<<<pl.W, 128, 0, st>>>(wk.segpart, pl.J, wk.winsum);
+        SNARKV_LAUNCH_CHECK(ctx, "k_window_sum");
+        sg.launched();
+        k_msm_final<<<1, 32, 0, st>>>(wk.winsum, pl.W, pl.c, out_format, d_out_affine, d_out_jacobian);
+        SNARKV_LAUNCH_CHECK(ctx, "k_msm_final");
+        sg.launched();
+    }
+    return SNARKV_OK;
+}
+
+int msm_run_device(snarkv_ctx* ctx, const void* d_scalars, const void* d_points, size_t n, int scalar_format, int point_format,
+                   int out_format, int flags, void* d_out_affine, void* d_out_jacobian, void* d_status) {
+    const int check = (flags & SNARKV_CHECK_INPUTS) ? 1 : 0;
+    MsmWork wk;
+    int rc = msm_alloc(ctx, n, d_status, wk);
+    if (rc) return rc;
+    rc = msm_sort_phase(ctx, wk, d_scalars, n, scalar_format, check);
+    if (rc) return rc;
+    return msm_point_phase(ctx, wk, d_points, n, point_format, out_format, check, d_out_affine, d_out_jacobian);
+}
+
+// snarkv_g1_msm: host slices in, 64-byte affine result out.  Scalars go first; the (2x larger) point copy is issued after
+// the sort kernels are queued so that the copy engine and the SMs overlap.
+int msm_run_host(snarkv_ctx* ctx, const uint8_t* scalars, const uint8_t* points, size_t n, int format, int flags, uint8_t* out) {
+    const int check = (flags & SNARKV_CHECK_INPUTS) ? 1 : 0;
+    MsmWork wk;
+    int rc = msm_alloc(ctx, n, nullptr, wk);
+    if (rc) return rc;
+    uint8_t* d_s = (uint8_t*)ctx->wsget(WS_IO_A, n * 32);
+    uint8_t* d_p = (uint8_t*)ctx->wsget(WS_IO_B, n * 64);
+    uint8_t* d_o = (uint8_t*)ctx->wsget(WS_OUT, 256);
+    if (!d_s || !d_p || !d_o) return SNARKV_ERR_CUDA;
+    cudaStream_t st = ctx->stream;
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_s, scalars, n * 32, cudaMemcpyHostToDevice, st));
+    rc = msm_sort_phase(ctx, wk, d_s, n, format, check);
+    if (rc) return rc;
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_p, points, n * 64, cudaMemcpyHostToDevice, ctx->copy_stream));
+    SNARKV_CUDA_TRY(ctx, cudaEventRecord(ctx->copy_done, ctx->copy_stream));
+    SNARKV_CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->copy_done, 0));
+    rc = msm_point_phase(ctx, wk, d_p, n, format, format, check, d_o, nullptr);
+    if (rc) return rc;
+    int status = 0;
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(out, d_o, 64, cudaMemcpyDeviceToHost, st));
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(&status, wk.status, 4, cudaMemcpyDeviceToHost, st));
+    SNARKV_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    if (status != 0) return ctx->fail(status, status == SNARKV_ERR_BAD_SCALAR ? "scalar is not a canonical Fr" : "point is not a valid G1Affine");
+    return SNARKV_OK;
+}
+
+int msm_fold_partials_device(snarkv_ctx* ctx, const void* d_partials, size_t k, int format, void* d_out_affine) {
+    if (k == 0 || k > (1u << 20)) return ctx->fail(SNARKV_ERR_USAGE, "fold_partials: bad k");
+    Stage sg(ctx, "msm_fold_partials");
+    k_fold_partials<<<1, 32, 0, ctx->stream>>>((const uint8_t*)d_partials, (uint32_t)k, format, d_out_affine);
+    SNARKV_LAUNCH_CHECK(ctx, "k_fold_partials");
+    sg.launched();
+    return SNARKV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// batch of small independent MSMs: the literal GPU analogue of loader/native.rs:61-71 — one thread per term computes
+// base * scalar (double-and-add over the canonical bits, MSB first), one thread per MSM folds its terms and normalises.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_batch_term_mul(const uint8_t* __restrict__ scalars, const uint8_t* __restrict__ points,
+                                                        size_t total, int format, int check, uint8_t* __restrict__ terms,
+                                                        int* __restrict__ status) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    Fr s = fp_load<FR>(scalars + i * 32);
+    G1Affine p = g1_affine_load(points, i);
+    if (format == SNARKV_MONTGOMERY) s = fp_from_mont(s);
+    else {
+        if (check && !fp_is_canonical(s)) atomicCAS(status, 0, SNARKV_ERR_BAD_SCALAR);
+        if (check && (!fp_is_canonical(p.x) || !fp_is_canonical(p.y))) atomicCAS(status, 0, SNARKV_ERR_BAD_POINT);
+        p.x = fp_to_mont(p.x);
+        p.y = fp_to_mont(p.y);
+    }
+    if (check && !g1_affine_is_on_curve(p)) atomicCAS(status, 0, SNARKV_ERR_BAD_POINT);
+    G1Xyzz acc = xyzz_identity();
+    if (!g1_affine_is_identity(p)) {
+        for (int b = 253; b >= 0; --b) {
+            acc = xyzz_dbl(acc);
+            if ((s.v[b >> 5] >> (b & 31)) & 1u) xyzz_madd(acc, p.x, p.y);
+        }
+    }
+    xyzz_store(terms, i, acc);
+}
+
+__global__ void __launch_bounds__(128) k_batch_segment_sum(const uint8_t* __restrict__ terms, const uint64_t* __restrict__ offsets,
+                                                           size_t m, int format, uint8_t* __restrict__ out) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    G1Xyzz acc = xyzz_identity();
+    for (uint64_t i = offsets[j]; i < offsets[j + 1]; ++i) acc = xyzz_add(acc, xyzz_load(terms, i));
+    store_affine_fmt(out + j * 64, xyzz_to_affine(acc), format);
+}
+
+int msm_batch_device(snarkv_ctx* ctx, const void* d_scalars, const void* d_points, const void* d_offsets, size_t m, size_t total,
+                     int format, int flags, void* d_out_affine, void* d_status) {
+    const int check = (flags & SNARKV_CHECK_INPUTS) ? 1 : 0;
+    uint8_t* terms = (uint8_t*)ctx->wsget(WS_BATCH_TERMS, total * 128);
+    if (!terms) return SNARKV_ERR_CUDA;
+    SNARKV_CUDA_TRY(ctx, cudaMemsetAsync(d_status, 0, 4, ctx->stream));
+    {
+        Stage sg(ctx, "msm_batch_term_mul");
+        k_batch_term_mul<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>((const uint8_t*)d_scalars, (const uint8_t*)d_points,
+                                                                                  total, format, check, terms, (int*)d_status);
+        SNARKV_LAUNCH_CHECK(ctx, "k_batch_term_mul");
+        sg.launched();
+    }
+    {
+        Stage sg(ctx, "msm_batch_segment_sum");
+        k_batch_segment_sum<<<(unsigned)((m + 127) / 128), 128, 0, ctx->stream>>>(terms, (const uint64_t*)d_offsets, m, format,
+                                                                                 (uint8_t*)d_out_affine);
+        SNARKV_LAUNCH_CHECK(ctx, "k_batch_segment_sum");
+        sg.launched();
+    }
+    return SNARKV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// r.powers(n)  (snark-verifier/src/loader.rs:71-78) on the device: out[i] = r^i in Montgomery form
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void k_fr_powers(const uint8_t* __restrict__ r_in, int format, size_t n, uint8_t* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr r = fp_load<FR>(r_in);
+    if (format == SNARKV_CANONICAL) r = fp_to_mont(r);
+    Fr acc = fp_one<FR>();
+    for (size_t e = i; e != 0; e >>= 1) {
+        if (e & 1) acc = fp_mul(acc, r);
+        r = fp_sqr(r);
+    }
+    fp_store<FR>(out + i * 32, acc);
+}
+
+int fr_powers_device(snarkv_ctx* ctx, const void* d_r, int format, size_t n, void* d_out_mont) {
+    Stage sg(ctx, "fr_powers");
+    k_fr_powers<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((const uint8_t*)d_r, format, n, (uint8_t*)d_out_mont);
+    SNARKV_LAUNCH_CHECK(ctx, "k_fr_powers");
+    sg.launched();
+    return SNARKV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// element-wise field operations (test support for the parity suite: pins fp.cuh against the golden field vectors)
+// ---------------------------------------------------------------------------------------------------------------------
+template <Field F>
+__global__ void k_field_op(int op, const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, size_t n, uint8_t* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fp<F> x = fp_to_mont(fp_load<F>(a + i * 32));
+    Fp<F> y = fp_to_mont(fp_load<F>(b + i * 32));
+    Fp<F> r;
+    switch (op) {
+        case 0: r = fp_mul(x, y); break;
+        case 1: r = fp_add(x, y); break;
+        case 2: r = fp_sub(x, y); break;
+        case 3: r = fp_inv(x); break;
+        default: r = fp_sqr(x); break;
+    }
+    fp_store<F>(out + i * 32, fp_from_mont(r));
+}
+
+int field_op_device(snarkv_ctx* ctx, int field, int op, const void* d_a, const void* d_b, size_t n, void* d_out) {
+    const unsigned blocks = (unsigned)((n + 127) / 128);
+    if (field == 0) k_field_op<FQ><<<blocks, 128, 0, ctx->stream>>>(op, (const uint8_t*)d_a, (const uint8_t*)d_b, n, (uint8_t*)d_out);
+    else k_field_op<FR><<<blocks, 128, 0, ctx->stream>>>(op, (const uint8_t*)d_a, (const uint8_t*)d_b, n, (uint8_t*)d_out);
+    SNARKV_LAUNCH_CHECK(ctx, "k_field_op");
+    ctx->launches++;
+    return SNARKV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// synthetic workload generators (definition in include/snarkv_cuda.h; the test suite restates it independently)
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    uint64_t z = x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__global__ void k_synth_scalars(uint64_t seed, uint64_t start, size_t n, int format, uint8_t* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr s;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        uint64_t l = splitmix64(seed * 0x100000001B3ull + (start + i) * 4 + k);
+        if (k == 3) l &= (1ull << 62) - 1;
+        s.v[2 * k] = (uint32_t)l;
+        s.v[2 * k + 1] = (uint32_t)(l >> 32);
+    }
+    if (!fp_is_canonical(s)) {  // one conditional subtraction of r (value < 2^254 < 2r)
+        uint32_t borrow = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            uint64_t d = (uint64_t)s.v[k] - fp_mod_limb<FR>(k) - borrow;
+            s.v[k] = (uint32_t)d;
+            borrow = (uint32_t)(d >> 63);
+        }
+    }
+    if (format == SNARKV_MONTGOMERY) s = fp_to_mont(s);
+    fp_store<FR>(out + i * 32, s);
+}
+
+__global__ void __launch_bounds__(128) k_synth_points(uint64_t seed, uint64_t start, size_t n, int format, uint8_t* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t t = splitmix64(seed * 0x100000001B3ull + 0x5151515151515151ull + start + i) | 1ull;
+    Fq gx = fp_one<FQ>();
+    Fq gy = fp_dbl(gx);
+    G1Xyzz acc = xyzz_identity();
+    for (int b = 63 - __clzll((long long)t); b >= 0; --b) {
+        acc = xyzz_dbl(acc);
+        if ((t >> b) & 1ull) xyzz_madd(acc, gx, gy);
+    }
+    store_affine_fmt(out + i * 64, xyzz_to_affine(acc), format);
+}
+
+int synth_scalars_device(snarkv_ctx* ctx, uint64_t seed, uint64_t start, size_t n, int format, void* d_out) {
+    if (n == 0) return SNARKV_OK;
+    k_synth_scalars<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(seed, start, n, format, (uint8_t*)d_out);
+    SNARKV_LAUNCH_CHECK(ctx, "k_synth_scalars");
+    ctx->launches++;
+    return SNARKV_OK;
+}
+int synth_points_device(snarkv_ctx* ctx, uint64_t seed, uint64_t start, size_t n, int format, void* d_out) {
+    if (n == 0) return SNARKV_OK;
+    k_synth_points<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(seed, start, n, format, (uint8_t*)d_out);
+    SNARKV_LAUNCH_CHECK(ctx, "k_synth_points");
+    ctx->launches++;
+    return SNARKV_OK;
+}
+
+}  // namespace snarkv

@@ -1,0 +1,335 @@
+"""GPU parity suite: the CUDA path (through the C-ABI of include/snarkv_cuda.h) against
+  (1) the committed golden vectors (tests/golden, from the independent Python big-int model),
+  (2) the C++ oracle (oracle/) on seeded inputs at sizes it finishes in seconds,
+  (3) size-independent properties at full size (discrete-log checksum, linearity).
+Bar: bit-exact (integer arithmetic only).  Shapes follow the reference's own tests: accept valid, reject tampered
+(system/halo2/test/kzg/native.rs:57-68, test/kzg/evm.rs:58-62), mock accumulator (s*G, G) (test/kzg.rs:37-45)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import oracle
+import snark_verifier_b200 as sv
+from oracle import bn254_model as m
+
+pytestmark = pytest.mark.gpu
+H = bytes.fromhex
+le = m.fe_to_le
+
+
+@pytest.fixture(scope="module")
+def loader():
+    L = sv.CudaLoader(0)
+    yield L
+    L.close()
+
+
+@pytest.fixture(scope="module")
+def mont_loader():
+    L = sv.CudaLoader(0, fmt=sv.MONTGOMERY)
+    yield L
+    L.close()
+
+
+def to_mont_pts(pb):
+    return b"".join(oracle.fp_to_mont(0, pb[i:i + 32]) for i in range(0, len(pb), 32))
+
+
+def to_mont_scalars(sb):
+    return b"".join(oracle.fp_to_mont(1, sb[i:i + 32]) for i in range(0, len(sb), 32))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# field layer
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("field,name", [(0, "fq"), (1, "fr")])
+def test_device_field_ops_match_golden(loader, golden, field, name):
+    g = golden("field")[name]
+    a = b"".join(H(x[0]) for x in g["mul"]); b = b"".join(H(x[1]) for x in g["mul"])
+    n = len(g["mul"])
+    assert loader.field_op(field, 0, a, b, n) == b"".join(H(x[2]) for x in g["mul"])
+    mod = m.P if field == 0 else m.R
+    ai = [int.from_bytes(H(x[0]), "little") for x in g["mul"]]
+    bi = [int.from_bytes(H(x[1]), "little") for x in g["mul"]]
+    assert loader.field_op(field, 1, a, b, n) == b"".join(le((x + y) % mod) for x, y in zip(ai, bi))
+    assert loader.field_op(field, 2, a, b, n) == b"".join(le((x - y) % mod) for x, y in zip(ai, bi))
+    inv_in = b"".join(H(x[0]) for x in g["inv"])
+    assert loader.field_op(field, 3, inv_in, inv_in, len(g["inv"])) == b"".join(H(x[1]) for x in g["inv"])
+
+
+def test_device_field_mul_random_vs_python(loader):
+    rng = np.random.default_rng(5)
+    n = 4096
+    for field, mod in ((0, m.P), (1, m.R)):
+        xs = [int.from_bytes(rng.bytes(32), "little") % mod for _ in range(n)]
+        ys = [int.from_bytes(rng.bytes(32), "little") % mod for _ in range(n)]
+        got = loader.field_op(field, 0, b"".join(map(le, xs)), b"".join(map(le, ys)), n)
+        assert got == b"".join(le(x * y % mod) for x, y in zip(xs, ys))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# MSM
+# ---------------------------------------------------------------------------------------------------------------------
+def test_msm_golden_cases(loader, golden):
+    for case in golden("msm"):
+        got = loader.msm(H(case["scalars"]), H(case["points"]), case["n"], flags=sv.CHECK_INPUTS)
+        assert got == H(case["expected"]), case["name"]
+
+
+def test_msm_golden_cases_montgomery_layout(mont_loader, golden):
+    """halo2curves in-memory layout in, same layout out (the zero-copy path of the Rust glue)."""
+    for case in golden("msm"):
+        got = mont_loader.msm(to_mont_scalars(H(case["scalars"])), to_mont_pts(H(case["points"])), case["n"])
+        assert got == to_mont_pts(H(case["expected"])), case["name"]
+
+
+def test_msm_pairs_api_is_native_loader_shape(loader, golden):
+    case = golden("msm")[3]
+    s, p, n = H(case["scalars"]), H(case["points"]), case["n"]
+    pairs = [(s[32 * i:32 * i + 32], p[64 * i:64 * i + 64]) for i in range(n)]
+    assert loader.multi_scalar_multiplication(pairs) == H(case["expected"])
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 33, 100, 1000, 4097, 1 << 14])
+def test_msm_vs_oracle_seeded(loader, n):
+    s = oracle.synth_scalars(21, 0, n)
+    p = oracle.synth_points(21, 0, n, 8)
+    exp = oracle.msm_pippenger(s, p, n, 8)
+    assert loader.msm(s, p, n) == exp
+    if n <= 100:
+        assert exp == oracle.msm_native(s, p, n)  # the literal NativeLoader fold (native.rs:61-71)
+
+
+@pytest.mark.parametrize("c", [2, 3, 4, 8, 11, 13, 16])
+def test_msm_every_window_size_agrees(loader, c):
+    n = 3000
+    s = oracle.synth_scalars(22, 0, n)
+    p = oracle.synth_points(22, 0, n, 8)
+    exp = oracle.msm_pippenger(s, p, n, 8)
+    loader.set_window_bits(c)
+    try:
+        assert loader.msm(s, p, n) == exp
+    finally:
+        loader.set_window_bits(0)
+
+
+def test_msm_skewed_scalars_single_bucket(loader):
+    """All scalars equal / tiny scalars: every term lands in the same bucket of each window (worst-case balance)."""
+    n = 5000
+    p = oracle.synth_points(23, 0, n, 8)
+    for val in (1, 2, 0xFFFF, m.R - 1):
+        s = le(val) * n
+        assert loader.msm(s, p, n) == oracle.msm_pippenger(s, p, n, 8), val
+
+
+def test_msm_empty_and_invalid_inputs(loader):
+    with pytest.raises(sv.Error):
+        loader.msm(b"", b"", 0)                      # native.rs:69 .unwrap() on empty
+    g = m.g1_to_bytes(m.G1_GEN)
+    with pytest.raises(sv.Error):
+        loader.msm(le(m.R), g, 1, flags=sv.CHECK_INPUTS)      # non-canonical scalar: from_repr fails
+    off = le(1) + le(3)
+    with pytest.raises(sv.Error):
+        loader.msm(le(5), off, 1, flags=sv.CHECK_INPUTS)      # not on the curve: from_xy fails
+    with pytest.raises(sv.Error):
+        loader.msm(le(5), le(m.P) + le(2), 1, flags=sv.CHECK_INPUTS)
+
+
+def test_msm_batch_matches_native_fold(loader):
+    sizes = [1, 21, 3, 20, 1, 24, 7]              # StandardPlonk shapes: 21+3 (GWC), 20+1 (SHPLONK), SURVEY §3.1
+    offs = [0]
+    for k in sizes:
+        offs.append(offs[-1] + k)
+    total = offs[-1]
+    s = oracle.synth_scalars(31, 0, total)
+    p = oracle.synth_points(31, 0, total, 8)
+    got = loader.msm_batch(s, p, offs)
+    for j, k in enumerate(sizes):
+        lo = offs[j]
+        assert got[j] == oracle.msm_native(s[32 * lo:32 * (lo + k)], p[64 * lo:64 * (lo + k)], k), j
+
+
+def test_msm_host_mirror_evaluate(loader):
+    """util::msm::Msm algebra on the host + evaluate(Some(gen)) through the loader."""
+    pts = [oracle.synth_points(41, i, 1) for i in range(3)]
+    a = sv.Msm.base(loader, pts[0]) * 5 + sv.Msm.base(loader, pts[1]) * 7 + sv.Msm.base(loader, pts[0]) * 11
+    a = a + sv.Msm.constant_(loader, 13)
+    assert len(a.bases) == 2                                   # push dedupes equal bases (util/msm.rs:109-116)
+    g = m.g1_to_bytes(m.G1_GEN)
+    exp = oracle.msm_native(le(13) + le(16) + le(7), g + pts[0] + pts[1], 3)
+    assert a.evaluate(g) == exp
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# device-resident operands, synthetic generators, Jacobian partials
+# ---------------------------------------------------------------------------------------------------------------------
+def test_synth_generators_match_oracle(loader):
+    import torch
+    n = 3000
+    ds = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
+    dp = torch.empty(n * 64, dtype=torch.uint8, device="cuda")
+    loader.synth_scalars_device(9, 100, n, ds.data_ptr())
+    loader.synth_points_device(9, 100, n, dp.data_ptr())
+    torch.cuda.synchronize()
+    assert bytes(ds.cpu().numpy()) == oracle.synth_scalars(9, 100, n)
+    assert bytes(dp.cpu().numpy()) == oracle.synth_points(9, 100, n, 8)
+
+
+def test_device_msm_partials_fold_like_rayon_chunks(loader):
+    """util/msm.rs:322-336: chunk the terms, one partial per chunk, fold the Jacobian partials, to_affine."""
+    import torch
+    n, k = 6000, 3
+    s = oracle.synth_scalars(12, 0, n); p = oracle.synth_points(12, 0, n, 8)
+    ds = torch.frombuffer(bytearray(s), dtype=torch.uint8).cuda()
+    dp = torch.frombuffer(bytearray(p), dtype=torch.uint8).cuda()
+    parts = torch.zeros(k * 96, dtype=torch.uint8, device="cuda")
+    out = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    chunk = n // k
+    for j in range(k):
+        loader.msm_device(ds.data_ptr() + 32 * j * chunk, dp.data_ptr() + 64 * j * chunk, chunk,
+                          d_out_jacobian=parts.data_ptr() + 96 * j)
+        torch.cuda.synchronize()
+    loader.fold_partials_device(parts.data_ptr(), k, out.data_ptr())
+    torch.cuda.synchronize()
+    assert bytes(out.cpu().numpy()) == oracle.msm_pippenger(s, p, n, 8)
+
+
+@pytest.mark.parametrize("logn", [20, 22])
+def test_msm_full_size_dlog_checksum(loader, logn):
+    """Size-independent property at BASELINE sizes: P_i = [t_i]G  =>  MSM = [sum s_i t_i mod r] G."""
+    import torch
+    n = 1 << logn
+    ds = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
+    dp = torch.empty(n * 64, dtype=torch.uint8, device="cuda")
+    out = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    loader.synth_scalars_device(77, 0, n, ds.data_ptr())
+    loader.synth_points_device(77, 0, n, dp.data_ptr())
+    loader.msm_device(ds.data_ptr(), dp.data_ptr(), n, d_out_affine=out.data_ptr())
+    torch.cuda.synchronize()
+    s_host = ds.cpu().numpy()
+    t = oracle.synth_point_scalars(77, 0, n)
+    assert bytes(s_host[:32 * 64]) == oracle.synth_scalars(77, 0, 64)
+    exp = oracle.msm_expected_from_dlogs(s_host, t, n)
+    assert bytes(out.cpu().numpy()) == exp
+    # spot-check generated points against the oracle's own scalar multiplication
+    pts = dp[: 64 * 16].cpu().numpy().tobytes()
+    assert pts == oracle.synth_points(77, 0, 16, 1)
+
+
+def test_msm_linearity_property(loader):
+    """MSM(s, P) + MSM(s', P) == MSM(s + s', P) at a size the oracle never sees."""
+    import torch
+    n = 1 << 18
+    dp = torch.empty(n * 64, dtype=torch.uint8, device="cuda")
+    loader.synth_points_device(55, 0, n, dp.data_ptr())
+    s1 = np.frombuffer(oracle.synth_scalars(55, 0, n), dtype=np.uint8)
+    s2 = np.frombuffer(oracle.synth_scalars(56, 0, n), dtype=np.uint8)
+    a = [int.from_bytes(s1[32 * i:32 * i + 32].tobytes(), "little") for i in range(n)]
+    b = [int.from_bytes(s2[32 * i:32 * i + 32].tobytes(), "little") for i in range(n)]
+    s3 = b"".join(le((x + y) % m.R) for x, y in zip(a, b))
+    pts = dp.cpu().numpy().tobytes()
+    r1, r2, r3 = loader.msm(s1.tobytes(), pts, n), loader.msm(s2.tobytes(), pts, n), loader.msm(s3, pts, n)
+    assert oracle.g1_add(r1, r2) == r3
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# KZG decide / accumulate
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def kzg(loader, golden):
+    g = golden("pairing")
+    dk = sv.KzgDecidingKey(m.g1_to_bytes(m.G1_GEN), H(g["g2_generator"]), H(g["s_g2"]))
+    return sv.KzgAs(loader, dk)
+
+
+def test_decide_golden_accept_reject_and_gt_bytes(kzg, golden):
+    g = golden("pairing")
+    checks = g["checks"]
+    lhs = b"".join(H(c["lhs"]) for c in checks); rhs = b"".join(H(c["rhs"]) for c in checks)
+    acc, gt = kzg.decide_batch(lhs, rhs, len(checks), want_gt=True)
+    assert list(acc) == [int(c["accept"]) for c in checks]
+    for i, c in enumerate(checks):
+        assert gt[384 * i:384 * (i + 1)] == H(c["gt"]), c["name"]
+    # e(G1, G2) itself: lhs = G, rhs = identity
+    acc, gt = kzg.decide_batch(m.g1_to_bytes(m.G1_GEN), bytes(64), 1, want_gt=True)
+    assert acc == b"\x00" and gt == H(g["e_G1_G2"])
+
+
+def test_decide_and_decide_all_error_behaviour(kzg, golden):
+    checks = {c["name"]: c for c in golden("pairing")["checks"]}
+    ok = sv.KzgAccumulator(H(checks["mock_sG_G"]["lhs"]), H(checks["mock_sG_G"]["rhs"]))
+    bad = sv.KzgAccumulator(H(checks["tampered_rhs"]["lhs"]), H(checks["tampered_rhs"]["rhs"]))
+    kzg.decide(ok)
+    kzg.decide_all([ok, ok])
+    kzg.decide_all([])
+    with pytest.raises(sv.AssertionFailure, match="e\\(lhs, g2\\)"):
+        kzg.decide(bad)
+    with pytest.raises(sv.AssertionFailure):
+        kzg.decide_all([ok, bad, ok])
+
+
+def test_decide_batch_vs_oracle_random_mix(kzg, golden):
+    g = golden("pairing")
+    s = int.from_bytes(H(g["s"]), "little")
+    rng = np.random.default_rng(8)
+    n = 96
+    gen = m.g1_to_bytes(m.G1_GEN)
+    lhs, rhs = [], []
+    for i in range(n):
+        a = int.from_bytes(rng.bytes(31), "little") + 1
+        bad = (i % 3 == 1)
+        lhs.append(oracle.g1_mul(gen, le((a * s + (1 if bad else 0)) % m.R)))
+        rhs.append(oracle.g1_mul(gen, le(a)))
+    lhs, rhs = b"".join(lhs), b"".join(rhs)
+    acc, gt = kzg.decide_batch(lhs, rhs, n, want_gt=True)
+    oacc, ogt = oracle.kzg_decide_batch(lhs, rhs, n, H(g["g2_generator"]), H(g["s_g2"]), threads=8, hoist=0, want_gt=True)
+    assert acc == oacc and gt == ogt
+    assert list(acc) == [0 if i % 3 == 1 else 1 for i in range(n)]
+
+
+def test_decide_rejects_off_curve_accumulator(kzg):
+    acc, _ = kzg.decide_batch(le(1) + le(3), m.g1_to_bytes(m.G1_GEN), 1)
+    assert acc == b"\x00"
+
+
+def test_decide_needs_key():
+    L = sv.CudaLoader(0)
+    try:
+        acc = ctypes.create_string_buffer(1)
+        rc = L.lib.snarkv_kzg_decide_batch(L.h, bytes(64), bytes(64), 1, sv.CANONICAL, acc, None)
+        assert rc == sv.ERR_NO_KEY
+    finally:
+        L.close()
+
+
+def test_bad_deciding_key_is_rejected(loader):
+    with pytest.raises(sv.Error):
+        sv.KzgAs(loader, sv.KzgDecidingKey(bytes(64), le(1) + le(2) + le(3) + le(4), bytes(128)))
+
+
+def test_accumulate_golden_then_decide(kzg, golden):
+    for c in golden("accumulate"):
+        n = c["n"]
+        lhs, rhs = H(c["lhs"]), H(c["rhs"])
+        accs = [sv.KzgAccumulator(lhs[64 * i:64 * i + 64], rhs[64 * i:64 * i + 64]) for i in range(n)]
+        out = kzg.verify(accs, H(c["r"]))
+        assert out.lhs == H(c["out_lhs"]) and out.rhs == H(c["out_rhs"])
+        kzg.decide(out)          # an accumulation of valid accumulators is valid
+
+
+def test_accumulate_256_vs_oracle(kzg, golden):
+    """BASELINE config 4 shape: 256 accumulators (a_i s G, a_i G), powers of r, then one decide."""
+    g = golden("pairing")
+    s = int.from_bytes(H(g["s"]), "little")
+    n = 256
+    gen = m.g1_to_bytes(m.G1_GEN)
+    a = [int.from_bytes(oracle.synth_scalars(91, i, 1), "little") for i in range(n)]
+    lhs = b"".join(oracle.g1_mul(gen, le(x * s % m.R)) for x in a)
+    rhs = b"".join(oracle.g1_mul(gen, le(x)) for x in a)
+    r = oracle.synth_scalars(92, 0, 1)
+    accs = [sv.KzgAccumulator(lhs[64 * i:64 * i + 64], rhs[64 * i:64 * i + 64]) for i in range(n)]
+    out = kzg.verify(accs, r)
+    ol, orr = oracle.kzg_accumulate(lhs, rhs, n, r)
+    assert (out.lhs, out.rhs) == (ol, orr)
+    kzg.decide(out)
