@@ -78,6 +78,12 @@ int snarkv_set_window_bits(snarkv_ctx* ctx, int c);
 int snarkv_g1_msm(snarkv_ctx* ctx, const uint8_t* scalars, const uint8_t* points, size_t n, int format, int flags,
                   uint8_t out_affine[64]);
 
+/* One rank's share of a chunk-partitioned MSM (util/msm.rs:322-332: `scalars.chunks(chunk_size).zip(bases.chunks(..))`, one
+ * serial MSM per chunk): host slices in, the chunk's Jacobian partial (96 B) left in DEVICE memory, ready for the
+ * all-gather + snarkv_g1_fold_partials_device that replaces the fold at util/msm.rs:333-335.  Synchronises the stream. */
+int snarkv_g1_msm_partial(snarkv_ctx* ctx, const uint8_t* scalars, const uint8_t* points, size_t n, int format, int flags,
+                          void* d_out_jacobian);
+
 /* Same operation on operands already resident in this device's HBM (pointers from cudaMalloc / a torch tensor's
  * data_ptr()).  Results are written to DEVICE memory, nothing is synchronised or copied to the host:
  *   d_out_affine   64 B  affine result in `format`            (may be NULL)
@@ -138,6 +144,9 @@ int snarkv_debug_field_op(snarkv_ctx* ctx, int field, int op, const uint8_t* a, 
 /* ---- instrumentation -----------------------------------------------------------------------------------------------------
  * When enabled, every pipeline stage of the next MSM / decide call is bracketed by CUDA events on the context's stream.
  * snarkv_profile_read synchronises and returns up to `cap` (name, milliseconds, launches) records of the LAST call. */
+/* The MSM plan the library would use for n terms: out = {window bits c, windows W, buckets per window 2^(c-1), max points
+ * per accumulate task}.  Pure host-side query (no launch). */
+int snarkv_g1_msm_plan(snarkv_ctx* ctx, size_t n, uint32_t out[4]);
 typedef struct {
     const char* name; /* static string, e.g. "msm_bucket_accumulate" */
     float ms;

@@ -57,6 +57,7 @@ C_ABI = {
     "snarkv_set_stream": (_i, [_vp, _vp]),
     "snarkv_set_window_bits": (_i, [_vp, _i]),
     "snarkv_g1_msm": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp]),
+    "snarkv_g1_msm_partial": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp]),
     "snarkv_g1_msm_device": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp, _vp, _vp]),
     "snarkv_g1_fold_partials_device": (_i, [_vp, _vp, _sz, _i, _vp]),
     "snarkv_g1_msm_batch": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _vp]),
@@ -67,6 +68,7 @@ C_ABI = {
     "snarkv_synth_scalars_device": (_i, [_vp, _u64, _u64, _sz, _i, _vp]),
     "snarkv_synth_points_device": (_i, [_vp, _u64, _u64, _sz, _i, _vp]),
     "snarkv_debug_field_op": (_i, [_vp, _i, _i, _vp, _vp, _sz, _vp]),
+    "snarkv_g1_msm_plan": (_i, [_vp, _sz, ctypes.POINTER(ctypes.c_uint32)]),
     "snarkv_profile_enable": (_i, [_vp, _i]),
     "snarkv_profile_read": (_i, [_vp, ctypes.POINTER(_StageTime), _i]),
     "snarkv_launch_count": (_u64, [_vp]),
@@ -147,6 +149,11 @@ class CudaLoader:
     def set_window_bits(self, c):
         self._check(self.lib.snarkv_set_window_bits(self.h, c), "set_window_bits")
 
+    def msm_plan(self, n):
+        out = (ctypes.c_uint32 * 4)()
+        self._check(self.lib.snarkv_g1_msm_plan(self.h, n, out), "msm_plan")
+        return {"window_bits": out[0], "windows": out[1], "buckets_per_window": out[2], "task_len": out[3]}
+
     def profile(self, on=True):
         self._check(self.lib.snarkv_profile_enable(self.h, 1 if on else 0), "profile_enable")
 
@@ -181,6 +188,11 @@ class CudaLoader:
         out = ctypes.create_string_buffer(64)
         self._check(self.lib.snarkv_g1_msm(self.h, _addr(scalars), _addr(points), n, self.fmt, flags, out), "multi_scalar_multiplication")
         return out.raw
+
+    def msm_partial(self, scalars, points, n, d_out_jacobian, flags=0):
+        """Host slices in, 96-byte Jacobian partial left on the device (one rank's chunk of util/msm.rs:322-336)."""
+        self._check(self.lib.snarkv_g1_msm_partial(self.h, _addr(scalars), _addr(points), n, self.fmt, flags, _addr(d_out_jacobian)),
+                    "msm_partial")
 
     def msm_device(self, d_scalars, d_points, n, d_out_affine=None, d_out_jacobian=None, d_status=None, flags=0):
         self._check(self.lib.snarkv_g1_msm_device(self.h, _addr(d_scalars), _addr(d_points), n, self.fmt, flags,

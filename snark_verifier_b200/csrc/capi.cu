@@ -77,6 +77,12 @@ int snarkv_set_window_bits(snarkv_ctx* ctx, int c) {
     return SNARKV_OK;
 }
 
+int snarkv_g1_msm_plan(snarkv_ctx* ctx, size_t n, uint32_t out[4]) {
+    if (!ctx || !out) return SNARKV_ERR_USAGE;
+    msm_plan_query(ctx, n, out);
+    return SNARKV_OK;
+}
+
 int snarkv_profile_enable(snarkv_ctx* ctx, int on) {
     if (!ctx) return SNARKV_ERR_USAGE;
     ctx->profiling = on != 0;
@@ -108,7 +114,16 @@ int snarkv_g1_msm(snarkv_ctx* ctx, const uint8_t* scalars, const uint8_t* points
     if (n == 0) return ctx->fail(SNARKV_ERR_EMPTY, "multi_scalar_multiplication on an empty slice");
     if (!scalars || !points || !out_affine || bad_format(format)) return ctx->fail(SNARKV_ERR_USAGE, "snarkv_g1_msm: bad argument");
     ctx->profile_begin_call();
-    return msm_run_host(ctx, scalars, points, n, format, flags, out_affine);
+    return msm_run_host(ctx, scalars, points, n, format, flags, out_affine, nullptr);
+}
+
+int snarkv_g1_msm_partial(snarkv_ctx* ctx, const uint8_t* scalars, const uint8_t* points, size_t n, int format, int flags,
+                          void* d_out_jacobian) {
+    CTX_GUARD(ctx);
+    if (n == 0) return ctx->fail(SNARKV_ERR_EMPTY, "multi_scalar_multiplication on an empty slice");
+    if (!scalars || !points || !d_out_jacobian || bad_format(format)) return ctx->fail(SNARKV_ERR_USAGE, "snarkv_g1_msm_partial: bad argument");
+    ctx->profile_begin_call();
+    return msm_run_host(ctx, scalars, points, n, format, flags, nullptr, d_out_jacobian);
 }
 
 int snarkv_g1_msm_device(snarkv_ctx* ctx, const void* d_scalars, const void* d_points, size_t n, int format, int flags,

@@ -28,6 +28,11 @@ enum WsSlot : int {
     WS_BUCKETS,           // W x NB x 128 B
     WS_SEGPART,           // W x J  x 128 B
     WS_WINSUM,            // W x 128 B
+    WS_TASK_BASE,         // W x NB u32
+    WS_WINDOW_TASKS,      // W u32
+    WS_TASKS,             // W x cap uint2
+    WS_TASK_OUT,          // W x cap x 128 B
+    WS_BIG,               // 1 + W x NB u32
     WS_STATUS,            // 4 B
     WS_OUT,               // small outputs (affine 64 + jacobian 96)
     WS_IO_A,              // staging for host-buffer entry points
@@ -148,7 +153,9 @@ struct Stage {
 // internal entry points shared between translation units
 int msm_run_device(snarkv_ctx* ctx, const void* d_scalars, const void* d_points, size_t n, int scalar_format, int point_format,
                    int out_format, int flags, void* d_out_affine, void* d_out_jacobian, void* d_status);
-int msm_run_host(snarkv_ctx* ctx, const uint8_t* scalars, const uint8_t* points, size_t n, int format, int flags, uint8_t* out);
+int msm_run_host(snarkv_ctx* ctx, const uint8_t* scalars, const uint8_t* points, size_t n, int format, int flags, uint8_t* out,
+                 void* d_out_jacobian);
+void msm_plan_query(snarkv_ctx* ctx, size_t n, uint32_t out[4]);
 int msm_fold_partials_device(snarkv_ctx* ctx, const void* d_partials, size_t k, int format, void* d_out_affine);
 int msm_batch_device(snarkv_ctx* ctx, const void* d_scalars, const void* d_points, const void* d_offsets, size_t m, size_t total,
                      int format, int flags, void* d_out_affine, void* d_status);

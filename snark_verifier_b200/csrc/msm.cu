@@ -28,6 +28,8 @@ struct MsmPlan {
     uint32_t NB;   // buckets per window = 2^(c-1), bucket values 1..NB
     uint32_t seg;  // buckets per reduce thread
     uint32_t J;    // segments per window
+    uint32_t T;    // max points per accumulate task (a bucket with more points is split into ceil(cnt / T) tasks)
+    uint32_t cap;  // task slots per window: sum_b ceil(cnt_b / T) <= NB + n / T
 };
 
 static int choose_window_bits(size_t n) {
@@ -55,6 +57,11 @@ static MsmPlan make_plan(size_t n, int c_override) {
     p.NB = 1u << (p.c - 1);
     p.seg = p.NB < 16 ? p.NB : 16;
     p.J = (p.NB + p.seg - 1) / p.seg;
+    const size_t avg = (n + p.NB - 1) / p.NB;
+    size_t T = 2 * avg;   // uniformly random digits never reach 2x the mean once the mean is >= 64
+    if (T < 64) T = 64;
+    p.T = (uint32_t)T;
+    p.cap = p.NB + (uint32_t)(n / T) + 1;
     return p;
 }
 
@@ -113,43 +120,64 @@ __global__ void __launch_bounds__(256) k_digits(const uint8_t* __restrict__ scal
     }
 }
 
-// K2: exclusive scan of each window's histogram; one block per window.
+// K2: per-window exclusive scans, one block per window: `offsets` = start of each bucket's run in the sorted array,
+// `task_base` = index of the bucket's first accumulate task (a bucket of cnt points owns ceil(cnt / T) tasks).
 __global__ void __launch_bounds__(1024) k_scan(const uint32_t* __restrict__ counts, uint32_t* __restrict__ offsets,
-                                               uint32_t* __restrict__ cursor, uint32_t NB) {
-    __shared__ uint32_t warp_tot[32];
-    const uint32_t w = blockIdx.x, t = threadIdx.x, T = blockDim.x;
-    const uint32_t per = (NB + T - 1) / T;
+                                               uint32_t* __restrict__ cursor, uint32_t* __restrict__ task_base,
+                                               uint32_t* __restrict__ window_tasks, uint32_t NB, uint32_t T) {
+    __shared__ uint2 warp_tot[32];
+    const uint32_t w = blockIdx.x, t = threadIdx.x, NT = blockDim.x;
+    const uint32_t per = (NB + NT - 1) / NT;
     const uint32_t lo = min(t * per, NB), hi = min(lo + per, NB);
     const uint32_t* cw = counts + (size_t)w * NB;
-    uint32_t sum = 0;
-    for (uint32_t k = lo; k < hi; ++k) sum += cw[k];
-    // block-wide exclusive scan of `sum`
-    uint32_t incl = sum;
+    uint2 sum = make_uint2(0, 0);
+    for (uint32_t k = lo; k < hi; ++k) {
+        const uint32_t c = cw[k];
+        sum.x += c;
+        sum.y += (c + T - 1) / T;
+    }
+    uint2 incl = sum;
     const uint32_t lane = t & 31, wid = t >> 5;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= (uint32_t)o) incl += v;
+        uint32_t vx = __shfl_up_sync(0xffffffffu, incl.x, o), vy = __shfl_up_sync(0xffffffffu, incl.y, o);
+        if (lane >= (uint32_t)o) { incl.x += vx; incl.y += vy; }
     }
     if (lane == 31) warp_tot[wid] = incl;
     __syncthreads();
     if (wid == 0) {
-        uint32_t v = lane < (T >> 5) ? warp_tot[lane] : 0;
-        uint32_t iv = v;
+        uint2 v = lane < (NT >> 5) ? warp_tot[lane] : make_uint2(0, 0);
+        uint2 iv = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            uint32_t u = __shfl_up_sync(0xffffffffu, iv, o);
-            if (lane >= (uint32_t)o) iv += u;
+            uint32_t ux = __shfl_up_sync(0xffffffffu, iv.x, o), uy = __shfl_up_sync(0xffffffffu, iv.y, o);
+            if (lane >= (uint32_t)o) { iv.x += ux; iv.y += uy; }
         }
-        warp_tot[lane] = iv - v;
+        if (lane == 31) window_tasks[w] = iv.y;
+        warp_tot[lane] = make_uint2(iv.x - v.x, iv.y - v.y);
     }
     __syncthreads();
-    uint32_t running = warp_tot[wid] + incl - sum;
+    uint32_t run_off = warp_tot[wid].x + incl.x - sum.x;
+    uint32_t run_task = warp_tot[wid].y + incl.y - sum.y;
     for (uint32_t k = lo; k < hi; ++k) {
-        offsets[(size_t)w * NB + k] = running;
-        cursor[(size_t)w * NB + k] = running;
-        running += cw[k];
+        const uint32_t c = cw[k];
+        offsets[(size_t)w * NB + k] = run_off;
+        cursor[(size_t)w * NB + k] = run_off;
+        task_base[(size_t)w * NB + k] = run_task;
+        run_off += c;
+        run_task += (c + T - 1) / T;
     }
+}
+
+// K2b: task descriptors.  Task slot (w, task_base[b] + j) = (bucket b, part j).
+__global__ void __launch_bounds__(256) k_build_tasks(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ task_base,
+                                                     uint32_t NB, uint32_t total, uint32_t T, uint32_t cap, uint2* __restrict__ tasks) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= total) return;
+    const uint32_t w = tid / NB, b = tid - w * NB;
+    const uint32_t parts = (counts[tid] + T - 1) / T;
+    uint2* out = tasks + (size_t)w * cap + task_base[tid];
+    for (uint32_t j = 0; j < parts; ++j) out[j] = make_uint2(b, j);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -159,29 +187,78 @@ __global__ void __launch_bounds__(1024) k_scan(const uint32_t* __restrict__ coun
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_bucket_accumulate(const uint8_t* __restrict__ points, const uint32_t* __restrict__ sorted,
                                                            const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts,
-                                                           size_t n, uint32_t NB, uint32_t total, uint8_t* __restrict__ buckets) {
+                                                           const uint2* __restrict__ tasks, const uint32_t* __restrict__ window_tasks,
+                                                           size_t n, uint32_t NB, uint32_t T, uint32_t cap,
+                                                           uint8_t* __restrict__ task_out) {
+    const uint32_t w = blockIdx.y;
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= window_tasks[w]) return;
+    const uint2 task = tasks[(size_t)w * cap + slot];
+    const uint32_t bucket = w * NB + task.x;
+    const uint32_t first = task.y * T;
+    const uint32_t cnt = min(T, counts[bucket] - first);
+    const uint32_t* list = sorted + (size_t)w * n + offsets[bucket] + first;
+    G1Xyzz acc = xyzz_identity();
+    uint32_t e = list[0];
+    G1Affine nxt = g1_affine_load(points, e & 0x7fffffffu);
+    for (uint32_t k = 0; k < cnt; ++k) {
+        G1Affine cur = nxt;
+        const uint32_t neg = e >> 31;
+        if (k + 1 < cnt) {
+            e = list[k + 1];
+            nxt = g1_affine_load(points, e & 0x7fffffffu);
+        }
+        if (g1_affine_is_identity(cur)) continue;
+        if (neg) cur.y = fp_neg(cur.y);
+        xyzz_madd(acc, cur.x, cur.y);
+    }
+    xyzz_store(task_out, (size_t)w * cap + slot, acc);
+}
+
+// K4b: bucket = sum of its task results (one copy in the common case of one task per bucket).  Buckets split into more
+// than MERGE_SERIAL tasks (heavily skewed digit distributions) are queued for the block-wide merge below.
+#define SNARKV_MERGE_SERIAL 16u
+__global__ void __launch_bounds__(128) k_bucket_merge(const uint8_t* __restrict__ task_out, const uint32_t* __restrict__ counts,
+                                                      const uint32_t* __restrict__ task_base, uint32_t NB, uint32_t total, uint32_t T,
+                                                      uint32_t cap, uint8_t* __restrict__ buckets, uint32_t* __restrict__ big_count,
+                                                      uint32_t* __restrict__ big_list) {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= total) return;
     const uint32_t w = tid / NB;
-    const uint32_t cnt = counts[tid];
-    const uint32_t* list = sorted + (size_t)w * n + offsets[tid];
-    G1Xyzz acc = xyzz_identity();
-    if (cnt > 0) {
-        uint32_t e = list[0];
-        G1Affine nxt = g1_affine_load(points, e & 0x7fffffffu);
-        for (uint32_t k = 0; k < cnt; ++k) {
-            G1Affine cur = nxt;
-            const uint32_t neg = e >> 31;
-            if (k + 1 < cnt) {
-                e = list[k + 1];
-                nxt = g1_affine_load(points, e & 0x7fffffffu);
-            }
-            if (g1_affine_is_identity(cur)) continue;
-            if (neg) cur.y = fp_neg(cur.y);
-            xyzz_madd(acc, cur.x, cur.y);
-        }
+    const uint32_t parts = (counts[tid] + T - 1) / T;
+    if (parts > SNARKV_MERGE_SERIAL) {
+        big_list[atomicAdd(big_count, 1u)] = tid;
+        return;
     }
+    const size_t base = (size_t)w * cap + task_base[tid];
+    G1Xyzz acc = xyzz_identity();
+    if (parts == 1) acc = xyzz_load(task_out, base);
+    else
+        for (uint32_t j = 0; j < parts; ++j) acc = xyzz_add(acc, xyzz_load(task_out, base + j));
     xyzz_store(buckets, tid, acc);
+}
+__global__ void __launch_bounds__(128) k_bucket_merge_big(const uint8_t* __restrict__ task_out, const uint32_t* __restrict__ counts,
+                                                          const uint32_t* __restrict__ task_base, uint32_t NB, uint32_t T, uint32_t cap,
+                                                          uint8_t* __restrict__ buckets, const uint32_t* __restrict__ big_count,
+                                                          const uint32_t* __restrict__ big_list) {
+    __shared__ G1Xyzz sm[128];
+    const uint32_t t = threadIdx.x;
+    for (uint32_t q = blockIdx.x; q < *big_count; q += gridDim.x) {
+        const uint32_t tid = big_list[q];
+        const uint32_t w = tid / NB;
+        const uint32_t parts = (counts[tid] + T - 1) / T;
+        const size_t base = (size_t)w * cap + task_base[tid];
+        G1Xyzz acc = xyzz_identity();
+        for (uint32_t j = t; j < parts; j += blockDim.x) acc = xyzz_add(acc, xyzz_load(task_out, base + j));
+        sm[t] = acc;
+        __syncthreads();
+        for (uint32_t s = blockDim.x >> 1; s > 0; s >>= 1) {
+            if (t < s) sm[t] = xyzz_add(sm[t], sm[t + s]);
+            __syncthreads();
+        }
+        if (t == 0) xyzz_store(buckets, tid, sm[0]);
+        __syncthreads();
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -271,7 +348,9 @@ struct MsmWork {
     MsmPlan pl;
     int* status;
     uint32_t *counts, *offsets, *cursor, *sorted;
-    uint8_t *buckets, *segpart, *winsum;
+    uint32_t *task_base, *window_tasks, *big;   // big = [count | list of bucket ids]
+    uint2* tasks;
+    uint8_t *task_out, *buckets, *segpart, *winsum;
 };
 
 static int msm_alloc(snarkv_ctx* ctx, size_t n, void* d_status, MsmWork& wk) {
@@ -289,7 +368,13 @@ static int msm_alloc(snarkv_ctx* ctx, size_t n, void* d_status, MsmWork& wk) {
     wk.buckets = (uint8_t*)ctx->wsget(WS_BUCKETS, nbk * 128);
     wk.segpart = (uint8_t*)ctx->wsget(WS_SEGPART, (size_t)pl.W * pl.J * 128);
     wk.winsum = (uint8_t*)ctx->wsget(WS_WINSUM, (size_t)pl.W * 128);
-    if (!wk.status || !wk.counts || !wk.offsets || !wk.cursor || !wk.sorted || !wk.buckets || !wk.segpart || !wk.winsum)
+    wk.task_base = (uint32_t*)ctx->wsget(WS_TASK_BASE, nbk * 4);
+    wk.window_tasks = (uint32_t*)ctx->wsget(WS_WINDOW_TASKS, (size_t)pl.W * 4);
+    wk.big = (uint32_t*)ctx->wsget(WS_BIG, (nbk + 1) * 4);
+    wk.tasks = (uint2*)ctx->wsget(WS_TASKS, (size_t)pl.W * pl.cap * 8);
+    wk.task_out = (uint8_t*)ctx->wsget(WS_TASK_OUT, (size_t)pl.W * pl.cap * 128);
+    if (!wk.status || !wk.counts || !wk.offsets || !wk.cursor || !wk.sorted || !wk.buckets || !wk.segpart || !wk.winsum ||
+        !wk.task_base || !wk.window_tasks || !wk.big || !wk.tasks || !wk.task_out)
         return SNARKV_ERR_CUDA;
     return SNARKV_OK;
 }
@@ -311,8 +396,11 @@ static int msm_sort_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* d_scal
     }
     {
         Stage sg(ctx, "msm_scan");
-        k_scan<<<pl.W, 1024, 0, st>>>(wk.counts, wk.offsets, wk.cursor, pl.NB);
+        k_scan<<<pl.W, 1024, 0, st>>>(wk.counts, wk.offsets, wk.cursor, wk.task_base, wk.window_tasks, pl.NB, pl.T);
         SNARKV_LAUNCH_CHECK(ctx, "k_scan");
+        sg.launched();
+        k_build_tasks<<<(unsigned)((nbk + 255) / 256), 256, 0, st>>>(wk.counts, wk.task_base, pl.NB, (uint32_t)nbk, pl.T, pl.cap, wk.tasks);
+        SNARKV_LAUNCH_CHECK(ctx, "k_build_tasks");
         sg.launched();
     }
     {
@@ -346,9 +434,23 @@ static int msm_point_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* d_poi
     }
     {
         Stage sg(ctx, "msm_bucket_accumulate");
-        const uint32_t total = (uint32_t)nbk;
-        k_bucket_accumulate<<<(total + 127) / 128, 128, 0, st>>>(points, wk.sorted, wk.offsets, wk.counts, n, pl.NB, total, wk.buckets);
+        dim3 grid((pl.cap + 127) / 128, pl.W);
+        k_bucket_accumulate<<<grid, 128, 0, st>>>(points, wk.sorted, wk.offsets, wk.counts, wk.tasks, wk.window_tasks, n, pl.NB, pl.T,
+                                                 pl.cap, wk.task_out);
         SNARKV_LAUNCH_CHECK(ctx, "k_bucket_accumulate");
+        sg.launched();
+    }
+    {
+        Stage sg(ctx, "msm_bucket_merge");
+        const uint32_t total = (uint32_t)nbk;
+        SNARKV_CUDA_TRY(ctx, cudaMemsetAsync(wk.big, 0, 4, st));
+        k_bucket_merge<<<(total + 127) / 128, 128, 0, st>>>(wk.task_out, wk.counts, wk.task_base, pl.NB, total, pl.T, pl.cap, wk.buckets,
+                                                            wk.big, wk.big + 1);
+        SNARKV_LAUNCH_CHECK(ctx, "k_bucket_merge");
+        sg.launched();
+        k_bucket_merge_big<<<ctx->sm_count, 128, 0, st>>>(wk.task_out, wk.counts, wk.task_base, pl.NB, pl.T, pl.cap, wk.buckets, wk.big,
+                                                          wk.big + 1);
+        SNARKV_LAUNCH_CHECK(ctx, "k_bucket_merge_big");
         sg.launched();
     }
     {
@@ -383,7 +485,8 @@ int msm_run_device(snarkv_ctx* ctx, const void* d_scalars, const void* d_points,
 
 // snarkv_g1_msm: host slices in, 64-byte affine result out.  Scalars go first; the (2x larger) point copy is issued after
 // the sort kernels are queued so that the copy engine and the SMs overlap.
-int msm_run_host(snarkv_ctx* ctx, const uint8_t* scalars, const uint8_t* points, size_t n, int format, int flags, uint8_t* out) {
+int msm_run_host(snarkv_ctx* ctx, const uint8_t* scalars, const uint8_t* points, size_t n, int format, int flags, uint8_t* out,
+                 void* d_out_jacobian) {
     const int check = (flags & SNARKV_CHECK_INPUTS) ? 1 : 0;
     MsmWork wk;
     int rc = msm_alloc(ctx, n, nullptr, wk);
@@ -399,14 +502,19 @@ int msm_run_host(snarkv_ctx* ctx, const uint8_t* scalars, const uint8_t* points,
     SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_p, points, n * 64, cudaMemcpyHostToDevice, ctx->copy_stream));
     SNARKV_CUDA_TRY(ctx, cudaEventRecord(ctx->copy_done, ctx->copy_stream));
     SNARKV_CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->copy_done, 0));
-    rc = msm_point_phase(ctx, wk, d_p, n, format, format, check, d_o, nullptr);
+    rc = msm_point_phase(ctx, wk, d_p, n, format, format, check, out ? d_o : nullptr, d_out_jacobian);
     if (rc) return rc;
     int status = 0;
-    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(out, d_o, 64, cudaMemcpyDeviceToHost, st));
+    if (out) SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(out, d_o, 64, cudaMemcpyDeviceToHost, st));
     SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(&status, wk.status, 4, cudaMemcpyDeviceToHost, st));
     SNARKV_CUDA_TRY(ctx, cudaStreamSynchronize(st));
     if (status != 0) return ctx->fail(status, status == SNARKV_ERR_BAD_SCALAR ? "scalar is not a canonical Fr" : "point is not a valid G1Affine");
     return SNARKV_OK;
+}
+
+void msm_plan_query(snarkv_ctx* ctx, size_t n, uint32_t out[4]) {
+    const MsmPlan pl = make_plan(n ? n : 1, ctx->window_bits);
+    out[0] = pl.c; out[1] = pl.W; out[2] = pl.NB; out[3] = pl.T;
 }
 
 int msm_fold_partials_device(snarkv_ctx* ctx, const void* d_partials, size_t k, int format, void* d_out_affine) {
