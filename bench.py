@@ -165,9 +165,8 @@ def main():
     dev = torch.device("cuda", local_rank)
 
     n_total = 1 << args.log_n
-    chunk = (n_total + world - 1) // world           # util/msm.rs:322 chunk_size = ceil(n / threads)
-    lo = min(rank * chunk, n_total)
-    n_local = min(chunk, n_total - lo)
+    from snark_verifier_b200.sharding import chunk_bounds
+    lo, n_local = chunk_bounds(n_total, world, rank)   # util/msm.rs:322 chunk_size = ceil(n / threads)
 
     L = sv.CudaLoader(local_rank)
     if args.window_bits:

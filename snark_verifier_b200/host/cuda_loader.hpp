@@ -1,0 +1,167 @@
+// cuda_loader.hpp — C++ host mirror of the reference's Loader / Msm / Decider surface over the C ABI (include/snarkv_cuda.h).
+//
+// The reference is Rust; this image has no Rust toolchain, so the host side above the C ABI is C++ with the reference's names
+// and semantics (paths relative to /root/reference/snark-verifier/src):
+//   CudaLoader::multi_scalar_multiplication  <->  EcPointLoader::multi_scalar_multiplication  loader.rs:108-113, native.rs:61-71
+//   CudaLoader::ec_point_assert_eq           <->  native.rs:50-59
+//   Msm                                      <->  util/msm.rs:20-128 (constant / scalars / bases, scale, push w/ dedupe, evaluate)
+//   KzgDecidingKey, KzgAccumulator           <->  pcs/kzg/decider.rs:6-42, pcs/kzg/accumulator.rs:6-26
+//   KzgAs::{decide, decide_all, verify}      <->  pcs/kzg/decider.rs:70-93, pcs/kzg/accumulation.rs:41-63
+//   AssertionFailure                         <->  Error::AssertionFailure (lib.rs:18-28)
+// Loaded values are plain host values exactly as NativeLoader keeps them (native.rs:44,75): Fr = 32 bytes, G1Affine = 64 bytes,
+// canonical little-endian (SNARKV_CANONICAL).  There is no arithmetic in this header except the Fr bookkeeping of `Msm`, which
+// the caller supplies through the tiny `FrOps` policy (the reference does that part with halo2curves' Fr on the host as well).
+#pragma once
+#include <array>
+#include <cstdint>
+#include <cstring>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/snarkv_cuda.h"
+
+namespace snarkv {
+
+using Fr = std::array<uint8_t, 32>;        // PrimeField::to_repr()
+using G1Affine = std::array<uint8_t, 64>;  // x || y, identity = (0,0)
+using G2Affine = std::array<uint8_t, 128>;
+using Gt = std::array<uint8_t, 384>;
+
+struct Error : std::runtime_error { using std::runtime_error::runtime_error; };
+struct AssertionFailure : Error { using Error::Error; };   // Error::AssertionFailure(String)
+struct CudaError : Error { using Error::Error; };          // no device / runtime failure: never replaced by a CPU path
+
+class CudaLoader {
+  public:
+    explicit CudaLoader(int device = 0) {
+        if (snarkv_init(device, &ctx_) != SNARKV_OK || !ctx_) throw CudaError("snarkv_init failed: no sm_100 GPU (no CPU fallback)");
+    }
+    ~CudaLoader() { snarkv_destroy(ctx_); }
+    CudaLoader(const CudaLoader&) = delete;
+    CudaLoader& operator=(const CudaLoader&) = delete;
+
+    G1Affine ec_point_load_const(const G1Affine& value) const { return value; }
+    void ec_point_assert_eq(const std::string& annotation, const G1Affine& lhs, const G1Affine& rhs) const {
+        if (lhs != rhs) throw AssertionFailure(annotation);
+    }
+    // pairs: (&scalar, &base) exactly like `&[(&LoadedScalar, &LoadedEcPoint)]`
+    G1Affine multi_scalar_multiplication(const std::vector<std::pair<const Fr*, const G1Affine*>>& pairs) {
+        std::vector<uint8_t> s(pairs.size() * 32), p(pairs.size() * 64);
+        for (size_t i = 0; i < pairs.size(); ++i) {
+            memcpy(&s[32 * i], pairs[i].first->data(), 32);
+            memcpy(&p[64 * i], pairs[i].second->data(), 64);
+        }
+        return msm(s.data(), p.data(), pairs.size());
+    }
+    G1Affine msm(const uint8_t* scalars, const uint8_t* points, size_t n, int flags = 0) {
+        G1Affine out;
+        check(snarkv_g1_msm(ctx_, scalars, points, n, SNARKV_CANONICAL, flags, out.data()), "multi_scalar_multiplication");
+        return out;
+    }
+    snarkv_ctx* raw() { return ctx_; }
+    void check(int rc, const char* what) {
+        if (rc == SNARKV_OK) return;
+        std::string msg = std::string(what) + ": " + snarkv_last_error(ctx_) + " (rc=" + std::to_string(rc) + ")";
+        if (rc == SNARKV_ERR_CUDA) throw CudaError(msg);
+        throw Error(msg);
+    }
+
+  private:
+    snarkv_ctx* ctx_ = nullptr;
+};
+
+// Fr bookkeeping policy for Msm: the caller provides add/mul on canonical 32-byte scalars (any bignum will do).
+struct FrOps {
+    Fr (*add)(const Fr&, const Fr&);
+    Fr (*mul)(const Fr&, const Fr&);
+    Fr one;
+};
+
+// util/msm.rs:20-24
+class Msm {
+  public:
+    Msm(CudaLoader& loader, const FrOps& ops) : loader_(&loader), ops_(&ops) {}
+    static Msm constant(CudaLoader& l, const FrOps& o, const Fr& c) { Msm m(l, o); m.constant_ = c; return m; }   // :46-52
+    static Msm base(CudaLoader& l, const FrOps& o, const G1Affine& b) {                                              // :54-61
+        Msm m(l, o); m.scalars_.push_back(o.one); m.bases_.push_back(b); return m;
+    }
+    size_t size() const { return bases_.size(); }
+    Msm& scale(const Fr& factor) {                                                                                   // :100-107
+        if (constant_) constant_ = ops_->mul(*constant_, factor);
+        for (auto& s : scalars_) s = ops_->mul(s, factor);
+        return *this;
+    }
+    void push(const Fr& scalar, const G1Affine& base) {                                                              // :109-116
+        for (size_t i = 0; i < bases_.size(); ++i)
+            if (bases_[i] == base) { scalars_[i] = ops_->add(scalars_[i], scalar); return; }
+        scalars_.push_back(scalar);
+        bases_.push_back(base);
+    }
+    Msm& extend(const Msm& other) {                                                                                  // :118-128
+        if (other.constant_) constant_ = constant_ ? ops_->add(*constant_, *other.constant_) : *other.constant_;
+        for (size_t i = 0; i < other.bases_.size(); ++i) push(other.scalars_[i], other.bases_[i]);
+        return *this;
+    }
+    // evaluate(gen): prepend (constant, gen) and call the loader's MSM                                               // :81-98
+    G1Affine evaluate(const std::optional<G1Affine>& gen) const {
+        std::vector<std::pair<const Fr*, const G1Affine*>> pairs;
+        if (constant_) {
+            if (!gen) throw Error("Msm::evaluate: constant term without a generator");  // the reference unwraps None
+            pairs.emplace_back(&*constant_, &*gen);
+        }
+        for (size_t i = 0; i < bases_.size(); ++i) pairs.emplace_back(&scalars_[i], &bases_[i]);
+        return loader_->multi_scalar_multiplication(pairs);
+    }
+
+  private:
+    CudaLoader* loader_;
+    const FrOps* ops_;
+    std::optional<Fr> constant_;
+    std::vector<Fr> scalars_;
+    std::vector<G1Affine> bases_;
+};
+
+struct KzgAccumulator { G1Affine lhs, rhs; };            // pcs/kzg/accumulator.rs:6-26
+struct KzgDecidingKey { G1Affine g; G2Affine g2, s_g2; };  // pcs/kzg/decider.rs:6-42 (svk.g, g2, s_g2)
+
+// KzgAs<Bn256, MOS> restricted to the hot path
+class KzgAs {
+  public:
+    static constexpr const char* ASSERTION = "e(lhs, g2)\xC2\xB7" "e(rhs, -s_g2) == O";   // decider.rs:81
+    KzgAs(CudaLoader& loader, const KzgDecidingKey& dk) : loader_(&loader) {
+        loader.check(snarkv_kzg_set_deciding_key(loader.raw(), dk.g.data(), dk.g2.data(), dk.s_g2.data()), "KzgDecidingKey");
+    }
+    void decide(const KzgAccumulator& acc) { decide_all({acc}); }                            // decider.rs:70-82
+    void decide_all(const std::vector<KzgAccumulator>& accs) {                              // decider.rs:84-93
+        if (accs.empty()) return;
+        std::vector<uint8_t> lhs(accs.size() * 64), rhs(accs.size() * 64), accept(accs.size());
+        for (size_t i = 0; i < accs.size(); ++i) {
+            memcpy(&lhs[64 * i], accs[i].lhs.data(), 64);
+            memcpy(&rhs[64 * i], accs[i].rhs.data(), 64);
+        }
+        loader_->check(snarkv_kzg_decide_batch(loader_->raw(), lhs.data(), rhs.data(), accs.size(), SNARKV_CANONICAL, accept.data(), nullptr),
+                       "decide");
+        for (uint8_t a : accept)
+            if (a != 1) throw AssertionFailure(ASSERTION);
+    }
+    // AccumulationScheme::verify: (sum r^i lhs_i, sum r^i rhs_i)                              accumulation.rs:41-63
+    KzgAccumulator verify(const std::vector<KzgAccumulator>& instances, const Fr& r) {
+        std::vector<uint8_t> lhs(instances.size() * 64), rhs(instances.size() * 64);
+        for (size_t i = 0; i < instances.size(); ++i) {
+            memcpy(&lhs[64 * i], instances[i].lhs.data(), 64);
+            memcpy(&rhs[64 * i], instances[i].rhs.data(), 64);
+        }
+        KzgAccumulator out;
+        loader_->check(snarkv_kzg_accumulate(loader_->raw(), lhs.data(), rhs.data(), instances.size(), r.data(), SNARKV_CANONICAL,
+                                             out.lhs.data(), out.rhs.data()), "KzgAs::verify");
+        return out;
+    }
+
+  private:
+    CudaLoader* loader_;
+};
+
+}  // namespace snarkv

@@ -349,3 +349,23 @@ def test_accumulate_256_vs_oracle(kzg, golden):
     ol, orr = oracle.kzg_accumulate(lhs, rhs, n, r)
     assert (out.lhs, out.rhs) == (ol, orr)
     kzg.decide(out)
+
+
+def test_cpp_host_mirror(tmp_path, golden):
+    """Compile and run the C++ mirror of the reference's Loader/Decider surface (host/cuda_loader.hpp) against golden data."""
+    import os, struct, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "host_mirror_test"
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-o", str(exe), os.path.join(root, "tests", "host_mirror_test.cpp"),
+                           "-L" + os.path.join(root, "snark_verifier_b200"), "-lsnarkv_cuda",
+                           "-Wl,-rpath," + os.path.join(root, "snark_verifier_b200")])
+    case = golden("msm")[3]
+    g = golden("pairing")
+    checks = {c["name"]: c for c in g["checks"]}
+    blob = struct.pack("<I", case["n"]) + H(case["scalars"]) + H(case["points"]) + H(case["expected"])
+    blob += H(g["g2_generator"]) + H(g["s_g2"])
+    blob += H(checks["valid_0"]["lhs"]) + H(checks["valid_0"]["rhs"]) + H(checks["tampered_rhs"]["rhs"])
+    inp = tmp_path / "in.bin"
+    inp.write_bytes(blob)
+    out = subprocess.run([str(exe), str(inp)], capture_output=True, text=True)
+    assert out.returncode == 0 and "host mirror ok" in out.stdout, out.stderr
