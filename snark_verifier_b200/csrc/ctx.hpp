@@ -33,6 +33,7 @@ enum WsSlot : int {
     WS_TASKS,             // W x cap uint2
     WS_TASK_OUT,          // W x cap x 128 B
     WS_BIG,               // 1 + W x NB u32
+    WS_ORDER,             // W x cap u32
     WS_STATUS,            // 4 B
     WS_OUT,               // small outputs (affine 64 + jacobian 96)
     WS_IO_A,              // staging for host-buffer entry points

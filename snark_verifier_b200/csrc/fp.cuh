@@ -11,6 +11,7 @@
 #pragma once
 #include <cstdint>
 
+#include "fp_inv.cuh"
 #include "fp_ptx.inc"
 
 namespace snarkv {
@@ -148,6 +149,31 @@ template <Field F> __device__ __noinline__ Fp<F> fp_inv(const Fp<F>& a) {
         if ((e[i >> 5] >> (i & 31)) & 1u) r = fp_mul(r, a);
     }
     return r;
+}
+
+// R^3 mod m
+template <Field F> __device__ __forceinline__ Fp<F> fp_r3() {
+    Fp<F> r;
+    if constexpr (F == FQ) { constexpr uint32_t m[8] = SNARKV_FQ_R3_LIMBS;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.v[i] = m[i]; }
+    else { constexpr uint32_t m[8] = SNARKV_FR_R3_LIMBS;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.v[i] = m[i]; }
+    return r;
+}
+// Inverse on a serial critical path: binary extended GCD (fp_inv.cuh) on the raw Montgomery value aR gives (aR)^-1;
+// one Montgomery multiplication by R^3 turns it into a^-1 R.  Data-dependent control flow: use from ONE thread (or lanes
+// holding identical data), not in throughput kernels.
+template <Field F> __device__ __noinline__ Fp<F> fp_inv_serial(const Fp<F>& a) {
+    U256 x, p;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { x.v[i] = a.v[i]; p.v[i] = fp_mod_limb<F>(i); }
+    U256 y = u256_inv_mod(x, p);
+    Fp<F> t;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t.v[i] = y.v[i];
+    return fp_mul(t, fp_r3<F>());
 }
 
 // ---- 128-bit vectorised global memory access ----------------------------------------------------------------------------

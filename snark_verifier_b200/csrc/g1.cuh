@@ -186,6 +186,88 @@ __device__ __forceinline__ G1Affine xyzz_to_affine(const G1Xyzz& p) {
     return r;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// 4-lane point arithmetic for serial critical paths (the window-combining Horner chain of util/msm.rs:285-287 and the fold
+// of per-GPU partials, util/msm.rs:333-335).  Lanes 0..3 of a warp hold IDENTICAL copies of the operands; the independent
+// field multiplications of each formula are computed one per lane and exchanged with shuffles, so a doubling is 3 and an
+// addition 4 dependent multiplications deep instead of 9 and 14.  ONE warp calls these together; every aligned group of four lanes computes
+// the same thing (`lane` = threadIdx.x & 3), lanes 0..3 publish through the 4-entry shared scratch `xch`.
+// ---------------------------------------------------------------------------------------------------------------------
+// exchange: lane k (< 4) publishes its product in shared memory, everyone reads all four (cheaper than shuffles here: the
+// compiler wraps every partial-convergence shuffle in a WARPSYNC/ENDCOLLECTIVE pair, ~750 cycles per 8-word broadcast).
+struct Fq4 { Fq v[4]; };
+__device__ __forceinline__ Fq4 fq_exchange4(Fq* xch, const Fq& mine) {
+    __syncwarp();
+    if (threadIdx.x < 4) fp_store<FQ>(&xch[threadIdx.x], mine);
+    __syncwarp();
+    Fq4 o;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint4* q = reinterpret_cast<const uint4*>(&xch[k]);
+        uint4 lo = q[0], hi = q[1];
+        o.v[k].v[0] = lo.x; o.v[k].v[1] = lo.y; o.v[k].v[2] = lo.z; o.v[k].v[3] = lo.w;
+        o.v[k].v[4] = hi.x; o.v[k].v[5] = hi.y; o.v[k].v[6] = hi.z; o.v[k].v[7] = hi.w;
+    }
+    return o;
+}
+__device__ __forceinline__ Fq fq_sel4(int lane, const Fq& a0, const Fq& a1, const Fq& a2, const Fq& a3) {
+    Fq r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.v[i] = lane == 0 ? a0.v[i] : lane == 1 ? a1.v[i] : lane == 2 ? a2.v[i] : a3.v[i];
+    return r;
+}
+
+static __device__ __noinline__ G1Xyzz xyzz_dbl_x4(const G1Xyzz& p, int lane, Fq* xch) {
+    if (xyzz_is_identity(p)) return p;
+    const Fq u = fp_dbl(p.y);
+    Fq4 r = fq_exchange4(xch, fp_mul(fq_sel4(lane, u, p.x, u, p.x), fq_sel4(lane, u, p.x, u, p.x)));      // V = U^2 | XX = X^2
+    const Fq v = r.v[0];
+    const Fq m = fp_add(fp_dbl(r.v[1]), r.v[1]);
+    r = fq_exchange4(xch, fp_mul(fq_sel4(lane, u, p.x, m, v), fq_sel4(lane, v, v, m, p.zz)));             // W | S | M^2 | ZZ3
+    const Fq w = r.v[0], s = r.v[1];
+    G1Xyzz o;
+    o.zz = r.v[3];
+    o.x = fp_sub(r.v[2], fp_dbl(s));
+    r = fq_exchange4(xch, fp_mul(fq_sel4(lane, m, w, w, w), fq_sel4(lane, fp_sub(s, o.x), p.y, p.zzz, p.zzz)));  // M(S-X3) | W Y | W ZZZ
+    o.y = fp_sub(r.v[0], r.v[1]);
+    o.zzz = r.v[2];
+    return o;
+}
+static __device__ __noinline__ G1Xyzz xyzz_add_x4(const G1Xyzz& a, const G1Xyzz& b, int lane, Fq* xch) {
+    if (xyzz_is_identity(a)) return b;
+    if (xyzz_is_identity(b)) return a;
+    Fq4 r = fq_exchange4(xch, fp_mul(fq_sel4(lane, a.x, b.x, a.y, b.y), fq_sel4(lane, b.zz, a.zz, b.zzz, a.zzz)));  // U1 | U2 | S1 | S2
+    const Fq u1 = r.v[0], s1 = r.v[2];
+    const Fq p = fp_sub(r.v[1], u1), rr = fp_sub(r.v[3], s1);
+    if (fp_is_zero(p)) {
+        if (fp_is_zero(rr)) return xyzz_dbl_x4(a, lane, xch);
+        return xyzz_identity();
+    }
+    r = fq_exchange4(xch, fp_mul(fq_sel4(lane, p, rr, a.zz, a.zzz), fq_sel4(lane, p, rr, b.zz, b.zzz)));           // PP | R^2 | ZZ1 ZZ2 | ZZZ1 ZZZ2
+    const Fq pp = r.v[0], r2 = r.v[1], zz12 = r.v[2], zzz12 = r.v[3];
+    r = fq_exchange4(xch, fp_mul(fq_sel4(lane, p, u1, zz12, zz12), pp));                                          // PPP | Q | ZZ3
+    const Fq ppp = r.v[0], q = r.v[1];
+    G1Xyzz o;
+    o.zz = r.v[2];
+    o.x = fp_sub(fp_sub(r2, ppp), fp_dbl(q));
+    r = fq_exchange4(xch, fp_mul(fq_sel4(lane, rr, s1, zzz12, zzz12), fq_sel4(lane, fp_sub(q, o.x), ppp, ppp, ppp)));  // R(Q-X3) | S1 PPP | ZZZ3
+    o.y = fp_sub(r.v[0], r.v[1]);
+    o.zzz = r.v[2];
+    return o;
+}
+// to_affine with the serial (binary-GCD) inverse; every lane computes the same value
+static __device__ __noinline__ G1Affine xyzz_to_affine_serial(const G1Xyzz& p) {
+    G1Affine r;
+    if (xyzz_is_identity(p)) {
+        r.x = fp_zero<FQ>(); r.y = fp_zero<FQ>();
+        return r;
+    }
+    Fq t = fp_inv_serial(fp_mul(p.zz, p.zzz));
+    r.x = fp_mul(p.x, fp_mul(t, p.zzz));
+    r.y = fp_mul(p.y, fp_mul(t, p.zz));
+    return r;
+}
+
 // y^2 == x^3 + 3 (Montgomery-form inputs); the identity (0,0) is accepted — `CurveAffine::from_xy` semantics plus
 // halo2curves' identity encoding
 __device__ __forceinline__ bool g1_affine_is_on_curve(const G1Affine& p) {

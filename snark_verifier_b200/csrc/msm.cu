@@ -33,17 +33,12 @@ struct MsmPlan {
 };
 
 static int choose_window_bits(size_t n) {
-    // few, long buckets keep the one-thread-per-bucket accumulate kernel balanced; enough buckets keep it occupied.
-    if (n < (1u << 6)) return 4;
-    if (n < (1u << 8)) return 5;
-    if (n < (1u << 10)) return 7;
-    if (n < (1u << 12)) return 9;
-    if (n < (1u << 14)) return 10;
-    if (n < (1u << 16)) return 11;
-    if (n < (1u << 18)) return 12;
-    if (n < (1u << 20)) return 13;
-    if (n < (1u << 22)) return 14;
-    if (n < (1u << 24)) return 15;
+    // Measured sweep on B200 (profiles/r01_window_sweep_first.txt).  Window sizes whose top window holds only 1-2 significant
+    // bits of a 254-bit scalar (c = 9, 11, 12, 14, 18) funnel n/4 terms into three counters/buckets and are avoided.
+    if (n < (1u << 8)) return 6;
+    if (n < (1u << 12)) return 8;
+    if (n < (1u << 17)) return 13;
+    if (n < (1u << 21)) return 15;
     return 16;
 }
 
@@ -180,6 +175,53 @@ __global__ void __launch_bounds__(256) k_build_tasks(const uint32_t* __restrict_
     for (uint32_t j = 0; j < parts; ++j) out[j] = make_uint2(b, j);
 }
 
+// K2c: order each window's tasks by length (longest first) with a shared-memory counting sort over 1024 quantised length
+// bins, so that the 32 tasks of a warp run for (almost) the same number of additions and the long tasks start first.
+#define SNARKV_ORDER_BINS 1024
+__global__ void __launch_bounds__(1024) k_order_tasks(const uint32_t* __restrict__ counts, const uint2* __restrict__ tasks,
+                                                      const uint32_t* __restrict__ window_tasks, uint32_t NB, uint32_t T, uint32_t cap,
+                                                      uint32_t* __restrict__ order) {
+    __shared__ uint32_t hist[SNARKV_ORDER_BINS];
+    __shared__ uint32_t warp_tot[32];
+    const uint32_t w = blockIdx.x, t = threadIdx.x;
+    const uint32_t nt = window_tasks[w];
+    const uint2* tw = tasks + (size_t)w * cap;
+    hist[t] = 0;
+    __syncthreads();
+    auto bin_of = [&](uint2 task) -> uint32_t {
+        const uint32_t len = min(T, counts[(size_t)w * NB + task.x] - task.y * T);       // 1..T
+        const uint32_t q = (uint32_t)(((uint64_t)len * (SNARKV_ORDER_BINS - 1)) / T);    // 0..BINS-1
+        return (SNARKV_ORDER_BINS - 1) - q;                                              // longest first
+    };
+    for (uint32_t i = t; i < nt; i += blockDim.x) atomicAdd(&hist[bin_of(tw[i])], 1u);
+    __syncthreads();
+    // exclusive scan of the 1024 bins (one per thread)
+    const uint32_t v = hist[t];
+    uint32_t incl = v;
+    const uint32_t lane = t & 31, wid = t >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += u;
+    }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t x = warp_tot[lane], ix = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t u = __shfl_up_sync(0xffffffffu, ix, o);
+            if (lane >= (uint32_t)o) ix += u;
+        }
+        warp_tot[lane] = ix - x;
+    }
+    __syncthreads();
+    hist[t] = warp_tot[wid] + incl - v;
+    __syncthreads();
+    uint32_t* ow = order + (size_t)w * cap;
+    for (uint32_t i = t; i < nt; i += blockDim.x) ow[atomicAdd(&hist[bin_of(tw[i])], 1u)] = i;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // K4: bucket accumulation — the multi-scalar multiplication proper.  `buckets[scalar - 1].add_assign(base)` of
 // util/msm.rs:291-296, with Bucket::{None, Affine, Projective} (util/msm.rs:228-246) collapsed into the XYZZ identity test.
@@ -188,11 +230,12 @@ __global__ void __launch_bounds__(256) k_build_tasks(const uint32_t* __restrict_
 __global__ void __launch_bounds__(128) k_bucket_accumulate(const uint8_t* __restrict__ points, const uint32_t* __restrict__ sorted,
                                                            const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts,
                                                            const uint2* __restrict__ tasks, const uint32_t* __restrict__ window_tasks,
-                                                           size_t n, uint32_t NB, uint32_t T, uint32_t cap,
-                                                           uint8_t* __restrict__ task_out) {
+                                                           const uint32_t* __restrict__ order, size_t n, uint32_t NB, uint32_t T,
+                                                           uint32_t cap, uint8_t* __restrict__ task_out) {
     const uint32_t w = blockIdx.y;
-    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= window_tasks[w]) return;
+    const uint32_t rank = blockIdx.x * blockDim.x + threadIdx.x;
+    if (rank >= window_tasks[w]) return;
+    const uint32_t slot = order[(size_t)w * cap + rank];
     const uint2 task = tasks[(size_t)w * cap + slot];
     const uint32_t bucket = w * NB + task.x;
     const uint32_t first = task.y * T;
@@ -201,6 +244,7 @@ __global__ void __launch_bounds__(128) k_bucket_accumulate(const uint8_t* __rest
     G1Xyzz acc = xyzz_identity();
     uint32_t e = list[0];
     G1Affine nxt = g1_affine_load(points, e & 0x7fffffffu);
+#pragma unroll 1
     for (uint32_t k = 0; k < cnt; ++k) {
         G1Affine cur = nxt;
         const uint32_t neg = e >> 31;
@@ -316,27 +360,34 @@ __device__ __forceinline__ void store_jacobian(void* out, const G1Jac& j) {
 // caller's `.to_affine()` (native.rs:70).
 __global__ void k_msm_final(const uint8_t* __restrict__ winsum, uint32_t W, uint32_t c, int format, void* out_affine,
                             void* out_jacobian) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    // one warp; every aligned group of 4 lanes runs the same 4-lane point arithmetic (g1.cuh: *_x4), thread 0 stores
+    __shared__ Fq xch[4];
+    const int lane = threadIdx.x & 3;
     G1Xyzz acc = xyzz_load(winsum, W - 1);
     for (uint32_t w = W - 1; w-- > 0;) {
-        for (uint32_t k = 0; k < c; ++k) acc = xyzz_dbl(acc);
-        acc = xyzz_add(acc, xyzz_load(winsum, w));
+        for (uint32_t k = 0; k < c; ++k) acc = xyzz_dbl_x4(acc, lane, xch);
+        acc = xyzz_add_x4(acc, xyzz_load(winsum, w), lane, xch);
     }
-    if (out_jacobian) store_jacobian(out_jacobian, xyzz_to_jacobian(acc));
-    if (out_affine) store_affine_fmt(out_affine, xyzz_to_affine(acc), format);
+    if (out_jacobian && threadIdx.x == 0) store_jacobian(out_jacobian, xyzz_to_jacobian(acc));
+    if (out_affine) {
+        G1Affine a = xyzz_to_affine_serial(acc);
+        if (threadIdx.x == 0) store_affine_fmt(out_affine, a, format);
+    }
 }
 
 // fold of per-GPU Jacobian partials (util/msm.rs:333-335) + to_affine
 __global__ void k_fold_partials(const uint8_t* __restrict__ partials, uint32_t k, int format, void* out_affine) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    __shared__ Fq xch[4];
+    const int lane = threadIdx.x & 3;
     G1Xyzz acc = xyzz_identity();
     for (uint32_t i = 0; i < k; ++i) {
         G1Jac j;
         const uint8_t* p = partials + (size_t)i * 96;
         j.x = fp_load<FQ>(p); j.y = fp_load<FQ>(p + 32); j.z = fp_load<FQ>(p + 64);
-        acc = xyzz_add(acc, jacobian_to_xyzz(j));
+        acc = xyzz_add_x4(acc, jacobian_to_xyzz(j), lane, xch);
     }
-    store_affine_fmt(out_affine, xyzz_to_affine(acc), format);
+    G1Affine a = xyzz_to_affine_serial(acc);
+    if (threadIdx.x == 0) store_affine_fmt(out_affine, a, format);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -350,6 +401,7 @@ struct MsmWork {
     uint32_t *counts, *offsets, *cursor, *sorted;
     uint32_t *task_base, *window_tasks, *big;   // big = [count | list of bucket ids]
     uint2* tasks;
+    uint32_t* order;
     uint8_t *task_out, *buckets, *segpart, *winsum;
 };
 
@@ -373,8 +425,9 @@ static int msm_alloc(snarkv_ctx* ctx, size_t n, void* d_status, MsmWork& wk) {
     wk.big = (uint32_t*)ctx->wsget(WS_BIG, (nbk + 1) * 4);
     wk.tasks = (uint2*)ctx->wsget(WS_TASKS, (size_t)pl.W * pl.cap * 8);
     wk.task_out = (uint8_t*)ctx->wsget(WS_TASK_OUT, (size_t)pl.W * pl.cap * 128);
+    wk.order = (uint32_t*)ctx->wsget(WS_ORDER, (size_t)pl.W * pl.cap * 4);
     if (!wk.status || !wk.counts || !wk.offsets || !wk.cursor || !wk.sorted || !wk.buckets || !wk.segpart || !wk.winsum ||
-        !wk.task_base || !wk.window_tasks || !wk.big || !wk.tasks || !wk.task_out)
+        !wk.task_base || !wk.window_tasks || !wk.big || !wk.tasks || !wk.task_out || !wk.order)
         return SNARKV_ERR_CUDA;
     return SNARKV_OK;
 }
@@ -401,6 +454,9 @@ static int msm_sort_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* d_scal
         sg.launched();
         k_build_tasks<<<(unsigned)((nbk + 255) / 256), 256, 0, st>>>(wk.counts, wk.task_base, pl.NB, (uint32_t)nbk, pl.T, pl.cap, wk.tasks);
         SNARKV_LAUNCH_CHECK(ctx, "k_build_tasks");
+        sg.launched();
+        k_order_tasks<<<pl.W, 1024, 0, st>>>(wk.counts, wk.tasks, wk.window_tasks, pl.NB, pl.T, pl.cap, wk.order);
+        SNARKV_LAUNCH_CHECK(ctx, "k_order_tasks");
         sg.launched();
     }
     {
@@ -435,8 +491,8 @@ static int msm_point_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* d_poi
     {
         Stage sg(ctx, "msm_bucket_accumulate");
         dim3 grid((pl.cap + 127) / 128, pl.W);
-        k_bucket_accumulate<<<grid, 128, 0, st>>>(points, wk.sorted, wk.offsets, wk.counts, wk.tasks, wk.window_tasks, n, pl.NB, pl.T,
-                                                 pl.cap, wk.task_out);
+        k_bucket_accumulate<<<grid, 128, 0, st>>>(points, wk.sorted, wk.offsets, wk.counts, wk.tasks, wk.window_tasks, wk.order, n, pl.NB,
+                                                 pl.T, pl.cap, wk.task_out);
         SNARKV_LAUNCH_CHECK(ctx, "k_bucket_accumulate");
         sg.launched();
     }
@@ -461,10 +517,13 @@ static int msm_point_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* d_poi
         sg.launched();
     }
     {
-        Stage sg(ctx, "msm_window_combine");
+        Stage sg(ctx, "msm_window_sum");
         k_window_sum<<<pl.W, 128, 0, st>>>(wk.segpart, pl.J, wk.winsum);
         SNARKV_LAUNCH_CHECK(ctx, "k_window_sum");
         sg.launched();
+    }
+    {
+        Stage sg(ctx, "msm_final");
         k_msm_final<<<1, 32, 0, st>>>(wk.winsum, pl.W, pl.c, out_format, d_out_affine, d_out_jacobian);
         SNARKV_LAUNCH_CHECK(ctx, "k_msm_final");
         sg.launched();
