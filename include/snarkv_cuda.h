@@ -69,6 +69,10 @@ int snarkv_set_stream(snarkv_ctx* ctx, void* cuda_stream);
 /* MSM tuning: window bits c (0 = choose from n). */
 int snarkv_set_window_bits(snarkv_ctx* ctx, int c);
 
+/* KZG decide tuning: 0 = choose from N (default), 1 = one thread per check (throughput), 2 = one thread block per check
+ * (latency).  Results are identical. */
+int snarkv_set_pairing_mode(snarkv_ctx* ctx, int mode);
+
 /* ---- a1: EcPointLoader::multi_scalar_multiplication --------------------------------------------------------------------
  * Replaces `NativeLoader::multi_scalar_multiplication(pairs) -> C` (loader.rs:108-113, loader/native.rs:61-71):
  *   out = to_affine( sum_i points[i] * scalars[i] ).
@@ -126,6 +130,16 @@ int snarkv_kzg_decide_batch(snarkv_ctx* ctx, const uint8_t* lhs, const uint8_t* 
 /* Device-resident variant: d_lhs/d_rhs N x 64 B, d_accept N bytes, d_gt N x 384 B or NULL; no host synchronisation. */
 int snarkv_kzg_decide_batch_device(snarkv_ctx* ctx, const void* d_lhs, const void* d_rhs, size_t N, int format, void* d_accept,
                                    void* d_gt);
+
+/* ---- a11: batched decision by random linear combination -------------------------------------------------------------------
+ * The reference batches pairing checks this way in the EVM loader's `decide_all` (pcs/kzg/decider.rs:146-185): with powers of a
+ * challenge rho,  lhs' = sum_i rho^i lhs_i,  rhs' = sum_i rho^i rhs_i  (two MSMs), then ONE `decide(lhs', rhs')`.
+ * All N accumulators valid  =>  *accept = 1;  any invalid one  =>  *accept = 0 except with probability ~N/r over rho.
+ * rho must be unpredictable to whoever produced the accumulators (the reference hashes all the points, decider.rs:164-168;
+ * hashing stays on the host).  lhs/rhs N x 64 B and rho 32 B in `format`; out_lhs/out_rhs (64 B each, may be NULL) return the
+ * combined accumulator.  Unlike snarkv_kzg_decide_batch this cannot say WHICH accumulator failed. */
+int snarkv_kzg_decide_all_fused(snarkv_ctx* ctx, const uint8_t* lhs, const uint8_t* rhs, size_t N, const uint8_t rho[32], int format,
+                                uint8_t* accept, uint8_t out_lhs[64], uint8_t out_rhs[64]);
 
 /* ---- synthetic workload (bench / tests) ----------------------------------------------------------------------------------
  * Deterministic inputs (the test suite restates the same definition independently):

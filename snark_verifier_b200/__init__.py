@@ -56,6 +56,7 @@ C_ABI = {
     "snarkv_version": (ctypes.c_char_p, []),
     "snarkv_set_stream": (_i, [_vp, _vp]),
     "snarkv_set_window_bits": (_i, [_vp, _i]),
+    "snarkv_set_pairing_mode": (_i, [_vp, _i]),
     "snarkv_g1_msm": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp]),
     "snarkv_g1_msm_partial": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp]),
     "snarkv_g1_msm_device": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp, _vp, _vp]),
@@ -64,6 +65,7 @@ C_ABI = {
     "snarkv_kzg_accumulate": (_i, [_vp, _vp, _vp, _sz, _vp, _i, _vp, _vp]),
     "snarkv_kzg_set_deciding_key": (_i, [_vp, _vp, _vp, _vp]),
     "snarkv_kzg_decide_batch": (_i, [_vp, _vp, _vp, _sz, _i, _vp, _vp]),
+    "snarkv_kzg_decide_all_fused": (_i, [_vp, _vp, _vp, _sz, _vp, _i, _vp, _vp, _vp]),
     "snarkv_kzg_decide_batch_device": (_i, [_vp, _vp, _vp, _sz, _i, _vp, _vp]),
     "snarkv_synth_scalars_device": (_i, [_vp, _u64, _u64, _sz, _i, _vp]),
     "snarkv_synth_points_device": (_i, [_vp, _u64, _u64, _sz, _i, _vp]),
@@ -145,6 +147,9 @@ class CudaLoader:
 
     def set_stream(self, cuda_stream):
         self._check(self.lib.snarkv_set_stream(self.h, ctypes.c_void_p(cuda_stream) if cuda_stream else None), "set_stream")
+
+    def set_pairing_mode(self, mode):
+        self._check(self.lib.snarkv_set_pairing_mode(self.h, mode), "set_pairing_mode")
 
     def set_window_bits(self, c):
         self._check(self.lib.snarkv_set_window_bits(self.h, c), "set_window_bits")
@@ -329,6 +334,14 @@ class KzgAs:
         acc, _ = self.decide_batch(lhs, rhs, len(accumulators))
         if any(b != 1 for b in acc):
             raise AssertionFailure(self.ASSERTION)
+
+    def decide_all_fused(self, lhs, rhs, n, rho):
+        """RLC batching of decider.rs:146-185: one accumulate (two MSMs with powers of rho) + ONE pairing.  -> (accept, KzgAccumulator)"""
+        L = self.loader
+        acc = ctypes.create_string_buffer(1)
+        ol, orr = ctypes.create_string_buffer(64), ctypes.create_string_buffer(64)
+        L._check(L.lib.snarkv_kzg_decide_all_fused(L.h, _addr(lhs), _addr(rhs), n, bytes(rho), L.fmt, acc, ol, orr), "decide_all_fused")
+        return acc.raw[0] == 1, KzgAccumulator(ol.raw, orr.raw)
 
     def verify(self, instances, r, blind=None):  # accumulation.rs:41-63
         accs = list(instances) + ([blind] if blind is not None else [])

@@ -77,6 +77,12 @@ int snarkv_set_window_bits(snarkv_ctx* ctx, int c) {
     return SNARKV_OK;
 }
 
+int snarkv_set_pairing_mode(snarkv_ctx* ctx, int mode) {
+    if (!ctx || mode < 0 || mode > 2) return SNARKV_ERR_USAGE;
+    ctx->pairing_mode = mode;
+    return SNARKV_OK;
+}
+
 int snarkv_g1_msm_plan(snarkv_ctx* ctx, size_t n, uint32_t out[4]) {
     if (!ctx || !out) return SNARKV_ERR_USAGE;
     msm_plan_query(ctx, n, out);
@@ -238,6 +244,44 @@ int snarkv_kzg_decide_batch(snarkv_ctx* ctx, const uint8_t* lhs, const uint8_t* 
     SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(accept, d_acc, N, cudaMemcpyDeviceToHost, st));
     if (gt_out) SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(gt_out, d_gt, N * 384, cudaMemcpyDeviceToHost, st));
     SNARKV_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return SNARKV_OK;
+}
+
+// ---- fused batch decision (RLC) ---------------------------------------------------------------------------------------------
+int snarkv_kzg_decide_all_fused(snarkv_ctx* ctx, const uint8_t* lhs, const uint8_t* rhs, size_t N, const uint8_t rho[32], int format,
+                                uint8_t* accept, uint8_t out_lhs[64], uint8_t out_rhs[64]) {
+    CTX_GUARD(ctx);
+    if (!ctx->has_key) return ctx->fail(SNARKV_ERR_NO_KEY, "decide before snarkv_kzg_set_deciding_key");
+    if (!lhs || !rhs || !rho || !accept || bad_format(format)) return ctx->fail(SNARKV_ERR_USAGE, "snarkv_kzg_decide_all_fused: bad argument");
+    if (N == 0) { *accept = 1; return SNARKV_OK; }   // decide_all over an empty Vec is Ok(())
+    ctx->profile_begin_call();
+    uint8_t* d_l = (uint8_t*)ctx->wsget(WS_IO_A, N * 64);
+    uint8_t* d_r = (uint8_t*)ctx->wsget(WS_IO_B, N * 64);
+    uint8_t* d_pw = (uint8_t*)ctx->wsget(WS_IO_C, N * 32 + 32);
+    uint8_t* d_o = (uint8_t*)ctx->wsget(WS_OUT, 256);   // [lhs' | rhs' | accept]
+    if (!d_l || !d_r || !d_pw || !d_o) return SNARKV_ERR_CUDA;
+    cudaStream_t st = ctx->stream;
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_pw, rho, 32, cudaMemcpyHostToDevice, st));
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_l, lhs, N * 64, cudaMemcpyHostToDevice, st));
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_r, rhs, N * 64, cudaMemcpyHostToDevice, st));
+    int rc = fr_powers_device(ctx, d_pw, format, N, d_pw + 32);
+    if (rc) return rc;
+    // layout of d_o: [lhs' 64 | rhs' 64 | accept 1 .. pad to 132 | status(lhs MSM) 4 | status(rhs MSM) 4]
+    rc = msm_run_device(ctx, d_pw + 32, d_l, N, SNARKV_MONTGOMERY, format, format, SNARKV_CHECK_INPUTS, d_o, nullptr, d_o + 132);
+    if (rc) return rc;
+    rc = msm_run_device(ctx, d_pw + 32, d_r, N, SNARKV_MONTGOMERY, format, format, SNARKV_CHECK_INPUTS, d_o + 64, nullptr, d_o + 136);
+    if (rc) return rc;
+    rc = kzg_decide_device(ctx, d_o, d_o + 64, 1, format, d_o + 128, nullptr);
+    if (rc) return rc;
+    uint8_t host[140];
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(host, d_o, 140, cudaMemcpyDeviceToHost, st));
+    SNARKV_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    int status_l, status_r;
+    memcpy(&status_l, host + 132, 4);
+    memcpy(&status_r, host + 136, 4);
+    *accept = (status_l == 0 && status_r == 0 && host[128] == 1) ? 1 : 0;   // a non-curve accumulator rejects the batch
+    if (out_lhs) memcpy(out_lhs, host, 64);
+    if (out_rhs) memcpy(out_rhs, host + 64, 64);
     return SNARKV_OK;
 }
 

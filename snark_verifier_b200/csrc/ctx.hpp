@@ -56,6 +56,7 @@ struct snarkv_ctx {
     cudaEvent_t copy_done = nullptr;
     std::string err;
     int window_bits = 0;
+    int pairing_mode = 0;   // 0 = choose from N, 1 = one thread per check, 2 = one block per check
     uint64_t launches = 0;
     int sm_count = 148;
 
@@ -166,6 +167,7 @@ int synth_scalars_device(snarkv_ctx* ctx, uint64_t seed, uint64_t start, size_t 
 int synth_points_device(snarkv_ctx* ctx, uint64_t seed, uint64_t start, size_t n, int format, void* d_out);
 int kzg_set_key(snarkv_ctx* ctx, const uint8_t g1[64], const uint8_t g2[128], const uint8_t s_g2[128]);
 int kzg_decide_device(snarkv_ctx* ctx, const void* d_lhs, const void* d_rhs, size_t N, int format, void* d_accept, void* d_gt);
+int kzg_decide_coop_device(snarkv_ctx* ctx, const void* d_lhs, const void* d_rhs, size_t N, int format, void* d_accept, void* d_gt);
 void kzg_free_key(snarkv_ctx* ctx);
 
 }  // namespace snarkv

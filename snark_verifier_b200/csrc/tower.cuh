@@ -54,7 +54,11 @@ __device__ __forceinline__ Fq2 fq2_mul_xi(const Fq2& a) {
     return {fp_sub(fp_add(t0, a.c0), a.c1), fp_add(fp_add(t1, a.c1), a.c0)};
 }
 static __device__ __noinline__ Fq2 fq2_inv(const Fq2& a) {
+#ifdef SNARKV_TOWER_SERIAL_INV
+    Fq n = fp_inv_serial(fp_add(fp_sqr(a.c0), fp_sqr(a.c1)));
+#else
     Fq n = fp_inv(fp_add(fp_sqr(a.c0), fp_sqr(a.c1)));
+#endif
     return {fp_mul(a.c0, n), fp_neg(fp_mul(a.c1, n))};
 }
 

@@ -255,7 +255,14 @@ def kzg(loader, golden):
     return sv.KzgAs(loader, dk)
 
 
-def test_decide_golden_accept_reject_and_gt_bytes(kzg, golden):
+@pytest.fixture(params=[1, 2], ids=["thread_per_check", "block_per_check"])
+def pairing_mode(request, loader):
+    loader.set_pairing_mode(request.param)
+    yield request.param
+    loader.set_pairing_mode(0)
+
+
+def test_decide_golden_accept_reject_and_gt_bytes(kzg, golden, pairing_mode):
     g = golden("pairing")
     checks = g["checks"]
     lhs = b"".join(H(c["lhs"]) for c in checks); rhs = b"".join(H(c["rhs"]) for c in checks)
@@ -281,7 +288,7 @@ def test_decide_and_decide_all_error_behaviour(kzg, golden):
         kzg.decide_all([ok, bad, ok])
 
 
-def test_decide_batch_vs_oracle_random_mix(kzg, golden):
+def test_decide_batch_vs_oracle_random_mix(kzg, golden, pairing_mode):
     g = golden("pairing")
     s = int.from_bytes(H(g["s"]), "little")
     rng = np.random.default_rng(8)
@@ -300,7 +307,7 @@ def test_decide_batch_vs_oracle_random_mix(kzg, golden):
     assert list(acc) == [0 if i % 3 == 1 else 1 for i in range(n)]
 
 
-def test_decide_rejects_off_curve_accumulator(kzg):
+def test_decide_rejects_off_curve_accumulator(kzg, pairing_mode):
     acc, _ = kzg.decide_batch(le(1) + le(3), m.g1_to_bytes(m.G1_GEN), 1)
     assert acc == b"\x00"
 
@@ -369,3 +376,29 @@ def test_cpp_host_mirror(tmp_path, golden):
     inp.write_bytes(blob)
     out = subprocess.run([str(exe), str(inp)], capture_output=True, text=True)
     assert out.returncode == 0 and "host mirror ok" in out.stdout, out.stderr
+
+
+def test_fused_rlc_decide_all_accepts_valid_rejects_one_bad(kzg, golden):
+    """decider.rs:146-185 shape: accumulate with powers of a challenge, one pairing.  4096 accumulators (BASELINE config 3)."""
+    g = golden("pairing")
+    s = int.from_bytes(H(g["s"]), "little")
+    n = 4096
+    gen = m.g1_to_bytes(m.G1_GEN)
+    base_l = oracle.g1_mul(gen, le(s)); base_r = gen
+    a = [int.from_bytes(oracle.synth_scalars(71, i, 1), "little") for i in range(64)]
+    lhs64 = [oracle.g1_mul(base_l, le(x)) for x in a]
+    rhs64 = [oracle.g1_mul(base_r, le(x)) for x in a]
+    lhs = b"".join(lhs64[i % 64] for i in range(n)); rhs = b"".join(rhs64[i % 64] for i in range(n))
+    rho = oracle.synth_scalars(72, 0, 1)
+    ok, acc = kzg.decide_all_fused(lhs, rhs, n, rho)
+    assert ok
+    # the combined accumulator equals the oracle's accumulate on a prefix-sized instance
+    k = 200
+    ok2, acc2 = kzg.decide_all_fused(lhs[:64 * k], rhs[:64 * k], k, rho)
+    assert ok2 and (acc2.lhs, acc2.rhs) == oracle.kzg_accumulate(lhs[:64 * k], rhs[:64 * k], k, rho)
+    bad = bytearray(rhs); bad[64 * 1234:64 * 1235] = oracle.g1_mul(gen, le(a[1234 % 64] + 1))
+    ok3, _ = kzg.decide_all_fused(lhs, bytes(bad), n, rho)
+    assert not ok3
+    off = bytearray(rhs); off[64 * 7:64 * 8] = le(1) + le(3)      # not on the curve
+    ok4, _ = kzg.decide_all_fused(lhs, bytes(off), n, rho)
+    assert not ok4

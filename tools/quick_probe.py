@@ -36,3 +36,22 @@ for lg in sizes:
         st = L.stage_times()
         print("n=2^%d c=%d%s best %.3f ms %.1f Mterm/s | " % (lg, c, "*" if c == c0 else " ", best, n / best / 1e3) +
               " ".join("%s=%.3f" % (a.replace("msm_", "").replace("bucket_", "b_").replace("digits_", "d_"), b) for a, b, _ in st), flush=True)
+
+# pairing probe: both kernels
+import oracle
+from oracle import bn254_model as m
+g2 = oracle.g2_generator(); sk = 0x1234567; s_g2 = oracle.g2_mul(g2, m.fe_to_le(sk)); gen = m.g1_to_bytes(m.G1_GEN)
+kz = sv.KzgAs(L, sv.KzgDecidingKey(gen, g2, s_g2))
+L.profile(True)
+for mode in (1, 2):
+    L.set_pairing_mode(mode)
+    for N in (1, 64, 1024, 4096, 1 << 14, 1 << 16):
+        with torch.cuda.stream(stream):
+            lhs = torch.frombuffer(bytearray(oracle.g1_mul(gen, m.fe_to_le(77 * sk)) * N), dtype=torch.uint8).cuda()
+            rhs = torch.frombuffer(bytearray(oracle.g1_mul(gen, m.fe_to_le(77)) * N), dtype=torch.uint8).cuda()
+            acc = torch.zeros(N, dtype=torch.uint8, device="cuda")
+            for rep in range(2):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream); kz.decide_batch_device(lhs.data_ptr(), rhs.data_ptr(), N, acc.data_ptr()); e1.record(stream)
+                stream.synchronize()
+        print("decide mode=%d N=%d: %.3f ms  %.0f checks/s  all_accept=%s" % (mode, N, e0.elapsed_time(e1), N / e0.elapsed_time(e1) * 1e3, bool(acc.min().item() == 1)), flush=True)
