@@ -39,11 +39,15 @@ int snarkv_init(int device, snarkv_ctx** out) {
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming) != cudaSuccess) {
+        cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete c;
         return SNARKV_ERR_CUDA;
     }
+    for (cudaEvent_t& e : c->copy_done)
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
+            delete c;
+            return SNARKV_ERR_CUDA;
+        }
     c->stream = c->own_stream;
     *out = c;
     return SNARKV_OK;
@@ -57,7 +61,8 @@ void snarkv_destroy(snarkv_ctx* ctx) {
     for (int i = 0; i < WS_SLOTS; ++i)
         if (ctx->ws[i]) cudaFree(ctx->ws[i]);
     for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
-    if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
+    for (cudaEvent_t e : ctx->copy_done)
+        if (e) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;

@@ -25,6 +25,7 @@ enum WsSlot : int {
     WS_OFFSETS,           // W x NB u32
     WS_CURSOR,            // W x NB u32
     WS_SORTED,            // W x n  u32
+    WS_DIGITS,            // W x n  u32 (window-major signed digits)
     WS_BUCKETS,           // W x NB x 128 B
     WS_SEGPART,           // W x J  x 128 B
     WS_WINSUM,            // W x 128 B
@@ -53,7 +54,7 @@ struct snarkv_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // second stream for host->device copies that overlap kernels
-    cudaEvent_t copy_done = nullptr;
+    cudaEvent_t copy_done[5] = {};        // one per host chunk + one fence
     std::string err;
     int window_bits = 0;
     int pairing_mode = 0;   // 0 = choose from N, 1 = one thread per check, 2 = one block per check

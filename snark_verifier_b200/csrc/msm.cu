@@ -8,9 +8,9 @@
 // output: all windows at once, signed digits (2^(c-1) buckets per window), and a counting sort so that each bucket's
 // points are contiguous:
 //
-//   K1 digits_count       scalar -> W signed c-bit digits; histogram[w][|d|]                    (HBM-bound, 32 B/term read)
+//   K1 digits_count       scalar -> W signed c-bit digits (stored window-major) + histogram     (HBM + L2 atomics)
 //   K2 scan               per-window exclusive prefix sum of the histogram                      (tiny)
-//   K3 digits_scatter     recompute digits; sorted[w][pos] = term index | sign                  (HBM/L2-atomic bound)
+//   K3 digits_scatter     window-major: sorted[w][pos] = term index | sign, per-window L2-resident (L2-atomic bound)
 //   K4 bucket_accumulate  one thread per (window, bucket): XYZZ += gathered affine points       (IMAD-pipe bound: the MSM)
 //   K5 bucket_reduce      per window  sum_b b * B_b  by segment running sums                    (small)
 //   K6 window_sum / final Horner over windows with c doublings each, to_affine                  (latency, 1 thread)
@@ -21,6 +21,8 @@
 #include "g1.cuh"
 
 namespace snarkv {
+
+#define SNARKV_HOST_CHUNKS 4
 
 struct MsmPlan {
     uint32_t c;    // window bits
@@ -33,13 +35,14 @@ struct MsmPlan {
 };
 
 static int choose_window_bits(size_t n) {
-    // Measured sweep on B200 (profiles/r01_window_sweep_first.txt).  Window sizes whose top window holds only 1-2 significant
+    // Measured sweeps on B200 (profiles/r01_window_sweep_*.txt).  Window sizes whose top window holds only 1-2 significant
     // bits of a 254-bit scalar (c = 9, 11, 12, 14, 18) funnel n/4 terms into three counters/buckets and are avoided.
     if (n < (1u << 8)) return 6;
     if (n < (1u << 12)) return 8;
     if (n < (1u << 17)) return 13;
-    if (n < (1u << 21)) return 15;
-    return 16;
+    if (n < (1u << 20)) return 15;
+    if (n < (1u << 23)) return 16;
+    return 17;
 }
 
 static MsmPlan make_plan(size_t n, int c_override) {
@@ -81,15 +84,15 @@ __global__ void k_points_prepare(const uint8_t* __restrict__ in, uint8_t* __rest
 // K1 / K3: signed-digit decomposition.  `windowed_scalar` of util/msm.rs:271-281 extracts unsigned c-bit digits from the
 // canonical little-endian repr; here each digit d in [0, 2^c) plus the carry from below is mapped to (-2^(c-1), 2^(c-1)].
 // ---------------------------------------------------------------------------------------------------------------------
-template <bool SCATTER>
+// K1: every scalar -> W signed digits, stored window-major (digits[w][i] = |d| | sign << 31, coalesced) + histogram.
 __global__ void __launch_bounds__(256) k_digits(const uint8_t* __restrict__ scalars, size_t n, int format, int check, uint32_t c,
                                                 uint32_t W, uint32_t NB, uint32_t* __restrict__ counters,
-                                                uint32_t* __restrict__ sorted, int* __restrict__ status) {
+                                                uint32_t* __restrict__ digits, int* __restrict__ status) {
     const uint32_t mask = (1u << c) - 1u;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         Fr s = fp_load<FR>(scalars + i * 32);
         if (format == SNARKV_MONTGOMERY) s = fp_from_mont(s);
-        else if (check && !SCATTER && !fp_is_canonical(s)) atomicCAS(status, 0, SNARKV_ERR_BAD_SCALAR);
+        else if (check && !fp_is_canonical(s)) atomicCAS(status, 0, SNARKV_ERR_BAD_SCALAR);
         uint32_t carry = 0;
         for (uint32_t w = 0; w < W; ++w) {
             uint32_t d = (s.v[0] & mask) + carry;
@@ -103,15 +106,24 @@ __global__ void __launch_bounds__(256) k_digits(const uint8_t* __restrict__ scal
                 neg = 1u;
                 carry = 1u;
             } else carry = 0u;
-            if (d != 0) {
-                uint32_t slot = w * NB + (d - 1u);
-                if (!SCATTER) atomicAdd(&counters[slot], 1u);
-                else {
-                    uint32_t pos = atomicAdd(&counters[slot], 1u);
-                    sorted[(size_t)w * n + pos] = (uint32_t)i | (neg << 31);
-                }
-            }
+            digits[(size_t)w * n + i] = d | (neg << 31);
+            if (d != 0) atomicAdd(&counters[w * NB + (d - 1u)], 1u);
         }
+    }
+}
+
+// K3: window-major scatter.  Consecutive blocks work on the same window, so the random 4-byte stores of a window land in a
+// n x 4 B region (64 MB at 2^24 terms) that stays resident in the 126 MB L2 until its 32-byte sectors are complete.
+__global__ void __launch_bounds__(256) k_scatter(const uint32_t* __restrict__ digits, size_t n, uint32_t W, uint32_t NB,
+                                                 uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
+    const size_t total = (size_t)W * n;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t e = digits[g];
+        const uint32_t d = e & 0x7fffffffu;
+        if (d == 0) continue;
+        const size_t w = g / n, i = g - w * n;
+        const uint32_t pos = atomicAdd(&cursor[w * NB + (d - 1u)], 1u);
+        sorted[w * n + pos] = (uint32_t)i | (e & 0x80000000u);
     }
 }
 
@@ -376,7 +388,7 @@ __global__ void k_msm_final(const uint8_t* __restrict__ winsum, uint32_t W, uint
 }
 
 // fold of per-GPU Jacobian partials (util/msm.rs:333-335) + to_affine
-__global__ void k_fold_partials(const uint8_t* __restrict__ partials, uint32_t k, int format, void* out_affine) {
+__global__ void k_fold_partials(const uint8_t* __restrict__ partials, uint32_t k, int format, void* out_affine, void* out_jacobian) {
     __shared__ Fq xch[4];
     const int lane = threadIdx.x & 3;
     G1Xyzz acc = xyzz_identity();
@@ -386,8 +398,11 @@ __global__ void k_fold_partials(const uint8_t* __restrict__ partials, uint32_t k
         j.x = fp_load<FQ>(p); j.y = fp_load<FQ>(p + 32); j.z = fp_load<FQ>(p + 64);
         acc = xyzz_add_x4(acc, jacobian_to_xyzz(j), lane, xch);
     }
-    G1Affine a = xyzz_to_affine_serial(acc);
-    if (threadIdx.x == 0) store_affine_fmt(out_affine, a, format);
+    if (out_jacobian && threadIdx.x == 0) store_jacobian(out_jacobian, xyzz_to_jacobian(acc));
+    if (out_affine) {
+        G1Affine a = xyzz_to_affine_serial(acc);
+        if (threadIdx.x == 0) store_affine_fmt(out_affine, a, format);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -398,7 +413,7 @@ __global__ void k_fold_partials(const uint8_t* __restrict__ partials, uint32_t k
 struct MsmWork {
     MsmPlan pl;
     int* status;
-    uint32_t *counts, *offsets, *cursor, *sorted;
+    uint32_t *counts, *offsets, *cursor, *sorted, *digits;
     uint32_t *task_base, *window_tasks, *big;   // big = [count | list of bucket ids]
     uint2* tasks;
     uint32_t* order;
@@ -417,6 +432,7 @@ static int msm_alloc(snarkv_ctx* ctx, size_t n, void* d_status, MsmWork& wk) {
     wk.offsets = (uint32_t*)ctx->wsget(WS_OFFSETS, nbk * 4);
     wk.cursor = (uint32_t*)ctx->wsget(WS_CURSOR, nbk * 4);
     wk.sorted = (uint32_t*)ctx->wsget(WS_SORTED, (size_t)pl.W * n * 4);
+    wk.digits = (uint32_t*)ctx->wsget(WS_DIGITS, (size_t)pl.W * n * 4);
     wk.buckets = (uint8_t*)ctx->wsget(WS_BUCKETS, nbk * 128);
     wk.segpart = (uint8_t*)ctx->wsget(WS_SEGPART, (size_t)pl.W * pl.J * 128);
     wk.winsum = (uint8_t*)ctx->wsget(WS_WINSUM, (size_t)pl.W * 128);
@@ -427,7 +443,7 @@ static int msm_alloc(snarkv_ctx* ctx, size_t n, void* d_status, MsmWork& wk) {
     wk.task_out = (uint8_t*)ctx->wsget(WS_TASK_OUT, (size_t)pl.W * pl.cap * 128);
     wk.order = (uint32_t*)ctx->wsget(WS_ORDER, (size_t)pl.W * pl.cap * 4);
     if (!wk.status || !wk.counts || !wk.offsets || !wk.cursor || !wk.sorted || !wk.buckets || !wk.segpart || !wk.winsum ||
-        !wk.task_base || !wk.window_tasks || !wk.big || !wk.tasks || !wk.task_out || !wk.order)
+        !wk.digits || !wk.task_base || !wk.window_tasks || !wk.big || !wk.tasks || !wk.task_out || !wk.order)
         return SNARKV_ERR_CUDA;
     return SNARKV_OK;
 }
@@ -442,9 +458,9 @@ static int msm_sort_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* d_scal
         Stage sg(ctx, "msm_digits_count");
         SNARKV_CUDA_TRY(ctx, cudaMemsetAsync(wk.status, 0, 4, st));
         SNARKV_CUDA_TRY(ctx, cudaMemsetAsync(wk.counts, 0, nbk * 4, st));
-        k_digits<false><<<dig_blocks, 256, 0, st>>>((const uint8_t*)d_scalars, n, scalar_format, check, pl.c, pl.W, pl.NB, wk.counts,
-                                                    nullptr, wk.status);
-        SNARKV_LAUNCH_CHECK(ctx, "k_digits<count>");
+        k_digits<<<dig_blocks, 256, 0, st>>>((const uint8_t*)d_scalars, n, scalar_format, check, pl.c, pl.W, pl.NB, wk.counts, wk.digits,
+                                             wk.status);
+        SNARKV_LAUNCH_CHECK(ctx, "k_digits");
         sg.launched();
     }
     {
@@ -461,9 +477,9 @@ static int msm_sort_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* d_scal
     }
     {
         Stage sg(ctx, "msm_digits_scatter");
-        k_digits<true><<<dig_blocks, 256, 0, st>>>((const uint8_t*)d_scalars, n, scalar_format, check, pl.c, pl.W, pl.NB, wk.cursor,
-                                                   wk.sorted, wk.status);
-        SNARKV_LAUNCH_CHECK(ctx, "k_digits<scatter>");
+        const size_t tot = (size_t)pl.W * n, wantb = (tot + 255) / 256, capb = (size_t)ctx->sm_count * 16;
+        k_scatter<<<(unsigned)(wantb < capb ? wantb : capb), 256, 0, st>>>(wk.digits, n, pl.W, pl.NB, wk.cursor, wk.sorted);
+        SNARKV_LAUNCH_CHECK(ctx, "k_scatter");
         sg.launched();
     }
     return SNARKV_OK;
@@ -542,32 +558,68 @@ int msm_run_device(snarkv_ctx* ctx, const void* d_scalars, const void* d_points,
     return msm_point_phase(ctx, wk, d_points, n, point_format, out_format, check, d_out_affine, d_out_jacobian);
 }
 
-// snarkv_g1_msm: host slices in, 64-byte affine result out.  Scalars go first; the (2x larger) point copy is issued after
-// the sort kernels are queued so that the copy engine and the SMs overlap.
+// snarkv_g1_msm / snarkv_g1_msm_partial: host slices in.  Small inputs: scalars first, the (2x larger) point copy is issued
+// after the sort kernels are queued so copy engine and SMs overlap.  Large inputs (>= 2^22 terms) are cut into 4 term-chunks
+// (the rayon chunking of util/msm.rs:322-336 again, now in time instead of across threads): chunk k+1 is copied on the copy
+// stream while chunk k runs its whole pipeline, and the Jacobian partials are folded at the end.
 int msm_run_host(snarkv_ctx* ctx, const uint8_t* scalars, const uint8_t* points, size_t n, int format, int flags, uint8_t* out,
                  void* d_out_jacobian) {
     const int check = (flags & SNARKV_CHECK_INPUTS) ? 1 : 0;
-    MsmWork wk;
-    int rc = msm_alloc(ctx, n, nullptr, wk);
-    if (rc) return rc;
+    if (n == 0) return ctx->fail(SNARKV_ERR_EMPTY, "multi_scalar_multiplication on an empty slice");
     uint8_t* d_s = (uint8_t*)ctx->wsget(WS_IO_A, n * 32);
     uint8_t* d_p = (uint8_t*)ctx->wsget(WS_IO_B, n * 64);
-    uint8_t* d_o = (uint8_t*)ctx->wsget(WS_OUT, 256);
+    uint8_t* d_o = (uint8_t*)ctx->wsget(WS_OUT, 1024);   // [affine 64 | pad | partials 4 x 96 @128 | status 4 x 4 @512]
     if (!d_s || !d_p || !d_o) return SNARKV_ERR_CUDA;
     cudaStream_t st = ctx->stream;
-    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_s, scalars, n * 32, cudaMemcpyHostToDevice, st));
-    rc = msm_sort_phase(ctx, wk, d_s, n, format, check);
-    if (rc) return rc;
-    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_p, points, n * 64, cudaMemcpyHostToDevice, ctx->copy_stream));
-    SNARKV_CUDA_TRY(ctx, cudaEventRecord(ctx->copy_done, ctx->copy_stream));
-    SNARKV_CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->copy_done, 0));
-    rc = msm_point_phase(ctx, wk, d_p, n, format, format, check, out ? d_o : nullptr, d_out_jacobian);
-    if (rc) return rc;
-    int status = 0;
+    const int K = n >= ((size_t)1 << 22) ? SNARKV_HOST_CHUNKS : 1;
+    int status[SNARKV_HOST_CHUNKS] = {0, 0, 0, 0};
+    int* d_status = (int*)(d_o + 512);
+    int rc;
+    if (K == 1) {
+        MsmWork wk;
+        rc = msm_alloc(ctx, n, d_status, wk);
+        if (rc) return rc;
+        SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_s, scalars, n * 32, cudaMemcpyHostToDevice, st));
+        rc = msm_sort_phase(ctx, wk, d_s, n, format, check);
+        if (rc) return rc;
+        SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_p, points, n * 64, cudaMemcpyHostToDevice, ctx->copy_stream));
+        SNARKV_CUDA_TRY(ctx, cudaEventRecord(ctx->copy_done[0], ctx->copy_stream));
+        SNARKV_CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->copy_done[0], 0));
+        rc = msm_point_phase(ctx, wk, d_p, n, format, format, check, out ? d_o : nullptr, d_out_jacobian);
+        if (rc) return rc;
+    } else {
+        const size_t chunk = (n + K - 1) / K;
+        // the copy stream must not run ahead of work already queued on the compute stream that still reads the staging buffers
+        SNARKV_CUDA_TRY(ctx, cudaEventRecord(ctx->copy_done[K], st));
+        SNARKV_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_done[K], 0));
+        for (int k = 0; k < K; ++k) {
+            const size_t lo = (size_t)k * chunk, len = (lo + chunk <= n) ? chunk : n - lo;
+            SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_s + lo * 32, scalars + lo * 32, len * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
+            SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_p + lo * 64, points + lo * 64, len * 64, cudaMemcpyHostToDevice, ctx->copy_stream));
+            SNARKV_CUDA_TRY(ctx, cudaEventRecord(ctx->copy_done[k], ctx->copy_stream));
+        }
+        for (int k = 0; k < K; ++k) {
+            const size_t lo = (size_t)k * chunk, len = (lo + chunk <= n) ? chunk : n - lo;
+            SNARKV_CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->copy_done[k], 0));
+            MsmWork wk;
+            rc = msm_alloc(ctx, len, d_status + k, wk);
+            if (rc) return rc;
+            rc = msm_sort_phase(ctx, wk, d_s + lo * 32, len, format, check);
+            if (rc) return rc;
+            rc = msm_point_phase(ctx, wk, d_p + lo * 64, len, format, format, check, nullptr, d_o + 128 + 96 * k);
+            if (rc) return rc;
+        }
+        Stage sg(ctx, "msm_fold_partials");
+        k_fold_partials<<<1, 32, 0, st>>>(d_o + 128, (uint32_t)K, format, out ? d_o : nullptr, d_out_jacobian);
+        SNARKV_LAUNCH_CHECK(ctx, "k_fold_partials");
+        sg.launched();
+    }
     if (out) SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(out, d_o, 64, cudaMemcpyDeviceToHost, st));
-    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(&status, wk.status, 4, cudaMemcpyDeviceToHost, st));
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(status, d_status, 4 * K, cudaMemcpyDeviceToHost, st));
     SNARKV_CUDA_TRY(ctx, cudaStreamSynchronize(st));
-    if (status != 0) return ctx->fail(status, status == SNARKV_ERR_BAD_SCALAR ? "scalar is not a canonical Fr" : "point is not a valid G1Affine");
+    for (int k = 0; k < K; ++k)
+        if (status[k] != 0)
+            return ctx->fail(status[k], status[k] == SNARKV_ERR_BAD_SCALAR ? "scalar is not a canonical Fr" : "point is not a valid G1Affine");
     return SNARKV_OK;
 }
 
@@ -579,7 +631,7 @@ void msm_plan_query(snarkv_ctx* ctx, size_t n, uint32_t out[4]) {
 int msm_fold_partials_device(snarkv_ctx* ctx, const void* d_partials, size_t k, int format, void* d_out_affine) {
     if (k == 0 || k > (1u << 20)) return ctx->fail(SNARKV_ERR_USAGE, "fold_partials: bad k");
     Stage sg(ctx, "msm_fold_partials");
-    k_fold_partials<<<1, 32, 0, ctx->stream>>>((const uint8_t*)d_partials, (uint32_t)k, format, d_out_affine);
+    k_fold_partials<<<1, 32, 0, ctx->stream>>>((const uint8_t*)d_partials, (uint32_t)k, format, d_out_affine, nullptr);
     SNARKV_LAUNCH_CHECK(ctx, "k_fold_partials");
     sg.launched();
     return SNARKV_OK;

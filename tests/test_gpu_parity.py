@@ -402,3 +402,26 @@ def test_fused_rlc_decide_all_accepts_valid_rejects_one_bad(kzg, golden):
     off = bytearray(rhs); off[64 * 7:64 * 8] = le(1) + le(3)      # not on the curve
     ok4, _ = kzg.decide_all_fused(lhs, bytes(off), n, rho)
     assert not ok4
+
+
+def test_host_entry_chunk_pipeline_matches_device_path(loader):
+    """n >= 2^22 goes through the 4-chunk copy/compute pipeline of snarkv_g1_msm; result must equal the resident path and the
+    discrete-log checksum.  n is not a multiple of 4 on purpose (ragged last chunk)."""
+    import torch
+    n = (1 << 22) + 3
+    ds = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
+    dp = torch.empty(n * 64, dtype=torch.uint8, device="cuda")
+    out = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    loader.synth_scalars_device(88, 0, n, ds.data_ptr())
+    loader.synth_points_device(88, 0, n, dp.data_ptr())
+    loader.msm_device(ds.data_ptr(), dp.data_ptr(), n, d_out_affine=out.data_ptr())
+    torch.cuda.synchronize()
+    hs, hp = ds.cpu().numpy(), dp.cpu().numpy()
+    got = loader.msm(hs, hp, n)
+    assert got == bytes(out.cpu().numpy())
+    assert got == oracle.msm_expected_from_dlogs(hs, oracle.synth_point_scalars(88, 0, n), n)
+    part = torch.zeros(96, dtype=torch.uint8, device="cuda")
+    loader.msm_partial(hs, hp, n, part.data_ptr())
+    loader.fold_partials_device(part.data_ptr(), 1, out.data_ptr())
+    torch.cuda.synchronize()
+    assert bytes(out.cpu().numpy()) == got
