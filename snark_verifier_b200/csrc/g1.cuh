@@ -210,10 +210,13 @@ __device__ __forceinline__ Fq4 fq_exchange4(Fq* xch, const Fq& mine) {
     }
     return o;
 }
+// branch-free 4-way select (lane-dependent ternaries would compile into divergent branch regions, one per limb)
 __device__ __forceinline__ Fq fq_sel4(int lane, const Fq& a0, const Fq& a1, const Fq& a2, const Fq& a3) {
+    const uint32_t m0 = 0u - (uint32_t)(lane == 0), m1 = 0u - (uint32_t)(lane == 1), m2 = 0u - (uint32_t)(lane == 2),
+                   m3 = 0u - (uint32_t)(lane == 3);
     Fq r;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) r.v[i] = lane == 0 ? a0.v[i] : lane == 1 ? a1.v[i] : lane == 2 ? a2.v[i] : a3.v[i];
+    for (int i = 0; i < 8; ++i) r.v[i] = (a0.v[i] & m0) | (a1.v[i] & m1) | (a2.v[i] & m2) | (a3.v[i] & m3);
     return r;
 }
 

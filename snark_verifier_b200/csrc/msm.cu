@@ -84,31 +84,88 @@ __global__ void k_points_prepare(const uint8_t* __restrict__ in, uint8_t* __rest
 // K1 / K3: signed-digit decomposition.  `windowed_scalar` of util/msm.rs:271-281 extracts unsigned c-bit digits from the
 // canonical little-endian repr; here each digit d in [0, 2^c) plus the carry from below is mapped to (-2^(c-1), 2^(c-1)].
 // ---------------------------------------------------------------------------------------------------------------------
+// ---- TMA (bulk async copy) helpers: 1-D cp.async.bulk global -> shared with mbarrier completion (SASS: UBLKCP / SYNCS) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+
 // K1: every scalar -> W signed digits, stored window-major (digits[w][i] = |d| | sign << 31, coalesced) + histogram.
-__global__ void __launch_bounds__(256) k_digits(const uint8_t* __restrict__ scalars, size_t n, int format, int check, uint32_t c,
-                                                uint32_t W, uint32_t NB, uint32_t* __restrict__ counters,
-                                                uint32_t* __restrict__ digits, int* __restrict__ status) {
+// The scalar stream is staged through shared memory by TMA bulk copies: one elected thread issues an 8 KB
+// cp.async.bulk per 256-scalar tile into a double buffer while the block decomposes the previous tile.
+#define SNARKV_DIGIT_TILE 256
+__global__ void __launch_bounds__(SNARKV_DIGIT_TILE) k_digits(const uint8_t* __restrict__ scalars, size_t n, int format, int check, uint32_t c,
+                                                              uint32_t W, uint32_t NB, uint32_t* __restrict__ counters,
+                                                              uint32_t* __restrict__ digits, int* __restrict__ status) {
+    __shared__ alignas(128) uint8_t tile[2][SNARKV_DIGIT_TILE * 32];
+    __shared__ alignas(8) uint64_t bar[2];
     const uint32_t mask = (1u << c) - 1u;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        Fr s = fp_load<FR>(scalars + i * 32);
-        if (format == SNARKV_MONTGOMERY) s = fp_from_mont(s);
-        else if (check && !fp_is_canonical(s)) atomicCAS(status, 0, SNARKV_ERR_BAD_SCALAR);
-        uint32_t carry = 0;
-        for (uint32_t w = 0; w < W; ++w) {
-            uint32_t d = (s.v[0] & mask) + carry;
-            // s >>= c  (c < 32)
+    const uint32_t tid = threadIdx.x;
+    const size_t ntiles = (n + SNARKV_DIGIT_TILE - 1) / SNARKV_DIGIT_TILE;
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](size_t t, uint32_t buf) {
+        const size_t first = t * SNARKV_DIGIT_TILE;
+        const uint32_t cnt = (uint32_t)((n - first < SNARKV_DIGIT_TILE) ? n - first : SNARKV_DIGIT_TILE);
+        tma_load_1d(tile[buf], scalars + first * 32, cnt * 32u, &bar[buf]);
+    };
+    size_t t = blockIdx.x;
+    if (tid == 0 && t < ntiles) issue(t, 0);
+    for (uint32_t it = 0; t < ntiles; t += gridDim.x, ++it) {
+        const uint32_t buf = it & 1u;
+        const size_t nxt = t + gridDim.x;
+        if (tid == 0 && nxt < ntiles) issue(nxt, buf ^ 1u);   // buf^1 was released by the __syncthreads closing iteration it-1
+        mbar_wait(&bar[buf], (it >> 1) & 1u);
+        const size_t i = t * SNARKV_DIGIT_TILE + tid;
+        if (i < n) {
+            Fr s;
+            {
+                const uint4* q = reinterpret_cast<const uint4*>(&tile[buf][tid * 32]);
+                uint4 lo = q[0], hi = q[1];
+                s.v[0] = lo.x; s.v[1] = lo.y; s.v[2] = lo.z; s.v[3] = lo.w; s.v[4] = hi.x; s.v[5] = hi.y; s.v[6] = hi.z; s.v[7] = hi.w;
+            }
+            if (format == SNARKV_MONTGOMERY) s = fp_from_mont(s);
+            else if (check && !fp_is_canonical(s)) atomicCAS(status, 0, SNARKV_ERR_BAD_SCALAR);
+            uint32_t carry = 0;
+            for (uint32_t w = 0; w < W; ++w) {
+                uint32_t d = (s.v[0] & mask) + carry;
+                // s >>= c  (c < 32)
 #pragma unroll
-            for (int j = 0; j < 7; ++j) s.v[j] = __funnelshift_r(s.v[j], s.v[j + 1], c);
-            s.v[7] >>= c;
-            uint32_t neg = 0;
-            if (d > NB) {
-                d = (mask + 1u) - d;
-                neg = 1u;
-                carry = 1u;
-            } else carry = 0u;
-            digits[(size_t)w * n + i] = d | (neg << 31);
-            if (d != 0) atomicAdd(&counters[w * NB + (d - 1u)], 1u);
+                for (int j = 0; j < 7; ++j) s.v[j] = __funnelshift_r(s.v[j], s.v[j + 1], c);
+                s.v[7] >>= c;
+                uint32_t neg = 0;
+                if (d > NB) {
+                    d = (mask + 1u) - d;
+                    neg = 1u;
+                    carry = 1u;
+                } else carry = 0u;
+                digits[(size_t)w * n + i] = d | (neg << 31);
+                if (d != 0) atomicAdd(&counters[w * NB + (d - 1u)], 1u);
+            }
         }
+        __syncthreads();
     }
 }
 
@@ -452,8 +509,9 @@ static int msm_sort_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* d_scal
     const MsmPlan& pl = wk.pl;
     cudaStream_t st = ctx->stream;
     const size_t nbk = (size_t)pl.W * pl.NB;
-    const size_t want = (n + 255) / 256, cap = (size_t)ctx->sm_count * 8;
+    const size_t want = (n + SNARKV_DIGIT_TILE - 1) / SNARKV_DIGIT_TILE, cap = (size_t)ctx->sm_count * 8;
     const int dig_blocks = (int)(want < cap ? want : cap);
+    if ((reinterpret_cast<uintptr_t>(d_scalars) & 15u) != 0) return ctx->fail(SNARKV_ERR_USAGE, "scalar buffer must be 16-byte aligned");
     {
         Stage sg(ctx, "msm_digits_count");
         SNARKV_CUDA_TRY(ctx, cudaMemsetAsync(wk.status, 0, 4, st));
