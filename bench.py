@@ -102,12 +102,14 @@ def cpu_pippenger_sample(log_n, threads, reps=1):
     """Oracle restatement of util/msm.rs:308-343 (`parallel` feature) on `threads` host threads; returns (terms/s, n)."""
     import oracle
     n = 1 << log_n
-    s = oracle.synth_scalars(SEED, 0, n)
-    p = oracle.synth_points(SEED, 0, n, threads)
+    # inputs in halo2curves' in-memory (Montgomery) layout, prepared outside the timed region: the Rust reference is handed
+    # `&[Fr]` / `&[G1Affine]` and never parses bytes on this path
+    s = oracle.to_mont_batch(1, oracle.synth_scalars(SEED, 0, n), n, threads)
+    p = oracle.to_mont_batch(0, oracle.synth_points(SEED, 0, n, threads), 2 * n, threads)
     best = None
     for _ in range(reps):
         t0 = time.perf_counter()
-        oracle.msm_pippenger(s, p, n, threads)
+        oracle.msm_pippenger_raw(s, p, n, threads)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     return n / best, n, best
@@ -171,13 +173,13 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     log_n = args.ref_log_n
     n = 1 << log_n
-    s = oracle.synth_scalars(SEED, 0, n)
-    p = oracle.synth_points(SEED, 0, n, threads)
+    s = oracle.to_mont_batch(1, oracle.synth_scalars(SEED, 0, n), n, threads)              # halo2curves in-memory layout,
+    p = oracle.to_mont_batch(0, oracle.synth_points(SEED, 0, n, threads), 2 * n, threads)  # prepared outside the timed region
     for _ in range(args.warmup):
-        oracle.msm_pippenger(s, p, n, threads)
+        oracle.msm_pippenger_raw(s, p, n, threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        oracle.msm_pippenger(s, p, n, threads)
+        oracle.msm_pippenger_raw(s, p, n, threads)
     dt = time.perf_counter() - t0
     val = n * args.steps / dt / 1e6
     sample = "2^%d-term slice of the synthetic 2^%d workload per step" % (log_n, args.log_n)

@@ -38,6 +38,8 @@ def lib():
             "oracle_g2_is_on_curve": [u8p],
             "oracle_msm_native": [vp, vp, sz, u8p],
             "oracle_msm_pippenger": [vp, vp, sz, i32, u8p],
+            "oracle_msm_pippenger_raw": [vp, vp, sz, i32, u8p],
+            "oracle_to_mont_batch": [i32, vp, sz, i32, vp],
             "oracle_kzg_decide": [u8p, u8p, u8p, u8p, u8p, u8p],
             "oracle_kzg_decide_batch": [vp, vp, sz, u8p, u8p, i32, i32, vp, vp],
             "oracle_kzg_accumulate": [vp, vp, sz, u8p, u8p, u8p],
@@ -93,6 +95,11 @@ def msm_native(scalars, points, n):
     o = _buf(64); _chk(lib().oracle_msm_native(_ptr(scalars), _ptr(points), n, o), "msm_native"); return o.raw
 def msm_pippenger(scalars, points, n, threads=1):
     o = _buf(64); _chk(lib().oracle_msm_pippenger(_ptr(scalars), _ptr(points), n, threads, o), "msm_pippenger"); return o.raw
+def msm_pippenger_raw(scalars_mont, points_mont, n, threads=1):
+    """halo2curves in-memory layout in (what the Rust reference holds), canonical affine bytes out; no parsing inside."""
+    o = _buf(64); _chk(lib().oracle_msm_pippenger_raw(_ptr(scalars_mont), _ptr(points_mont), n, threads, o), "msm_pippenger_raw"); return o.raw
+def to_mont_batch(field, data, n, threads=1):
+    o = _buf(32 * n); _chk(lib().oracle_to_mont_batch(field, _ptr(data), n, threads, ctypes.cast(o, ctypes.c_void_p)), "to_mont_batch"); return o.raw
 def kzg_decide(lhs, rhs, g2, s_g2, want_gt=True):
     acc = _buf(1); gt = _buf(384) if want_gt else None
     _chk(lib().oracle_kzg_decide(lhs, rhs, g2, s_g2, acc, gt), "kzg_decide")

@@ -615,6 +615,35 @@ int oracle_msm_pippenger(const uint8_t* scalars, const uint8_t* points, size_t n
     int rc = load_terms(scalars, points, n, s, p); if (rc) return rc;
     store_g1(msm_pippenger(s.data(), p.data(), n, threads).to_affine(), out); return 0;
 }
+// The same call on halo2curves' in-memory layout (Montgomery limbs, what `&[Fr]` / `&[G1Affine]` are in the Rust reference):
+// no parsing, no validation — only the algorithm of util/msm.rs:308-343 is inside the call.  This is the entry bench.py times.
+int oracle_msm_pippenger_raw(const uint8_t* scalars_mont, const uint8_t* points_mont, size_t n, int threads, uint8_t* out) {
+    if (n == 0) return -1;
+    static_assert(sizeof(Fr) == 32 && sizeof(G1Affine) == 64, "layout");
+    const Fr* s = reinterpret_cast<const Fr*>(scalars_mont);
+    const G1Affine* p = reinterpret_cast<const G1Affine*>(points_mont);
+    store_g1(msm_pippenger(s, p, n, threads).to_affine(), out); return 0;
+}
+// canonical -> Montgomery layout for n field elements of `field` (0 = Fq, 1 = Fr), multi-threaded (bench input preparation)
+int oracle_to_mont_batch(int field, const uint8_t* in, size_t n, int threads, uint8_t* out) {
+    if (threads < 1) threads = 1;
+    std::vector<std::thread> pool;
+    std::vector<int> rc(threads, 0);
+    size_t chunk = (n + threads - 1) / threads;
+    for (int t = 0; t < threads; ++t) {
+        size_t lo = (size_t)t * chunk, hi = lo + chunk < n ? lo + chunk : n;
+        if (lo >= hi) break;
+        pool.emplace_back([=, &rc] {
+            for (size_t i = lo; i < hi; ++i) {
+                if (field == 0) { Fq x; if (!Fq::from_le_bytes(in + 32 * i, x)) { rc[t] = -2; return; } memcpy(out + 32 * i, x.v, 32); }
+                else { Fr x; if (!Fr::from_le_bytes(in + 32 * i, x)) { rc[t] = -2; return; } memcpy(out + 32 * i, x.v, 32); }
+            }
+        });
+    }
+    for (auto& th : pool) th.join();
+    for (int r : rc) if (r) return r;
+    return 0;
+}
 // pcs/kzg/decider.rs:70-82;  *accept = 1/0;  gt_out may be NULL
 int oracle_kzg_decide(const uint8_t* lhs, const uint8_t* rhs, const uint8_t* g2, const uint8_t* s_g2, uint8_t* accept, uint8_t* gt_out) {
     G1Affine l, r; G2Affine a, b;

@@ -62,6 +62,14 @@ def test_msm_native_fold_and_pippenger(golden):
         assert oracle.msm_pippenger(s, p, n, 4) == exp, case["name"]       # util/msm.rs:308-343
 
 
+def test_msm_raw_layout_entry_matches_canonical_entry():
+    n = 500
+    s = oracle.synth_scalars(17, 0, n); p = oracle.synth_points(17, 0, n, 4)
+    sm = oracle.to_mont_batch(1, s, n, 3); pm = oracle.to_mont_batch(0, p, 2 * n, 3)
+    assert sm[:32] == oracle.fp_to_mont(1, s[:32]) and pm[32:64] == oracle.fp_to_mont(0, p[32:64])
+    assert oracle.msm_pippenger_raw(sm, pm, n, 4) == oracle.msm_pippenger(s, p, n, 4)
+
+
 def test_msm_empty_is_an_error():
     with pytest.raises(ValueError):       # .unwrap() on an empty fold panics, native.rs:69
         oracle.msm_native(b"", b"", 0)
