@@ -200,9 +200,7 @@ int snarkv_kzg_accumulate(snarkv_ctx* ctx, const uint8_t* lhs, const uint8_t* rh
     SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_r, rhs, n * 64, cudaMemcpyHostToDevice, st));
     int rc = fr_powers_device(ctx, d_pw, format, n, d_pw + 32);
     if (rc) return rc;
-    rc = msm_run_device(ctx, d_pw + 32, d_l, n, SNARKV_MONTGOMERY, format, format, 0, d_o, nullptr, nullptr);
-    if (rc) return rc;
-    rc = msm_run_device(ctx, d_pw + 32, d_r, n, SNARKV_MONTGOMERY, format, format, 0, d_o + 64, nullptr, nullptr);
+    rc = msm_run_device_pair(ctx, d_pw + 32, d_l, d_r, n, SNARKV_MONTGOMERY, format, format, 0, d_o, nullptr);
     if (rc) return rc;
     uint8_t host[128];
     SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(host, d_o, 128, cudaMemcpyDeviceToHost, st));
@@ -271,10 +269,9 @@ int snarkv_kzg_decide_all_fused(snarkv_ctx* ctx, const uint8_t* lhs, const uint8
     SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_r, rhs, N * 64, cudaMemcpyHostToDevice, st));
     int rc = fr_powers_device(ctx, d_pw, format, N, d_pw + 32);
     if (rc) return rc;
-    // layout of d_o: [lhs' 64 | rhs' 64 | accept 1 .. pad to 132 | status(lhs MSM) 4 | status(rhs MSM) 4]
-    rc = msm_run_device(ctx, d_pw + 32, d_l, N, SNARKV_MONTGOMERY, format, format, SNARKV_CHECK_INPUTS, d_o, nullptr, d_o + 132);
-    if (rc) return rc;
-    rc = msm_run_device(ctx, d_pw + 32, d_r, N, SNARKV_MONTGOMERY, format, format, SNARKV_CHECK_INPUTS, d_o + 64, nullptr, d_o + 136);
+    // layout of d_o: [lhs' 64 | rhs' 64 | accept 1 .. pad to 132 | status 4 | unused 4]
+    SNARKV_CUDA_TRY(ctx, cudaMemsetAsync(d_o + 136, 0, 4, st));
+    rc = msm_run_device_pair(ctx, d_pw + 32, d_l, d_r, N, SNARKV_MONTGOMERY, format, format, SNARKV_CHECK_INPUTS, d_o, d_o + 132);
     if (rc) return rc;
     rc = kzg_decide_device(ctx, d_o, d_o + 64, 1, format, d_o + 128, nullptr);
     if (rc) return rc;

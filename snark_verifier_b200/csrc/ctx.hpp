@@ -156,6 +156,8 @@ struct Stage {
 // internal entry points shared between translation units
 int msm_run_device(snarkv_ctx* ctx, const void* d_scalars, const void* d_points, size_t n, int scalar_format, int point_format,
                    int out_format, int flags, void* d_out_affine, void* d_out_jacobian, void* d_status);
+int msm_run_device_pair(snarkv_ctx* ctx, const void* d_scalars, const void* d_points0, const void* d_points1, size_t n, int scalar_format,
+                        int point_format, int out_format, int flags, void* d_out_affine, void* d_status);
 int msm_run_host(snarkv_ctx* ctx, const uint8_t* scalars, const uint8_t* points, size_t n, int format, int flags, uint8_t* out,
                  void* d_out_jacobian);
 void msm_plan_query(snarkv_ctx* ctx, size_t n, uint32_t out[4]);

@@ -296,7 +296,8 @@ __global__ void __launch_bounds__(1024) k_order_tasks(const uint32_t* __restrict
 // util/msm.rs:291-296, with Bucket::{None, Affine, Projective} (util/msm.rs:228-246) collapsed into the XYZZ identity test.
 // One thread per (window, bucket); the next point is fetched (4 x 128-bit loads) while the current addition runs.
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_bucket_accumulate(const uint8_t* __restrict__ points, const uint32_t* __restrict__ sorted,
+__global__ void __launch_bounds__(128) k_bucket_accumulate(const uint8_t* __restrict__ points0, const uint8_t* __restrict__ points1,
+                                                           const uint32_t* __restrict__ sorted,
                                                            const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts,
                                                            const uint2* __restrict__ tasks, const uint32_t* __restrict__ window_tasks,
                                                            const uint32_t* __restrict__ order, size_t n, uint32_t NB, uint32_t T,
@@ -304,6 +305,9 @@ __global__ void __launch_bounds__(128) k_bucket_accumulate(const uint8_t* __rest
     const uint32_t w = blockIdx.y;
     const uint32_t rank = blockIdx.x * blockDim.x + threadIdx.x;
     if (rank >= window_tasks[w]) return;
+    // blockIdx.z selects one of the base sets that share these scalars (KzgAs::verify: lhs and rhs points, accumulation.rs:53-60)
+    const uint8_t* __restrict__ points = blockIdx.z == 0 ? points0 : points1;
+    task_out += (size_t)blockIdx.z * gridDim.y * cap * 128;
     const uint32_t slot = order[(size_t)w * cap + rank];
     const uint2 task = tasks[(size_t)w * cap + slot];
     const uint32_t bucket = w * NB + task.x;
@@ -339,8 +343,10 @@ __global__ void __launch_bounds__(128) k_bucket_merge(const uint8_t* __restrict_
     if (tid >= total) return;
     const uint32_t w = tid / NB;
     const uint32_t parts = (counts[tid] + T - 1) / T;
+    task_out += (size_t)blockIdx.y * (total / NB) * cap * 128;
+    buckets += (size_t)blockIdx.y * total * 128;
     if (parts > SNARKV_MERGE_SERIAL) {
-        big_list[atomicAdd(big_count, 1u)] = tid;
+        if (blockIdx.y == 0) big_list[atomicAdd(big_count, 1u)] = tid;   // the list depends on the shared counts only
         return;
     }
     const size_t base = (size_t)w * cap + task_base[tid];
@@ -353,9 +359,11 @@ __global__ void __launch_bounds__(128) k_bucket_merge(const uint8_t* __restrict_
 __global__ void __launch_bounds__(128) k_bucket_merge_big(const uint8_t* __restrict__ task_out, const uint32_t* __restrict__ counts,
                                                           const uint32_t* __restrict__ task_base, uint32_t NB, uint32_t T, uint32_t cap,
                                                           uint8_t* __restrict__ buckets, const uint32_t* __restrict__ big_count,
-                                                          const uint32_t* __restrict__ big_list) {
+                                                          const uint32_t* __restrict__ big_list, uint32_t W) {
     __shared__ G1Xyzz sm[128];
     const uint32_t t = threadIdx.x;
+    task_out += (size_t)blockIdx.y * W * cap * 128;
+    buckets += (size_t)blockIdx.y * W * NB * 128;
     for (uint32_t q = blockIdx.x; q < *big_count; q += gridDim.x) {
         const uint32_t tid = big_list[q];
         const uint32_t w = tid / NB;
@@ -384,6 +392,8 @@ __global__ void __launch_bounds__(128) k_bucket_reduce(const uint8_t* __restrict
     const uint32_t w = blockIdx.y;
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= J) return;
+    buckets += (size_t)blockIdx.z * gridDim.y * NB * 128;
+    segpart += (size_t)blockIdx.z * gridDim.y * J * 128;
     const uint32_t lo = j * seg, hi = min(lo + seg, NB);
     G1Xyzz running = xyzz_identity(), acc = xyzz_identity();
     for (uint32_t idx = hi; idx-- > lo;) {
@@ -399,6 +409,8 @@ __global__ void __launch_bounds__(128) k_bucket_reduce(const uint8_t* __restrict
 __global__ void __launch_bounds__(128) k_window_sum(const uint8_t* __restrict__ segpart, uint32_t J, uint8_t* __restrict__ winsum) {
     __shared__ G1Xyzz sm[128];
     const uint32_t w = blockIdx.x, t = threadIdx.x;
+    segpart += (size_t)blockIdx.y * gridDim.x * J * 128;
+    winsum += (size_t)blockIdx.y * gridDim.x * 128;
     G1Xyzz acc = xyzz_identity();
     for (uint32_t j = t; j < J; j += blockDim.x) acc = xyzz_add(acc, xyzz_load(segpart, (size_t)w * J + j));
     sm[t] = acc;
@@ -429,8 +441,12 @@ __device__ __forceinline__ void store_jacobian(void* out, const G1Jac& j) {
 // caller's `.to_affine()` (native.rs:70).
 __global__ void k_msm_final(const uint8_t* __restrict__ winsum, uint32_t W, uint32_t c, int format, void* out_affine,
                             void* out_jacobian) {
-    // one warp; every aligned group of 4 lanes runs the same 4-lane point arithmetic (g1.cuh: *_x4), thread 0 stores
+    // one warp (= one block) per base set; every aligned group of 4 lanes runs the same 4-lane point arithmetic
+    // (g1.cuh: *_x4), thread 0 stores
     __shared__ Fq xch[4];
+    winsum += (size_t)blockIdx.x * W * 128;
+    if (out_affine) out_affine = (uint8_t*)out_affine + 64 * blockIdx.x;
+    if (out_jacobian) out_jacobian = (uint8_t*)out_jacobian + 96 * blockIdx.x;
     const int lane = threadIdx.x & 3;
     G1Xyzz acc = xyzz_load(winsum, W - 1);
     for (uint32_t w = W - 1; w-- > 0;) {
@@ -477,7 +493,7 @@ struct MsmWork {
     uint8_t *task_out, *buckets, *segpart, *winsum;
 };
 
-static int msm_alloc(snarkv_ctx* ctx, size_t n, void* d_status, MsmWork& wk) {
+static int msm_alloc(snarkv_ctx* ctx, size_t n, void* d_status, MsmWork& wk, int B = 1) {
     if (n == 0) return ctx->fail(SNARKV_ERR_EMPTY, "multi_scalar_multiplication on an empty slice");
     if (n >= (1ull << 31)) return ctx->fail(SNARKV_ERR_USAGE, "n must be < 2^31");
     wk.pl = make_plan(n, ctx->window_bits);
@@ -490,14 +506,14 @@ static int msm_alloc(snarkv_ctx* ctx, size_t n, void* d_status, MsmWork& wk) {
     wk.cursor = (uint32_t*)ctx->wsget(WS_CURSOR, nbk * 4);
     wk.sorted = (uint32_t*)ctx->wsget(WS_SORTED, (size_t)pl.W * n * 4);
     wk.digits = (uint32_t*)ctx->wsget(WS_DIGITS, (size_t)pl.W * n * 4);
-    wk.buckets = (uint8_t*)ctx->wsget(WS_BUCKETS, nbk * 128);
-    wk.segpart = (uint8_t*)ctx->wsget(WS_SEGPART, (size_t)pl.W * pl.J * 128);
-    wk.winsum = (uint8_t*)ctx->wsget(WS_WINSUM, (size_t)pl.W * 128);
+    wk.buckets = (uint8_t*)ctx->wsget(WS_BUCKETS, (size_t)B * nbk * 128);
+    wk.segpart = (uint8_t*)ctx->wsget(WS_SEGPART, (size_t)B * pl.W * pl.J * 128);
+    wk.winsum = (uint8_t*)ctx->wsget(WS_WINSUM, (size_t)B * pl.W * 128);
     wk.task_base = (uint32_t*)ctx->wsget(WS_TASK_BASE, nbk * 4);
     wk.window_tasks = (uint32_t*)ctx->wsget(WS_WINDOW_TASKS, (size_t)pl.W * 4);
     wk.big = (uint32_t*)ctx->wsget(WS_BIG, (nbk + 1) * 4);
     wk.tasks = (uint2*)ctx->wsget(WS_TASKS, (size_t)pl.W * pl.cap * 8);
-    wk.task_out = (uint8_t*)ctx->wsget(WS_TASK_OUT, (size_t)pl.W * pl.cap * 128);
+    wk.task_out = (uint8_t*)ctx->wsget(WS_TASK_OUT, (size_t)B * pl.W * pl.cap * 128);
     wk.order = (uint32_t*)ctx->wsget(WS_ORDER, (size_t)pl.W * pl.cap * 4);
     if (!wk.status || !wk.counts || !wk.offsets || !wk.cursor || !wk.sorted || !wk.buckets || !wk.segpart || !wk.winsum ||
         !wk.digits || !wk.task_base || !wk.window_tasks || !wk.big || !wk.tasks || !wk.task_out || !wk.order)
@@ -543,29 +559,34 @@ static int msm_sort_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* d_scal
     return SNARKV_OK;
 }
 
+// B = 1 or 2 base sets share the scalars / sort of `wk`; results land at d_out_affine + 64 z and d_out_jacobian + 96 z.
 static int msm_point_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* d_points, size_t n, int point_format, int out_format,
-                           int check, void* d_out_affine, void* d_out_jacobian) {
+                           int check, void* d_out_affine, void* d_out_jacobian, const void* d_points1 = nullptr) {
     const MsmPlan& pl = wk.pl;
     cudaStream_t st = ctx->stream;
     const size_t nbk = (size_t)pl.W * pl.NB;
-    const uint8_t* points = (const uint8_t*)d_points;
+    const int B = d_points1 ? 2 : 1;
+    const uint8_t* pts[2] = {(const uint8_t*)d_points, (const uint8_t*)d_points1};
     if (point_format == SNARKV_CANONICAL || check) {
         Stage sg(ctx, "msm_points_prepare");
         uint8_t* conv = nullptr;
         if (point_format == SNARKV_CANONICAL) {
-            conv = (uint8_t*)ctx->wsget(WS_POINTS_MONT, n * 64);
+            conv = (uint8_t*)ctx->wsget(WS_POINTS_MONT, (size_t)B * n * 64);
             if (!conv) return SNARKV_ERR_CUDA;
         }
         const size_t want = (n + 255) / 256, cap = (size_t)ctx->sm_count * 8;
-        k_points_prepare<<<(int)(want < cap ? want : cap), 256, 0, st>>>(points, conv, n, point_format, check, wk.status);
-        SNARKV_LAUNCH_CHECK(ctx, "k_points_prepare");
-        sg.launched();
-        if (conv) points = conv;
+        for (int z = 0; z < B; ++z) {
+            uint8_t* cz = conv ? conv + (size_t)z * n * 64 : nullptr;
+            k_points_prepare<<<(int)(want < cap ? want : cap), 256, 0, st>>>(pts[z], cz, n, point_format, check, wk.status);
+            SNARKV_LAUNCH_CHECK(ctx, "k_points_prepare");
+            sg.launched();
+            if (cz) pts[z] = cz;
+        }
     }
     {
         Stage sg(ctx, "msm_bucket_accumulate");
-        dim3 grid((pl.cap + 127) / 128, pl.W);
-        k_bucket_accumulate<<<grid, 128, 0, st>>>(points, wk.sorted, wk.offsets, wk.counts, wk.tasks, wk.window_tasks, wk.order, n, pl.NB,
+        dim3 grid((pl.cap + 127) / 128, pl.W, B);
+        k_bucket_accumulate<<<grid, 128, 0, st>>>(pts[0], pts[1], wk.sorted, wk.offsets, wk.counts, wk.tasks, wk.window_tasks, wk.order, n, pl.NB,
                                                  pl.T, pl.cap, wk.task_out);
         SNARKV_LAUNCH_CHECK(ctx, "k_bucket_accumulate");
         sg.launched();
@@ -574,35 +595,48 @@ static int msm_point_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* d_poi
         Stage sg(ctx, "msm_bucket_merge");
         const uint32_t total = (uint32_t)nbk;
         SNARKV_CUDA_TRY(ctx, cudaMemsetAsync(wk.big, 0, 4, st));
-        k_bucket_merge<<<(total + 127) / 128, 128, 0, st>>>(wk.task_out, wk.counts, wk.task_base, pl.NB, total, pl.T, pl.cap, wk.buckets,
+        k_bucket_merge<<<dim3((total + 127) / 128, B), 128, 0, st>>>(wk.task_out, wk.counts, wk.task_base, pl.NB, total, pl.T, pl.cap, wk.buckets,
                                                             wk.big, wk.big + 1);
         SNARKV_LAUNCH_CHECK(ctx, "k_bucket_merge");
         sg.launched();
-        k_bucket_merge_big<<<ctx->sm_count, 128, 0, st>>>(wk.task_out, wk.counts, wk.task_base, pl.NB, pl.T, pl.cap, wk.buckets, wk.big,
-                                                          wk.big + 1);
+        k_bucket_merge_big<<<dim3(ctx->sm_count, B), 128, 0, st>>>(wk.task_out, wk.counts, wk.task_base, pl.NB, pl.T, pl.cap, wk.buckets,
+                                                                   wk.big, wk.big + 1, pl.W);
         SNARKV_LAUNCH_CHECK(ctx, "k_bucket_merge_big");
         sg.launched();
     }
     {
         Stage sg(ctx, "msm_bucket_reduce");
-        dim3 grid((pl.J + 127) / 128, pl.W);
+        dim3 grid((pl.J + 127) / 128, pl.W, B);
         k_bucket_reduce<<<grid, 128, 0, st>>>(wk.buckets, pl.NB, pl.seg, pl.J, wk.segpart);
         SNARKV_LAUNCH_CHECK(ctx, "k_bucket_reduce");
         sg.launched();
     }
     {
         Stage sg(ctx, "msm_window_sum");
-        k_window_sum<<<pl.W, 128, 0, st>>>(wk.segpart, pl.J, wk.winsum);
+        k_window_sum<<<dim3(pl.W, B), 128, 0, st>>>(wk.segpart, pl.J, wk.winsum);
         SNARKV_LAUNCH_CHECK(ctx, "k_window_sum");
         sg.launched();
     }
     {
         Stage sg(ctx, "msm_final");
-        k_msm_final<<<1, 32, 0, st>>>(wk.winsum, pl.W, pl.c, out_format, d_out_affine, d_out_jacobian);
+        k_msm_final<<<B, 32, 0, st>>>(wk.winsum, pl.W, pl.c, out_format, d_out_affine, d_out_jacobian);
         SNARKV_LAUNCH_CHECK(ctx, "k_msm_final");
         sg.launched();
     }
     return SNARKV_OK;
+}
+
+// Two MSMs over the SAME scalars (KzgAs::verify: sum r^i lhs_i and sum r^i rhs_i, accumulation.rs:53-60): one digit/sort
+// phase, every point-phase kernel launched once with a batch dimension.  d_out_affine receives 2 x 64 B.
+int msm_run_device_pair(snarkv_ctx* ctx, const void* d_scalars, const void* d_points0, const void* d_points1, size_t n, int scalar_format,
+                        int point_format, int out_format, int flags, void* d_out_affine, void* d_status) {
+    const int check = (flags & SNARKV_CHECK_INPUTS) ? 1 : 0;
+    MsmWork wk;
+    int rc = msm_alloc(ctx, n, d_status, wk, 2);
+    if (rc) return rc;
+    rc = msm_sort_phase(ctx, wk, d_scalars, n, scalar_format, check);
+    if (rc) return rc;
+    return msm_point_phase(ctx, wk, d_points0, n, point_format, out_format, check, d_out_affine, nullptr, d_points1);
 }
 
 int msm_run_device(snarkv_ctx* ctx, const void* d_scalars, const void* d_points, size_t n, int scalar_format, int point_format,
