@@ -69,8 +69,8 @@ int snarkv_set_stream(snarkv_ctx* ctx, void* cuda_stream);
 /* MSM tuning: window bits c (0 = choose from n). */
 int snarkv_set_window_bits(snarkv_ctx* ctx, int c);
 
-/* KZG decide tuning: 0 = choose from N (default), 1 = one thread per check (throughput), 2 = one thread block per check
- * (latency).  Results are identical. */
+/* KZG decide tuning: 0 = choose from N (default), 1 = one thread per check (largest batches), 2 = cooperative (block or warp
+ * per check, chosen from N), 3 = one 160-thread block per check (lowest latency), 4 = one warp per check.  Results are identical. */
 int snarkv_set_pairing_mode(snarkv_ctx* ctx, int mode);
 
 /* ---- a1: EcPointLoader::multi_scalar_multiplication --------------------------------------------------------------------
@@ -106,6 +106,12 @@ int snarkv_g1_fold_partials_device(snarkv_ctx* ctx, const void* d_partials, size
  * (util/msm.rs:81-98) for many proofs at once; every segment must be non-empty. */
 int snarkv_g1_msm_batch(snarkv_ctx* ctx, const uint8_t* scalars, const uint8_t* points, const uint64_t* offsets, size_t m,
                         int format, int flags, uint8_t* out_affine);
+
+/* The same m MSMs fused into ONE by random linear combination:  out = sum_j rho^j * MSM_j  — the batching of
+ * pcs/kzg/decider.rs:146-185 applied to the verifier's `Msm::evaluate` calls themselves, so that a batch of proofs costs one
+ * large Pippenger pass instead of m small ones.  Scalars are multiplied by rho^j on the device (`r.powers(m)`, loader.rs:71-78). */
+int snarkv_g1_msm_batch_rlc(snarkv_ctx* ctx, const uint8_t* scalars, const uint8_t* points, const uint64_t* offsets, size_t m,
+                            const uint8_t rho[32], int format, int flags, uint8_t out_affine[64]);
 
 /* ---- a6: KzgAs::verify (accumulate) ------------------------------------------------------------------------------------
  * Replaces pcs/kzg/accumulation.rs:41-63: powers_of_r = r.powers(n) (loader.rs:71-78);

@@ -62,6 +62,7 @@ C_ABI = {
     "snarkv_g1_msm_device": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp, _vp, _vp]),
     "snarkv_g1_fold_partials_device": (_i, [_vp, _vp, _sz, _i, _vp]),
     "snarkv_g1_msm_batch": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _vp]),
+    "snarkv_g1_msm_batch_rlc": (_i, [_vp, _vp, _vp, _vp, _sz, _vp, _i, _i, _vp]),
     "snarkv_kzg_accumulate": (_i, [_vp, _vp, _vp, _sz, _vp, _i, _vp, _vp]),
     "snarkv_kzg_set_deciding_key": (_i, [_vp, _vp, _vp, _vp]),
     "snarkv_kzg_decide_batch": (_i, [_vp, _vp, _vp, _sz, _i, _vp, _vp]),
@@ -218,6 +219,15 @@ class CudaLoader:
     def field_op(self, field, op, a, b, n):
         out = ctypes.create_string_buffer(32 * n)
         self._check(self.lib.snarkv_debug_field_op(self.h, field, op, _addr(a), _addr(b), n, out), "field_op")
+        return out.raw
+
+    def msm_batch_rlc(self, scalars, points, offsets, rho, flags=0):
+        """sum_j rho^j * MSM_j as one MSM (scalars scaled by rho^j on the device)."""
+        m = len(offsets) - 1
+        off = (ctypes.c_uint64 * (m + 1))(*offsets)
+        out = ctypes.create_string_buffer(64)
+        self._check(self.lib.snarkv_g1_msm_batch_rlc(self.h, _addr(scalars), _addr(points), ctypes.cast(off, ctypes.c_void_p), m, bytes(rho),
+                                                     self.fmt, flags, out), "msm_batch_rlc")
         return out.raw
 
     # -- synthetic workload ---------------------------------------------------------------------------------------

@@ -83,7 +83,7 @@ int snarkv_set_window_bits(snarkv_ctx* ctx, int c) {
 }
 
 int snarkv_set_pairing_mode(snarkv_ctx* ctx, int mode) {
-    if (!ctx || mode < 0 || mode > 2) return SNARKV_ERR_USAGE;
+    if (!ctx || mode < 0 || mode > 4) return SNARKV_ERR_USAGE;
     ctx->pairing_mode = mode;
     return SNARKV_OK;
 }
@@ -179,6 +179,43 @@ int snarkv_g1_msm_batch(snarkv_ctx* ctx, const uint8_t* scalars, const uint8_t* 
     SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(&status, d_status, 4, cudaMemcpyDeviceToHost, st));
     SNARKV_CUDA_TRY(ctx, cudaStreamSynchronize(st));
     if (status != 0) return ctx->fail(status, status == SNARKV_ERR_BAD_SCALAR ? "scalar is not a canonical Fr" : "point is not a valid G1Affine");
+    return SNARKV_OK;
+}
+
+// sum_j rho^j * MSM_j as ONE MSM (scalars scaled on the device)
+int snarkv_g1_msm_batch_rlc(snarkv_ctx* ctx, const uint8_t* scalars, const uint8_t* points, const uint64_t* offsets, size_t m,
+                            const uint8_t rho[32], int format, int flags, uint8_t out_affine[64]) {
+    CTX_GUARD(ctx);
+    if (!scalars || !points || !offsets || !rho || !out_affine || bad_format(format) || m == 0)
+        return ctx->fail(SNARKV_ERR_USAGE, "snarkv_g1_msm_batch_rlc: bad argument");
+    if (offsets[0] != 0) return ctx->fail(SNARKV_ERR_USAGE, "offsets[0] must be 0");
+    for (size_t j = 0; j < m; ++j)
+        if (offsets[j + 1] <= offsets[j]) return ctx->fail(SNARKV_ERR_EMPTY, "empty or decreasing MSM segment");
+    const size_t total = offsets[m];
+    ctx->profile_begin_call();
+    uint8_t* d_s = (uint8_t*)ctx->wsget(WS_IO_A, total * 32);
+    uint8_t* d_p = (uint8_t*)ctx->wsget(WS_IO_B, total * 64);
+    uint64_t* d_off = (uint64_t*)ctx->wsget(WS_IO_C, (m + 1) * 8);
+    uint8_t* d_scaled = (uint8_t*)ctx->wsget(WS_IO_D, total * 32);
+    uint8_t* d_pw = (uint8_t*)ctx->wsget(WS_IO_E, m * 32 + 32);   // [rho | powers]
+    uint8_t* d_o = (uint8_t*)ctx->wsget(WS_OUT, 1024);            // [affine 64 | status 2 x 4 @64]
+    if (!d_s || !d_p || !d_off || !d_scaled || !d_pw || !d_o) return SNARKV_ERR_CUDA;
+    cudaStream_t st = ctx->stream;
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_pw, rho, 32, cudaMemcpyHostToDevice, st));
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_s, scalars, total * 32, cudaMemcpyHostToDevice, st));
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_off, offsets, (m + 1) * 8, cudaMemcpyHostToDevice, st));
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_p, points, total * 64, cudaMemcpyHostToDevice, st));
+    int rc = msm_batch_rlc_device(ctx, d_s, d_p, d_off, m, total, d_pw, format, flags, d_scaled, d_pw + 32, d_o, d_o + 64);
+    if (rc) return rc;
+    uint8_t host[72];
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(host, d_o, 72, cudaMemcpyDeviceToHost, st));
+    SNARKV_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    int st0, st1;
+    memcpy(&st0, host + 64, 4);
+    memcpy(&st1, host + 68, 4);
+    const int status = st0 ? st0 : st1;
+    if (status != 0) return ctx->fail(status, status == SNARKV_ERR_BAD_SCALAR ? "scalar is not a canonical Fr" : "point is not a valid G1Affine");
+    memcpy(out_affine, host, 64);
     return SNARKV_OK;
 }
 

@@ -41,6 +41,8 @@ enum WsSlot : int {
     WS_IO_B,
     WS_IO_C,
     WS_IO_D,
+    WS_IO_E,
+    WS_IO_F,
     WS_BATCH_TERMS,       // batch-MSM per-term XYZZ
     WS_PAIR_A,
     WS_PAIR_B,
@@ -164,6 +166,8 @@ void msm_plan_query(snarkv_ctx* ctx, size_t n, uint32_t out[4]);
 int msm_fold_partials_device(snarkv_ctx* ctx, const void* d_partials, size_t k, int format, void* d_out_affine);
 int msm_batch_device(snarkv_ctx* ctx, const void* d_scalars, const void* d_points, const void* d_offsets, size_t m, size_t total,
                      int format, int flags, void* d_out_affine, void* d_status);
+int msm_batch_rlc_device(snarkv_ctx* ctx, const void* d_scalars, const void* d_points, const void* d_offsets, size_t m, size_t total,
+                         const void* d_rho, int format, int flags, void* d_scaled, void* d_powers, void* d_out_affine, void* d_status);
 int fr_powers_device(snarkv_ctx* ctx, const void* d_r, int format, size_t n, void* d_out_mont);
 int field_op_device(snarkv_ctx* ctx, int field, int op, const void* d_a, const void* d_b, size_t n, void* d_out);
 int synth_scalars_device(snarkv_ctx* ctx, uint64_t seed, uint64_t start, size_t n, int format, void* d_out);

@@ -815,6 +815,49 @@ int fr_powers_device(snarkv_ctx* ctx, const void* d_r, int format, size_t n, voi
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// RLC fusion of many MSMs into one (the batching of pcs/kzg/decider.rs:146-185 applied before the MSM instead of after it):
+//   sum_j rho^j * MSM_j  =  one MSM over all terms with scalars  rho^j * s_ij .
+// k_fr_scale_segments multiplies every scalar of segment j by rho^j (powers from k_fr_powers) and leaves Montgomery form.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fr_scale_segments(const uint8_t* __restrict__ scalars, const uint64_t* __restrict__ offsets, size_t m,
+                                                           size_t total, int format, int check, const uint8_t* __restrict__ powers_mont,
+                                                           uint8_t* __restrict__ out_mont, int* __restrict__ status) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    size_t lo = 0, hi = m;   // largest j with offsets[j] <= i
+    while (hi - lo > 1) {
+        const size_t mid = (lo + hi) >> 1;
+        if (offsets[mid] <= i) lo = mid; else hi = mid;
+    }
+    Fr s = fp_load<FR>(scalars + i * 32);
+    if (format == SNARKV_CANONICAL) {
+        if (check && !fp_is_canonical(s)) atomicCAS(status, 0, SNARKV_ERR_BAD_SCALAR);
+        s = fp_to_mont(s);
+    }
+    fp_store<FR>(out_mont + i * 32, fp_mul(s, fp_load<FR>(powers_mont + lo * 32)));
+}
+
+int msm_batch_rlc_device(snarkv_ctx* ctx, const void* d_scalars, const void* d_points, const void* d_offsets, size_t m, size_t total,
+                         const void* d_rho, int format, int flags, void* d_scaled /* total x 32 B scratch */, void* d_powers /* m x 32 B */,
+                         void* d_out_affine, void* d_status) {
+    const int check = (flags & SNARKV_CHECK_INPUTS) ? 1 : 0;
+    int rc = fr_powers_device(ctx, d_rho, format, m, d_powers);
+    if (rc) return rc;
+    SNARKV_CUDA_TRY(ctx, cudaMemsetAsync(d_status, 0, 8, ctx->stream));
+    {
+        Stage sg(ctx, "fr_scale_segments");
+        k_fr_scale_segments<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>((const uint8_t*)d_scalars, (const uint64_t*)d_offsets, m,
+                                                                                      total, format, check, (const uint8_t*)d_powers,
+                                                                                      (uint8_t*)d_scaled, (int*)d_status);
+        SNARKV_LAUNCH_CHECK(ctx, "k_fr_scale_segments");
+        sg.launched();
+    }
+    // the MSM keeps its own status word right after ours so that a scalar error found above is not overwritten
+    return msm_run_device(ctx, d_scaled, d_points, total, SNARKV_MONTGOMERY, format, format, flags, d_out_affine, nullptr,
+                          (uint8_t*)d_status + 4);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // element-wise field operations (test support for the parity suite: pins fp.cuh against the golden field vectors)
 // ---------------------------------------------------------------------------------------------------------------------
 template <Field F>

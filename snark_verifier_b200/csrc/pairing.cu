@@ -251,8 +251,9 @@ int kzg_set_key(snarkv_ctx* ctx, const uint8_t g1[64], const uint8_t g2[128], co
 int kzg_decide_device(snarkv_ctx* ctx, const void* d_lhs, const void* d_rhs, size_t N, int format, void* d_accept, void* d_gt) {
     // Small and medium batches are latency-bound on one thread per check (13 ms per check regardless of N): give each check
     // a whole thread block instead (pairing_coop.cu).  Very large batches fill the machine either way; keep the leaner kernel.
-    // measured on B200: block-per-check 2.15 ms per wave of 3 blocks/SM; thread-per-check 13.2 ms flat up to ~16 K checks
-    const bool coop = ctx->pairing_mode == 2 || (ctx->pairing_mode == 0 && N <= (size_t)ctx->sm_count * 18);
+    // modes: 0 auto, 1 thread per check, 2 cooperative (block or warp per check by N), 3 block per check, 4 warp per check
+    // measured crossover on B200 (profiles/r01_pairing_modes.txt): warp-per-check 395 K checks/s vs thread-per-check 13.9 ms flat
+    const bool coop = ctx->pairing_mode >= 2 || (ctx->pairing_mode == 0 && N <= (size_t)ctx->sm_count * 37);
     if (coop) return kzg_decide_coop_device(ctx, d_lhs, d_rhs, N, format, d_accept, d_gt);
     Fq12* f = (Fq12*)ctx->wsget(WS_PAIR_A, N * sizeof(Fq12));
     uint8_t* bad = (uint8_t*)ctx->wsget(WS_PAIR_B, N);

@@ -21,7 +21,8 @@ namespace snarkv {
 
 namespace coop {
 
-constexpr int NT = 160;          // 5 warps: 144 product threads + 6 line-preparation threads (+ idle)
+// threads per check: 160 (5 warps: one product per thread, lowest latency) or 32 (one warp: 4-5 products per lane, ~5x the
+// checks per SM).  Template parameter NT of the kernel and of every cooperative operation below.
 constexpr int NREG = 14;         // Fq12 registers in shared memory
 constexpr int NUM_COEFFS = SNARKV_ATE_NUM_COEFFS;
 constexpr int NAF_LEN = SNARKV_ATE_NAF_LEN;
@@ -53,9 +54,10 @@ __device__ __forceinline__ void st(Fq* p, const Fq& a) {
 __device__ __forceinline__ Fq times9(const Fq& a) { return fp_add(fp_dbl(fp_dbl(fp_dbl(a))), a); }
 
 // line preparation for coefficient `idx` of pair `pair` into sm.line[buf]; executed by threads 144..149
+template <int NT>
 static __device__ __noinline__ void prep_line(Smem& sm, const uint8_t* __restrict__ coeffs, int pair, int idx, int buf, int t) {
-    const int k = t - 144;
-    if (k < 0 || k >= 6) return;
+    const int k = t - (NT - 6);   // the last six threads of the block
+    if (k < 0) return;
     const uint8_t* c = coeffs + ((size_t)pair * NUM_COEFFS + idx) * 192;   // cy(64) | cx(64) | c0(64)
     Fq v = fp_load<FQ>(c + 32 * k);
     if (k < 2) v = fp_mul(v, ld(&sm.py[pair]));
@@ -97,18 +99,18 @@ static __device__ __noinline__ void columns_and_fold(Smem& sm, Fq* dst, int nb, 
 
 // dst = a * b (full Fq12 product; dst may alias a or b).  While the products run, threads 144..149 optionally prepare the
 // line operands (pair, idx) for a later sparse product into sm.line[buf].
-static __device__ __noinline__ void op_mul(Smem& sm, Fq* dst, const Fq* a, const Fq* b, int t, const uint8_t* coeffs = nullptr,
-                                       int pair = 0, int idx = 0, int buf = 0) {
-    if (t < 144) st(&sm.prod[t], fp_mul(ld(&a[t / 12]), ld(&b[t % 12])));
-    else if (coeffs) prep_line(sm, coeffs, pair, idx, buf, t);
+template <int NT>
+static __device__ __noinline__ void op_mul(Smem& sm, Fq* dst, const Fq* a, const Fq* b, int t) {
+#pragma unroll 1
+    for (int q = t; q < 144; q += NT) st(&sm.prod[q], fp_mul(ld(&a[q / 12]), ld(&b[q % 12])));
     __syncthreads();
     columns_and_fold(sm, dst, 12, t);
 }
 // dst = a * line[buf]  (sparse: B = l0 + l1 w + l3 w^3)
-static __device__ __noinline__ void op_sparse(Smem& sm, Fq* dst, const Fq* a, int buf, int t, const uint8_t* coeffs = nullptr, int pair = 0,
-                                          int idx = 0, int nbuf = 0) {
-    if (t < 72) st(&sm.prod[t], fp_mul(ld(&a[t / 6]), ld(&sm.line[buf][t % 6])));
-    else if (coeffs) prep_line(sm, coeffs, pair, idx, nbuf, t);
+template <int NT>
+static __device__ __noinline__ void op_sparse(Smem& sm, Fq* dst, const Fq* a, int buf, int t) {
+#pragma unroll 1
+    for (int q = t; q < 72; q += NT) st(&sm.prod[q], fp_mul(ld(&a[q / 6]), ld(&sm.line[buf][q % 6])));
     __syncthreads();
     columns_and_fold(sm, dst, 6, t);
 }
@@ -166,6 +168,7 @@ static __device__ __noinline__ void op_inverse_serial(Fq* dst, const Fq* a, int 
 }
 
 // dst = a^u (u = BN parameter, 63 bits), a in the cyclotomic subgroup.  Uses BASE and dst as scratch.
+template <int NT>
 static __device__ __noinline__ void op_exp_by_u(Smem& sm, Fq* dst, const Fq* a, int t) {
     Fq* base = sm.reg[BASE];
     op_copy(base, a, t);
@@ -173,8 +176,8 @@ static __device__ __noinline__ void op_exp_by_u(Smem& sm, Fq* dst, const Fq* a, 
     const uint64_t u = SNARKV_BN_U;
 #pragma unroll 1
     for (int i = 61; i >= 0; --i) {
-        op_mul(sm, dst, dst, dst, t);
-        if ((u >> i) & 1ull) op_mul(sm, dst, dst, base, t);
+        op_mul<NT>(sm, dst, dst, dst, t);
+        if ((u >> i) & 1ull) op_mul<NT>(sm, dst, dst, base, t);
     }
 }
 
@@ -182,7 +185,8 @@ static __device__ __noinline__ void op_exp_by_u(Smem& sm, Fq* dst, const Fq* a, 
 
 using namespace coop;
 
-__global__ void __launch_bounds__(coop::NT, 3) k_kzg_decide_coop(const uint8_t* __restrict__ lhs, const uint8_t* __restrict__ rhs, size_t N, int format,
+template <int NT>
+__global__ void __launch_bounds__(NT, (NT == 32) ? 16 : 3) k_kzg_decide_coop(const uint8_t* __restrict__ lhs, const uint8_t* __restrict__ rhs, size_t N, int format,
                                                              const uint8_t* __restrict__ coeffs, const int* __restrict__ infinity,
                                                              uint8_t* __restrict__ accept, uint8_t* __restrict__ gt_out) {
     __shared__ Smem sm;
@@ -220,34 +224,34 @@ __global__ void __launch_bounds__(coop::NT, 3) k_kzg_decide_coop(const uint8_t* 
         // ---- multi-Miller loop (shared squarings; pairs with an identity skipped) ------------------------------------------
         // line operands are staged one step ahead by threads 144..149 during the previous operation's product phase
         int idx = 0;
-        if (live0) prep_line(sm, coeffs, 0, 0, 0, t);
-        if (live1) prep_line(sm, coeffs, 1, 0, 1, t);
+        if (live0) prep_line<NT>(sm, coeffs, 0, 0, 0, t);
+        if (live1) prep_line<NT>(sm, coeffs, 1, 0, 1, t);
         __syncthreads();
 #pragma unroll 1
         for (int b = NAF_LEN - 2; b >= 0; --b) {
             const int steps = (ATE_NAF[b] != 0) ? 2 : 1;
-            if (b != NAF_LEN - 2) op_mul(sm, f, f, f, t);
+            if (b != NAF_LEN - 2) op_mul<NT>(sm, f, f, f, t);
 #pragma unroll 1
             for (int s = 0; s < steps; ++s) {
                 // buffers 0/1 hold the operands for (pair 0, idx) / (pair 1, idx); refill each buffer for idx + 1 right after use
-                if (live0) op_sparse(sm, f, f, 0, t);
-                if (live1) op_sparse(sm, f, f, 1, t);
+                if (live0) op_sparse<NT>(sm, f, f, 0, t);
+                if (live1) op_sparse<NT>(sm, f, f, 1, t);
                 ++idx;
                 if (idx < NUM_COEFFS) {
-                    if (live0) prep_line(sm, coeffs, 0, idx, 0, t);
-                    if (live1) prep_line(sm, coeffs, 1, idx, 1, t);
+                    if (live0) prep_line<NT>(sm, coeffs, 0, idx, 0, t);
+                    if (live1) prep_line<NT>(sm, coeffs, 1, idx, 1, t);
                     __syncthreads();
                 }
             }
         }
 #pragma unroll 1
         for (int extra = 0; extra < 2; ++extra) {
-            if (live0) op_sparse(sm, f, f, 0, t);
-            if (live1) op_sparse(sm, f, f, 1, t);
+            if (live0) op_sparse<NT>(sm, f, f, 0, t);
+            if (live1) op_sparse<NT>(sm, f, f, 1, t);
             ++idx;
             if (idx < NUM_COEFFS) {
-                if (live0) prep_line(sm, coeffs, 0, idx, 0, t);
-                if (live1) prep_line(sm, coeffs, 1, idx, 1, t);
+                if (live0) prep_line<NT>(sm, coeffs, 0, idx, 0, t);
+                if (live1) prep_line<NT>(sm, coeffs, 1, idx, 1, t);
                 __syncthreads();
             }
         }
@@ -256,44 +260,44 @@ __global__ void __launch_bounds__(coop::NT, 3) k_kzg_decide_coop(const uint8_t* 
         // easy part: f <- conj(f) * f^-1 ; f <- f^(p^2) * f.   The single Fq12 inversion is serial (thread 0, tower code).
         op_inverse_serial(sm.reg[T0], f, t);
         op_conj(sm, sm.reg[T1], f, t);
-        op_mul(sm, f, sm.reg[T1], sm.reg[T0], t);
+        op_mul<NT>(sm, f, sm.reg[T1], sm.reg[T0], t);
         op_frobenius(sm, sm.reg[T0], f, 2, t);
-        op_mul(sm, f, sm.reg[T0], f, t);
+        op_mul<NT>(sm, f, sm.reg[T0], f, t);
         // hard part (p^4 - p^2 + 1)/r: y0 y1^2 y2^6 y3^12 y4^18 y5^30 y6^36 (Devegili-Scott-Dahab)
-        op_exp_by_u(sm, sm.reg[FU], f, t);
-        op_exp_by_u(sm, sm.reg[FU2], sm.reg[FU], t);
-        op_exp_by_u(sm, sm.reg[FU3], sm.reg[FU2], t);
+        op_exp_by_u<NT>(sm, sm.reg[FU], f, t);
+        op_exp_by_u<NT>(sm, sm.reg[FU2], sm.reg[FU], t);
+        op_exp_by_u<NT>(sm, sm.reg[FU3], sm.reg[FU2], t);
         op_frobenius(sm, sm.reg[Y0], f, 1, t);                       // y0 = f^p f^(p^2) f^(p^3)
         op_frobenius(sm, sm.reg[T0], f, 2, t);
-        op_mul(sm, sm.reg[Y0], sm.reg[Y0], sm.reg[T0], t);
+        op_mul<NT>(sm, sm.reg[Y0], sm.reg[Y0], sm.reg[T0], t);
         op_frobenius(sm, sm.reg[T0], f, 3, t);
-        op_mul(sm, sm.reg[Y0], sm.reg[Y0], sm.reg[T0], t);
+        op_mul<NT>(sm, sm.reg[Y0], sm.reg[Y0], sm.reg[T0], t);
         op_conj(sm, sm.reg[Y1], f, t);                               // y1 = 1/f
         op_frobenius(sm, sm.reg[Y2], sm.reg[FU2], 2, t);             // y2 = (f^(u^2))^(p^2)
         op_frobenius(sm, sm.reg[T0], sm.reg[FU], 1, t);              // y3 = 1/(f^u)^p
         op_conj(sm, sm.reg[Y3], sm.reg[T0], t);
         op_frobenius(sm, sm.reg[T0], sm.reg[FU2], 1, t);             // y4 = 1/(f^u (f^(u^2))^p)
-        op_mul(sm, sm.reg[T0], sm.reg[T0], sm.reg[FU], t);
+        op_mul<NT>(sm, sm.reg[T0], sm.reg[T0], sm.reg[FU], t);
         op_conj(sm, sm.reg[Y4], sm.reg[T0], t);
         op_conj(sm, sm.reg[Y5], sm.reg[FU2], t);                     // y5 = 1/f^(u^2)
         op_frobenius(sm, sm.reg[T0], sm.reg[FU3], 1, t);             // y6 = 1/(f^(u^3) (f^(u^3))^p)
-        op_mul(sm, sm.reg[T0], sm.reg[T0], sm.reg[FU3], t);
+        op_mul<NT>(sm, sm.reg[T0], sm.reg[T0], sm.reg[FU3], t);
         op_conj(sm, sm.reg[Y6], sm.reg[T0], t);
         Fq* t0 = sm.reg[T0];
         Fq* t1 = sm.reg[T1];
-        op_mul(sm, t0, sm.reg[Y6], sm.reg[Y6], t);                   // t0 = y6^2 y4 y5
-        op_mul(sm, t0, t0, sm.reg[Y4], t);
-        op_mul(sm, t0, t0, sm.reg[Y5], t);
-        op_mul(sm, t1, sm.reg[Y3], sm.reg[Y5], t);                   // t1 = y3 y5 t0
-        op_mul(sm, t1, t1, t0, t);
-        op_mul(sm, t0, t0, sm.reg[Y2], t);                           // t0 = t0 y2
-        op_mul(sm, t1, t1, t1, t);                                   // t1 = (t1^2 t0)^2
-        op_mul(sm, t1, t1, t0, t);
-        op_mul(sm, t1, t1, t1, t);
-        op_mul(sm, t0, t1, sm.reg[Y1], t);                           // t0 = t1 y1
-        op_mul(sm, t1, t1, sm.reg[Y0], t);                           // t1 = t1 y0
-        op_mul(sm, t0, t0, t0, t);                                   // gt = t0^2 t1
-        op_mul(sm, f, t0, t1, t);
+        op_mul<NT>(sm, t0, sm.reg[Y6], sm.reg[Y6], t);                   // t0 = y6^2 y4 y5
+        op_mul<NT>(sm, t0, t0, sm.reg[Y4], t);
+        op_mul<NT>(sm, t0, t0, sm.reg[Y5], t);
+        op_mul<NT>(sm, t1, sm.reg[Y3], sm.reg[Y5], t);                   // t1 = y3 y5 t0
+        op_mul<NT>(sm, t1, t1, t0, t);
+        op_mul<NT>(sm, t0, t0, sm.reg[Y2], t);                           // t0 = t0 y2
+        op_mul<NT>(sm, t1, t1, t1, t);                                   // t1 = (t1^2 t0)^2
+        op_mul<NT>(sm, t1, t1, t0, t);
+        op_mul<NT>(sm, t1, t1, t1, t);
+        op_mul<NT>(sm, t0, t1, sm.reg[Y1], t);                           // t0 = t1 y1
+        op_mul<NT>(sm, t1, t1, sm.reg[Y0], t);                           // t1 = t1 y0
+        op_mul<NT>(sm, t0, t0, t0, t);                                   // gt = t0^2 t1
+        op_mul<NT>(sm, f, t0, t1, t);
 
         // ---- verdict + optional GT bytes ------------------------------------------------------------------------------------
         if (t == 0) {
@@ -309,11 +313,17 @@ __global__ void __launch_bounds__(coop::NT, 3) k_kzg_decide_coop(const uint8_t* 
 int kzg_decide_coop_device(snarkv_ctx* ctx, const void* d_lhs, const void* d_rhs, size_t N, int format, void* d_accept, void* d_gt) {
     const uint8_t* base = (const uint8_t*)ctx->d_key_coeffs;
     const int* d_inf = (const int*)(base + (size_t)2 * coop::NUM_COEFFS * 192);
-    const size_t cap = (size_t)ctx->sm_count * 16;
+    // up to one wave of 160-thread blocks (3 per SM): lowest latency; beyond that one warp per check (16 per SM)
+    const bool wide = ctx->pairing_mode == 3 || (ctx->pairing_mode != 4 && N <= (size_t)ctx->sm_count * 3);
+    const size_t cap = (size_t)ctx->sm_count * (wide ? 3 : 16) * 4;
     const unsigned blocks = (unsigned)(N < cap ? N : cap);
-    Stage sg(ctx, "kzg_decide_coop");
-    k_kzg_decide_coop<<<blocks, coop::NT, 0, ctx->stream>>>((const uint8_t*)d_lhs, (const uint8_t*)d_rhs, N, format, base, d_inf,
-                                                          (uint8_t*)d_accept, (uint8_t*)d_gt);
+    Stage sg(ctx, wide ? "kzg_decide_block_per_check" : "kzg_decide_warp_per_check");
+    if (wide)
+        k_kzg_decide_coop<160><<<blocks, 160, 0, ctx->stream>>>((const uint8_t*)d_lhs, (const uint8_t*)d_rhs, N, format, base, d_inf,
+                                                              (uint8_t*)d_accept, (uint8_t*)d_gt);
+    else
+        k_kzg_decide_coop<32><<<blocks, 32, 0, ctx->stream>>>((const uint8_t*)d_lhs, (const uint8_t*)d_rhs, N, format, base, d_inf,
+                                                            (uint8_t*)d_accept, (uint8_t*)d_gt);
     SNARKV_LAUNCH_CHECK(ctx, "k_kzg_decide_coop");
     sg.launched();
     return SNARKV_OK;

@@ -235,6 +235,7 @@ def test_msm_linearity_property(loader):
     n = 1 << 18
     dp = torch.empty(n * 64, dtype=torch.uint8, device="cuda")
     loader.synth_points_device(55, 0, n, dp.data_ptr())
+    torch.cuda.synchronize()
     s1 = np.frombuffer(oracle.synth_scalars(55, 0, n), dtype=np.uint8)
     s2 = np.frombuffer(oracle.synth_scalars(56, 0, n), dtype=np.uint8)
     a = [int.from_bytes(s1[32 * i:32 * i + 32].tobytes(), "little") for i in range(n)]
@@ -255,7 +256,7 @@ def kzg(loader, golden):
     return sv.KzgAs(loader, dk)
 
 
-@pytest.fixture(params=[1, 2], ids=["thread_per_check", "block_per_check"])
+@pytest.fixture(params=[1, 3, 4], ids=["thread_per_check", "block_per_check", "warp_per_check"])
 def pairing_mode(request, loader):
     loader.set_pairing_mode(request.param)
     yield request.param
@@ -425,3 +426,36 @@ def test_host_entry_chunk_pipeline_matches_device_path(loader):
     loader.fold_partials_device(part.data_ptr(), 1, out.data_ptr())
     torch.cuda.synchronize()
     assert bytes(out.cpu().numpy()) == got
+
+
+def test_msm_batch_rlc_equals_combination_of_native_folds(loader):
+    """sum_j rho^j * MSM_j computed as one fused MSM == the same combination of the per-proof NativeLoader folds."""
+    sizes = [21, 3, 20, 1, 24, 7, 21, 3]
+    offs = [0]
+    for k in sizes:
+        offs.append(offs[-1] + k)
+    total = offs[-1]
+    s = oracle.synth_scalars(61, 0, total); p = oracle.synth_points(61, 0, total, 8)
+    rho = oracle.synth_scalars(62, 0, 1)
+    got = loader.msm_batch_rlc(s, p, offs, rho, flags=sv.CHECK_INPUTS)
+    r = int.from_bytes(rho, "little")
+    acc = bytes(64)
+    for j, k in enumerate(sizes):
+        lo = offs[j]
+        part = oracle.msm_native(s[32 * lo:32 * (lo + k)], p[64 * lo:64 * (lo + k)], k)
+        acc = oracle.g1_add(acc, oracle.g1_mul(part, le(pow(r, j, m.R))))
+    assert got == acc
+
+
+def test_msm_heavily_skewed_large(loader):
+    """2^20 terms, every scalar = 1 (Msm::base) or = r-1: one bucket per window holds every term -> 2048+ tasks per bucket."""
+    import torch
+    n = 1 << 20
+    dp = torch.empty(n * 64, dtype=torch.uint8, device="cuda")
+    loader.synth_points_device(66, 0, n, dp.data_ptr())
+    torch.cuda.synchronize()          # the *_device entry points are asynchronous on the loader's own stream
+    pts = dp.cpu().numpy()
+    t = oracle.synth_point_scalars(66, 0, n)
+    for val in (1, m.R - 1):
+        s = np.frombuffer(le(val) * n, dtype=np.uint8)
+        assert loader.msm(s, pts, n) == oracle.msm_expected_from_dlogs(s, t, n), val

@@ -1,5 +1,5 @@
 import os, sys, torch
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import snark_verifier_b200 as sv
 L = sv.CudaLoader(0)
 g2 = bytes.fromhex(
@@ -7,12 +7,15 @@ g2 = bytes.fromhex(
     "aa7dfa6601cce64c7bd3430c69e7d1e38f40cb8d8071ab4aeb6d8cdba55ec8125b9722d1dcdaac55f38eb37033314bbc95330c69ad999eec75f05f58d0890609")
 gen = (1).to_bytes(32, "little") + (2).to_bytes(32, "little")
 kz = sv.KzgAs(L, sv.KzgDecidingKey(gen, g2, g2))
-n = 1 << 18
+n = 1 << 17
 pts = torch.empty(n * 64, dtype=torch.uint8, device="cuda"); acc = torch.zeros(n, dtype=torch.uint8, device="cuda")
 L.synth_points_device(7, 0, n, pts.data_ptr())
-L.set_pairing_mode(1); L.profile(True)
-for cnt in (4096, 1 << 14, 1 << 16, 1 << 18):
-    for _ in range(2):
-        kz.decide_batch_device(pts.data_ptr(), pts.data_ptr(), cnt, acc.data_ptr()); torch.cuda.synchronize()
-    st = L.stage_times(); tot = sum(x[1] for x in st)
-    print("thread-mode N=%d: %.2f ms %.0f checks/s ok=%s %s" % (cnt, tot, cnt / tot * 1e3, bool(acc[:cnt].min().item() == 1), st))
+L.profile(True)
+for mode, name in ((1, "thread"), (3, "block"), (4, "warp"), (0, "auto")):
+    L.set_pairing_mode(mode)
+    for cnt in (1, 444, 1024, 2368, 4096, 1 << 14, 1 << 16, 1 << 17):
+        if mode == 3 and cnt > 4096: continue
+        for _ in range(2):
+            kz.decide_batch_device(pts.data_ptr(), pts.data_ptr(), cnt, acc.data_ptr()); torch.cuda.synchronize()
+        st = L.stage_times(); tot = sum(x[1] for x in st)
+        print("%-6s N=%-6d %8.2f ms %9.0f checks/s ok=%s" % (name, cnt, tot, cnt / tot * 1e3, bool(acc[:cnt].min().item() == 1)), flush=True)
