@@ -224,9 +224,9 @@ class CudaLoader:
     def msm_batch_rlc(self, scalars, points, offsets, rho, flags=0):
         """sum_j rho^j * MSM_j as one MSM (scalars scaled by rho^j on the device)."""
         m = len(offsets) - 1
-        off = (ctypes.c_uint64 * (m + 1))(*offsets)
+        off = offsets if hasattr(offsets, "ctypes") else (ctypes.c_uint64 * (m + 1))(*offsets)   # numpy uint64 array or sequence
         out = ctypes.create_string_buffer(64)
-        self._check(self.lib.snarkv_g1_msm_batch_rlc(self.h, _addr(scalars), _addr(points), ctypes.cast(off, ctypes.c_void_p), m, bytes(rho),
+        self._check(self.lib.snarkv_g1_msm_batch_rlc(self.h, _addr(scalars), _addr(points), _addr(off), m, bytes(rho),
                                                      self.fmt, flags, out), "msm_batch_rlc")
         return out.raw
 
