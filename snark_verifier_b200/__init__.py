@@ -83,6 +83,12 @@ def load_library():
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
+            # not a fallback: build the sm_100a library in-tree if the toolchain is here, otherwise fail loudly
+            import shutil
+            import subprocess
+            if shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"):
+                subprocess.call(["make", "-C", os.path.join(_HERE, "csrc"), "-j4", "-s"])
+        if not os.path.exists(LIB_PATH):
             raise CudaError(f"{LIB_PATH} is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
                             "there is no CPU fallback")
         lib = ctypes.CDLL(LIB_PATH)

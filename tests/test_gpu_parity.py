@@ -459,3 +459,70 @@ def test_msm_heavily_skewed_large(loader):
     for val in (1, m.R - 1):
         s = np.frombuffer(le(val) * n, dtype=np.uint8)
         assert loader.msm(s, pts, n) == oracle.msm_expected_from_dlogs(s, t, n), val
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# halo2curves in-memory layout (SNARKV_MONTGOMERY) through the KZG entry points, device-variant validation, odd inputs
+# ---------------------------------------------------------------------------------------------------------------------
+def test_decide_and_accumulate_in_montgomery_layout(mont_loader, golden):
+    g = golden("pairing")
+    kz = sv.KzgAs(mont_loader, sv.KzgDecidingKey(m.g1_to_bytes(m.G1_GEN), H(g["g2_generator"]), H(g["s_g2"])))   # key is always canonical
+    checks = g["checks"]
+    lhs = to_mont_pts(b"".join(H(c["lhs"]) for c in checks)); rhs = to_mont_pts(b"".join(H(c["rhs"]) for c in checks))
+    for mode in (1, 3, 4):
+        mont_loader.set_pairing_mode(mode)
+        acc, gt = kz.decide_batch(lhs, rhs, len(checks), want_gt=True)
+        assert list(acc) == [int(c["accept"]) for c in checks]
+        assert gt == b"".join(H(c["gt"]) for c in checks)          # GT is always canonical bytes
+    mont_loader.set_pairing_mode(0)
+    c = golden("accumulate")[2]
+    n = c["n"]
+    ml, mr = to_mont_pts(H(c["lhs"])), to_mont_pts(H(c["rhs"]))
+    accs = [sv.KzgAccumulator(ml[64 * i:64 * i + 64], mr[64 * i:64 * i + 64]) for i in range(n)]
+    out = kz.verify(accs, oracle.fp_to_mont(1, H(c["r"])))
+    assert (out.lhs, out.rhs) == (to_mont_pts(H(c["out_lhs"])), to_mont_pts(H(c["out_rhs"])))
+
+
+def test_device_entry_validation_and_alignment(loader):
+    import torch
+    n = 64
+    s = bytearray(oracle.synth_scalars(5, 0, n)); p = bytearray(oracle.synth_points(5, 0, n, 2))
+    s[32 * 7:32 * 8] = le(m.R)                      # non-canonical scalar
+    ds = torch.frombuffer(s, dtype=torch.uint8).cuda(); dp = torch.frombuffer(p, dtype=torch.uint8).cuda()
+    out = torch.zeros(64, dtype=torch.uint8, device="cuda"); st = torch.zeros(4, dtype=torch.uint8, device="cuda")
+    loader.msm_device(ds.data_ptr(), dp.data_ptr(), n, d_out_affine=out.data_ptr(), d_status=st.data_ptr(), flags=sv.CHECK_INPUTS)
+    torch.cuda.synchronize()
+    assert int.from_bytes(bytes(st.cpu().numpy()), "little", signed=True) == sv.ERR_BAD_SCALAR
+    p[64 * 9 + 32] ^= 1                              # y of point 9 off the curve
+    s[32 * 7:32 * 8] = le(5)
+    ds = torch.frombuffer(s, dtype=torch.uint8).cuda(); dp = torch.frombuffer(p, dtype=torch.uint8).cuda()
+    loader.msm_device(ds.data_ptr(), dp.data_ptr(), n, d_out_affine=out.data_ptr(), d_status=st.data_ptr(), flags=sv.CHECK_INPUTS)
+    torch.cuda.synchronize()
+    assert int.from_bytes(bytes(st.cpu().numpy()), "little", signed=True) == sv.ERR_BAD_POINT
+    with pytest.raises(sv.Error):                    # the TMA-staged scalar stream needs 16-byte alignment
+        loader.msm_device(ds.data_ptr() + 4, dp.data_ptr(), n - 1, d_out_affine=out.data_ptr())
+
+
+def test_fold_partials_with_identity_and_cancelling_partials(loader):
+    import torch
+    gen = m.g1_to_bytes(m.G1_GEN)
+    parts = torch.zeros(4 * 96, dtype=torch.uint8, device="cuda")
+    out = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    ds = torch.frombuffer(bytearray(le(7) + le(m.R - 7) + le(0) + le(3)), dtype=torch.uint8).cuda()
+    dp = torch.frombuffer(bytearray(gen * 4), dtype=torch.uint8).cuda()
+    for j in range(4):                               # partials: 7G, -7G, identity, 3G
+        loader.msm_device(ds.data_ptr() + 32 * j, dp.data_ptr() + 64 * j, 1, d_out_jacobian=parts.data_ptr() + 96 * j)
+        torch.cuda.synchronize()
+    loader.fold_partials_device(parts.data_ptr(), 4, out.data_ptr()); torch.cuda.synchronize()
+    assert bytes(out.cpu().numpy()) == oracle.g1_mul(gen, le(3))
+    loader.fold_partials_device(parts.data_ptr(), 3, out.data_ptr()); torch.cuda.synchronize()
+    assert bytes(out.cpu().numpy()) == bytes(64)     # 7G - 7G + O = identity = (0, 0)
+
+
+def test_msm_batch_validation_and_empty_segment(loader):
+    s = oracle.synth_scalars(6, 0, 8); p = oracle.synth_points(6, 0, 8, 2)
+    with pytest.raises(sv.Error):
+        loader.msm_batch(s, p, [0, 3, 3, 8])         # an empty MSM panics in the reference (native.rs:69)
+    bad = bytearray(p); bad[64 * 2:64 * 3] = le(1) + le(3)
+    with pytest.raises(sv.Error):
+        loader.msm_batch(s, bytes(bad), [0, 4, 8], flags=sv.CHECK_INPUTS)
