@@ -56,7 +56,7 @@ struct snarkv_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // second stream for host->device copies that overlap kernels
-    cudaEvent_t copy_done[5] = {};        // one per host chunk + one fence
+    cudaEvent_t copy_done[8] = {};        // one per host chunk (<= 6) + one fence
     std::string err;
     int window_bits = 0;
     int pairing_mode = 0;   // 0 = choose from N, 1 = one thread per check, 2 = one block per check

@@ -22,7 +22,7 @@
 
 namespace snarkv {
 
-#define SNARKV_HOST_CHUNKS 4
+#define SNARKV_HOST_CHUNKS 6
 
 struct MsmPlan {
     uint32_t c;    // window bits
@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(128) k_bucket_accumulate(const uint8_t* __rest
 __global__ void __launch_bounds__(128) k_bucket_merge(const uint8_t* __restrict__ task_out, const uint32_t* __restrict__ counts,
                                                       const uint32_t* __restrict__ task_base, uint32_t NB, uint32_t total, uint32_t T,
                                                       uint32_t cap, uint8_t* __restrict__ buckets, uint32_t* __restrict__ big_count,
-                                                      uint32_t* __restrict__ big_list) {
+                                                      uint32_t* __restrict__ big_list, int add_existing) {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= total) return;
     const uint32_t w = tid / NB;
@@ -350,8 +350,10 @@ __global__ void __launch_bounds__(128) k_bucket_merge(const uint8_t* __restrict_
         return;
     }
     const size_t base = (size_t)w * cap + task_base[tid];
-    G1Xyzz acc = xyzz_identity();
-    if (parts == 1) acc = xyzz_load(task_out, base);
+    // add_existing: this launch belongs to a later term-chunk of the same MSM; the bucket already holds the earlier chunks' sum
+    if (add_existing && parts == 0) return;
+    G1Xyzz acc = add_existing ? xyzz_load(buckets, tid) : xyzz_identity();
+    if (parts == 1 && !add_existing) acc = xyzz_load(task_out, base);
     else
         for (uint32_t j = 0; j < parts; ++j) acc = xyzz_add(acc, xyzz_load(task_out, base + j));
     xyzz_store(buckets, tid, acc);
@@ -359,7 +361,7 @@ __global__ void __launch_bounds__(128) k_bucket_merge(const uint8_t* __restrict_
 __global__ void __launch_bounds__(128) k_bucket_merge_big(const uint8_t* __restrict__ task_out, const uint32_t* __restrict__ counts,
                                                           const uint32_t* __restrict__ task_base, uint32_t NB, uint32_t T, uint32_t cap,
                                                           uint8_t* __restrict__ buckets, const uint32_t* __restrict__ big_count,
-                                                          const uint32_t* __restrict__ big_list, uint32_t W) {
+                                                          const uint32_t* __restrict__ big_list, uint32_t W, int add_existing) {
     __shared__ G1Xyzz sm[128];
     const uint32_t t = threadIdx.x;
     task_out += (size_t)blockIdx.y * W * cap * 128;
@@ -377,7 +379,7 @@ __global__ void __launch_bounds__(128) k_bucket_merge_big(const uint8_t* __restr
             if (t < s) sm[t] = xyzz_add(sm[t], sm[t + s]);
             __syncthreads();
         }
-        if (t == 0) xyzz_store(buckets, tid, sm[0]);
+        if (t == 0) xyzz_store(buckets, tid, add_existing ? xyzz_add(xyzz_load(buckets, tid), sm[0]) : sm[0]);
         __syncthreads();
     }
 }
@@ -559,9 +561,12 @@ static int msm_sort_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* d_scal
     return SNARKV_OK;
 }
 
-// B = 1 or 2 base sets share the scalars / sort of `wk`; results land at d_out_affine + 64 z and d_out_jacobian + 96 z.
-static int msm_point_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* d_points, size_t n, int point_format, int out_format,
-                           int check, void* d_out_affine, void* d_out_jacobian, const void* d_points1 = nullptr) {
+// Point phase, first half: (convert,) gather-accumulate the sorted terms into task results and merge them into the bucket
+// array.  B = 1 or 2 base sets share the scalars / sort of `wk`.  `add_existing`: the buckets already hold the sums of earlier
+// term-chunks of the same MSM (host entry point pipeline) and this chunk is added on top.  `conv_dst`: caller-provided
+// destination for the Montgomery copy of CANONICAL points (B must be 1).
+static int msm_accumulate_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* d_points, size_t n, int point_format, int check,
+                                const void* d_points1 = nullptr, int add_existing = 0, uint8_t* conv_dst = nullptr) {
     const MsmPlan& pl = wk.pl;
     cudaStream_t st = ctx->stream;
     const size_t nbk = (size_t)pl.W * pl.NB;
@@ -571,7 +576,7 @@ static int msm_point_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* d_poi
         Stage sg(ctx, "msm_points_prepare");
         uint8_t* conv = nullptr;
         if (point_format == SNARKV_CANONICAL) {
-            conv = (uint8_t*)ctx->wsget(WS_POINTS_MONT, (size_t)B * n * 64);
+            conv = conv_dst ? conv_dst : (uint8_t*)ctx->wsget(WS_POINTS_MONT, (size_t)B * n * 64);
             if (!conv) return SNARKV_ERR_CUDA;
         }
         const size_t want = (n + 255) / 256, cap = (size_t)ctx->sm_count * 8;
@@ -596,14 +601,22 @@ static int msm_point_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* d_poi
         const uint32_t total = (uint32_t)nbk;
         SNARKV_CUDA_TRY(ctx, cudaMemsetAsync(wk.big, 0, 4, st));
         k_bucket_merge<<<dim3((total + 127) / 128, B), 128, 0, st>>>(wk.task_out, wk.counts, wk.task_base, pl.NB, total, pl.T, pl.cap, wk.buckets,
-                                                            wk.big, wk.big + 1);
+                                                            wk.big, wk.big + 1, add_existing);
         SNARKV_LAUNCH_CHECK(ctx, "k_bucket_merge");
         sg.launched();
         k_bucket_merge_big<<<dim3(ctx->sm_count, B), 128, 0, st>>>(wk.task_out, wk.counts, wk.task_base, pl.NB, pl.T, pl.cap, wk.buckets,
-                                                                   wk.big, wk.big + 1, pl.W);
+                                                                   wk.big, wk.big + 1, pl.W, add_existing);
         SNARKV_LAUNCH_CHECK(ctx, "k_bucket_merge_big");
         sg.launched();
     }
+    return SNARKV_OK;
+}
+
+// Point phase, second half: bucket reduction, window sums, Horner tail, normalisation.  Results land at d_out_affine + 64 z and
+// d_out_jacobian + 96 z for base set z < B.
+static int msm_tail_phase(snarkv_ctx* ctx, const MsmWork& wk, int B, int out_format, void* d_out_affine, void* d_out_jacobian) {
+    const MsmPlan& pl = wk.pl;
+    cudaStream_t st = ctx->stream;
     {
         Stage sg(ctx, "msm_bucket_reduce");
         dim3 grid((pl.J + 127) / 128, pl.W, B);
@@ -624,6 +637,13 @@ static int msm_point_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* d_poi
         sg.launched();
     }
     return SNARKV_OK;
+}
+
+static int msm_point_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* d_points, size_t n, int point_format, int out_format,
+                           int check, void* d_out_affine, void* d_out_jacobian, const void* d_points1 = nullptr) {
+    int rc = msm_accumulate_phase(ctx, wk, d_points, n, point_format, check, d_points1);
+    if (rc) return rc;
+    return msm_tail_phase(ctx, wk, d_points1 ? 2 : 1, out_format, d_out_affine, d_out_jacobian);
 }
 
 // Two MSMs over the SAME scalars (KzgAs::verify: sum r^i lhs_i and sum r^i rhs_i, accumulation.rs:53-60): one digit/sort
@@ -651,61 +671,72 @@ int msm_run_device(snarkv_ctx* ctx, const void* d_scalars, const void* d_points,
 }
 
 // snarkv_g1_msm / snarkv_g1_msm_partial: host slices in.  Small inputs: scalars first, the (2x larger) point copy is issued
-// after the sort kernels are queued so copy engine and SMs overlap.  Large inputs (>= 2^22 terms) are cut into 4 term-chunks
-// (the rayon chunking of util/msm.rs:322-336 again, now in time instead of across threads): chunk k+1 is copied on the copy
-// stream while chunk k runs its whole pipeline, and the Jacobian partials are folded at the end.
+// after the sort kernels are queued so copy engine and SMs overlap.  Large inputs (>= 2^22 terms) are cut into term-chunks of
+// geometrically growing size (x1.5): chunk k+1 is copied on the copy stream while chunk k is sorted and accumulated INTO THE SAME
+// bucket array (plan fixed from the total n), so the first copy is short, no chunk pays its own reduce / Horner tail, and the
+// copy engine stays ahead of the SMs (96 B/term at ~50 GB/s vs ~2.9 ns/term of compute).
 int msm_run_host(snarkv_ctx* ctx, const uint8_t* scalars, const uint8_t* points, size_t n, int format, int flags, uint8_t* out,
                  void* d_out_jacobian) {
     const int check = (flags & SNARKV_CHECK_INPUTS) ? 1 : 0;
     if (n == 0) return ctx->fail(SNARKV_ERR_EMPTY, "multi_scalar_multiplication on an empty slice");
     uint8_t* d_s = (uint8_t*)ctx->wsget(WS_IO_A, n * 32);
     uint8_t* d_p = (uint8_t*)ctx->wsget(WS_IO_B, n * 64);
-    uint8_t* d_o = (uint8_t*)ctx->wsget(WS_OUT, 1024);   // [affine 64 | pad | partials 4 x 96 @128 | status 4 x 4 @512]
+    uint8_t* d_o = (uint8_t*)ctx->wsget(WS_OUT, 1024);   // [affine 64 | pad | status K x 4 @512]
     if (!d_s || !d_p || !d_o) return SNARKV_ERR_CUDA;
     cudaStream_t st = ctx->stream;
     const int K = n >= ((size_t)1 << 22) ? SNARKV_HOST_CHUNKS : 1;
-    int status[SNARKV_HOST_CHUNKS] = {0, 0, 0, 0};
+    int status[SNARKV_HOST_CHUNKS] = {};
     int* d_status = (int*)(d_o + 512);
-    int rc;
+    MsmWork wk;
+    int rc = msm_alloc(ctx, n, d_status, wk);   // plan (window bits, buckets, task length, slots) from the TOTAL size
+    if (rc) return rc;
     if (K == 1) {
-        MsmWork wk;
-        rc = msm_alloc(ctx, n, d_status, wk);
-        if (rc) return rc;
         SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_s, scalars, n * 32, cudaMemcpyHostToDevice, st));
         rc = msm_sort_phase(ctx, wk, d_s, n, format, check);
         if (rc) return rc;
         SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_p, points, n * 64, cudaMemcpyHostToDevice, ctx->copy_stream));
         SNARKV_CUDA_TRY(ctx, cudaEventRecord(ctx->copy_done[0], ctx->copy_stream));
         SNARKV_CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->copy_done[0], 0));
-        rc = msm_point_phase(ctx, wk, d_p, n, format, format, check, out ? d_o : nullptr, d_out_jacobian);
+        rc = msm_accumulate_phase(ctx, wk, d_p, n, format, check);
         if (rc) return rc;
     } else {
-        const size_t chunk = (n + K - 1) / K;
+        size_t lo[SNARKV_HOST_CHUNKS + 1];
+        double total_w = 0, wgt = 1;
+        for (int k = 0; k < K; ++k, wgt *= 1.5) total_w += wgt;
+        double acc_w = 0;
+        wgt = 1;
+        lo[0] = 0;
+        for (int k = 0; k < K; ++k, wgt *= 1.5) {
+            acc_w += wgt;
+            lo[k + 1] = (k == K - 1) ? n : (((size_t)((double)n * (acc_w / total_w))) & ~(size_t)255);
+        }
+        uint8_t* conv = nullptr;
+        if (format == SNARKV_CANONICAL) {
+            conv = (uint8_t*)ctx->wsget(WS_POINTS_MONT, n * 64);
+            if (!conv) return SNARKV_ERR_CUDA;
+        }
         // the copy stream must not run ahead of work already queued on the compute stream that still reads the staging buffers
         SNARKV_CUDA_TRY(ctx, cudaEventRecord(ctx->copy_done[K], st));
         SNARKV_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_done[K], 0));
         for (int k = 0; k < K; ++k) {
-            const size_t lo = (size_t)k * chunk, len = (lo + chunk <= n) ? chunk : n - lo;
-            SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_s + lo * 32, scalars + lo * 32, len * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
-            SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_p + lo * 64, points + lo * 64, len * 64, cudaMemcpyHostToDevice, ctx->copy_stream));
+            const size_t len = lo[k + 1] - lo[k];
+            SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_s + lo[k] * 32, scalars + lo[k] * 32, len * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
+            SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_p + lo[k] * 64, points + lo[k] * 64, len * 64, cudaMemcpyHostToDevice, ctx->copy_stream));
             SNARKV_CUDA_TRY(ctx, cudaEventRecord(ctx->copy_done[k], ctx->copy_stream));
         }
         for (int k = 0; k < K; ++k) {
-            const size_t lo = (size_t)k * chunk, len = (lo + chunk <= n) ? chunk : n - lo;
+            const size_t len = lo[k + 1] - lo[k];
             SNARKV_CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->copy_done[k], 0));
-            MsmWork wk;
-            rc = msm_alloc(ctx, len, d_status + k, wk);
+            MsmWork wc = wk;
+            wc.status = d_status + k;
+            rc = msm_sort_phase(ctx, wc, d_s + lo[k] * 32, len, format, check);
             if (rc) return rc;
-            rc = msm_sort_phase(ctx, wk, d_s + lo * 32, len, format, check);
-            if (rc) return rc;
-            rc = msm_point_phase(ctx, wk, d_p + lo * 64, len, format, format, check, nullptr, d_o + 128 + 96 * k);
+            rc = msm_accumulate_phase(ctx, wc, d_p + lo[k] * 64, len, format, check, nullptr, k > 0, conv ? conv + lo[k] * 64 : nullptr);
             if (rc) return rc;
         }
-        Stage sg(ctx, "msm_fold_partials");
-        k_fold_partials<<<1, 32, 0, st>>>(d_o + 128, (uint32_t)K, format, out ? d_o : nullptr, d_out_jacobian);
-        SNARKV_LAUNCH_CHECK(ctx, "k_fold_partials");
-        sg.launched();
     }
+    rc = msm_tail_phase(ctx, wk, 1, format, out ? d_o : nullptr, d_out_jacobian);
+    if (rc) return rc;
     if (out) SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(out, d_o, 64, cudaMemcpyDeviceToHost, st));
     SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(status, d_status, 4 * K, cudaMemcpyDeviceToHost, st));
     SNARKV_CUDA_TRY(ctx, cudaStreamSynchronize(st));

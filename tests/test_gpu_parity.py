@@ -426,6 +426,13 @@ def test_host_entry_chunk_pipeline_matches_device_path(loader):
     loader.fold_partials_device(part.data_ptr(), 1, out.data_ptr())
     torch.cuda.synchronize()
     assert bytes(out.cpu().numpy()) == got
+    # same pipeline on halo2curves' in-memory layout (no conversion kernel), with input validation on
+    Lm = sv.CudaLoader(0, fmt=sv.MONTGOMERY)
+    try:
+        ms = oracle.to_mont_batch(1, hs, n, 8); mp = oracle.to_mont_batch(0, hp, 2 * n, 8)
+        assert Lm.msm(ms, mp, n, flags=sv.CHECK_INPUTS) == to_mont_pts(got)
+    finally:
+        Lm.close()
 
 
 def test_msm_batch_rlc_equals_combination_of_native_folds(loader):
