@@ -69,6 +69,10 @@ int snarkv_set_stream(snarkv_ctx* ctx, void* cuda_stream);
 /* MSM tuning: window bits c (0 = choose from n). */
 int snarkv_set_window_bits(snarkv_ctx* ctx, int c);
 
+/* MSM tuning: GLV endomorphism split of every term into two half-length terms (halves the windows): 0 = for n < 2^22 (default),
+ * 1 = always, 2 = never.  Results are identical. */
+int snarkv_set_glv_mode(snarkv_ctx* ctx, int mode);
+
 /* KZG decide tuning: 0 = choose from N (default), 1 = one thread per check (largest batches), 2 = cooperative (block or warp
  * per check, chosen from N), 3 = one 160-thread block per check (lowest latency), 4 = one warp per check.  Results are identical. */
 int snarkv_set_pairing_mode(snarkv_ctx* ctx, int mode);

@@ -57,6 +57,7 @@ C_ABI = {
     "snarkv_set_stream": (_i, [_vp, _vp]),
     "snarkv_set_window_bits": (_i, [_vp, _i]),
     "snarkv_set_pairing_mode": (_i, [_vp, _i]),
+    "snarkv_set_glv_mode": (_i, [_vp, _i]),
     "snarkv_g1_msm": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp]),
     "snarkv_g1_msm_partial": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp]),
     "snarkv_g1_msm_device": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp, _vp, _vp]),
@@ -154,6 +155,9 @@ class CudaLoader:
 
     def set_stream(self, cuda_stream):
         self._check(self.lib.snarkv_set_stream(self.h, ctypes.c_void_p(cuda_stream) if cuda_stream else None), "set_stream")
+
+    def set_glv_mode(self, mode):
+        self._check(self.lib.snarkv_set_glv_mode(self.h, mode), "set_glv_mode")
 
     def set_pairing_mode(self, mode):
         self._check(self.lib.snarkv_set_pairing_mode(self.h, mode), "set_pairing_mode")

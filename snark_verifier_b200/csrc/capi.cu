@@ -82,6 +82,12 @@ int snarkv_set_window_bits(snarkv_ctx* ctx, int c) {
     return SNARKV_OK;
 }
 
+int snarkv_set_glv_mode(snarkv_ctx* ctx, int mode) {
+    if (!ctx || mode < 0 || mode > 2) return SNARKV_ERR_USAGE;
+    ctx->glv_mode = mode;
+    return SNARKV_OK;
+}
+
 int snarkv_set_pairing_mode(snarkv_ctx* ctx, int mode) {
     if (!ctx || mode < 0 || mode > 4) return SNARKV_ERR_USAGE;
     ctx->pairing_mode = mode;

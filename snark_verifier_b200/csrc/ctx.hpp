@@ -59,6 +59,7 @@ struct snarkv_ctx {
     cudaEvent_t copy_done[8] = {};        // one per host chunk (<= 6) + one fence
     std::string err;
     int window_bits = 0;
+    int glv_mode = 0;       // 0 = GLV for n < 2^22 (default), 1 = always, 2 = never
     int pairing_mode = 0;   // 0 = choose from N, 1 = one thread per check, 2 = one block per check
     uint64_t launches = 0;
     int sm_count = 148;

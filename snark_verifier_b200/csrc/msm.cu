@@ -19,6 +19,7 @@
 // workspace: histogram/offset/cursor W x NB x 4 B each, sorted indices W x n x 4 B, bucket sums W x NB x 128 B (XYZZ).
 #include "ctx.hpp"
 #include "g1.cuh"
+#include "glv.cuh"
 
 namespace snarkv {
 
@@ -32,11 +33,24 @@ struct MsmPlan {
     uint32_t J;    // segments per window
     uint32_t T;    // max points per accumulate task (a bucket with more points is split into ceil(cnt / T) tasks)
     uint32_t cap;  // task slots per window: sum_b ceil(cnt_b / T) <= NB + n / T
+    uint32_t glv;  // 1: every term is split into two half-length terms (P, k1), (phi(P), k2) — glv.cuh
 };
+// With GLV the pipeline sees nv = 2 n "virtual terms" (index i < n: P_i with k1, index n + i: phi(P_i) with k2) whose scalars
+// have 128 bits, so W = ceil(130 / c) windows instead of ceil(255 / c): the additions are the same in number, but the Horner
+// chain, the bucket reduction and the window sums are halved.  Worth it while those fixed costs matter and the window is 16 bits either way (n < 2^23); above, a
+// larger window (c = 17, 15 windows) saves more additions than GLV saves tail.
+static inline size_t plan_virtual_terms(const MsmPlan& p, size_t n) { return p.glv ? 2 * n : n; }
 
-static int choose_window_bits(size_t n) {
-    // Measured sweeps on B200 (profiles/r01_window_sweep_*.txt).  Window sizes whose top window holds only 1-2 significant
-    // bits of a 254-bit scalar (c = 9, 11, 12, 14, 18) funnel n/4 terms into three counters/buckets and are avoided.
+static int choose_window_bits(size_t n, bool glv) {
+    // Measured sweeps on B200 (profiles/r01_window_sweep_*.txt, r01_window_sweep_glv.txt).  n = number of (virtual) terms.
+    // Window sizes whose TOP window holds only a few significant bits funnel a large share of the terms into a handful of
+    // counters/buckets and are avoided: for 254-bit scalars that rules out c = 9, 11, 12, 14, 18; for the 128-bit halves of
+    // the GLV split the good sizes are the ones dividing 128 (8, 16) or leaving an almost empty top window (13).
+    if (glv) {
+        if (n < (1u << 12)) return 8;
+        if (n < (1u << 17)) return 13;
+        return 16;
+    }
     if (n < (1u << 8)) return 6;
     if (n < (1u << 12)) return 8;
     if (n < (1u << 17)) return 13;
@@ -45,15 +59,21 @@ static int choose_window_bits(size_t n) {
     return 17;
 }
 
-static MsmPlan make_plan(size_t n, int c_override) {
+static MsmPlan make_plan(size_t n_terms, int c_override, int glv_mode) {
     MsmPlan p;
-    int c = c_override > 0 ? c_override : choose_window_bits(n);
+    p.glv = (glv_mode == 1 || (glv_mode == 0 && n_terms < ((size_t)1 << 23))) ? 1u : 0u;
+    const size_t n = p.glv ? 2 * n_terms : n_terms;
+    int c = c_override > 0 ? c_override : choose_window_bits(n, p.glv != 0);
     if (c < 2) c = 2;
     if (c > 22) c = 22;
     p.c = (uint32_t)c;
-    p.W = (255 + p.c - 1) / p.c;
+    p.W = ((p.glv ? 130u : 255u) + p.c - 1) / p.c;
     p.NB = 1u << (p.c - 1);
-    p.seg = p.NB < 16 ? p.NB : 16;
+    // bucket-reduce segment length: each thread's chain is 2 seg additions + one small scalar multiple; short segments cut that
+    // latency, long ones cut the total work (the small multiples) once there are enough buckets to fill the machine
+    const size_t all_buckets = (size_t)p.W * p.NB;
+    p.seg = all_buckets >= ((size_t)1 << 18) ? 16 : 4;   // measured: 8 at 2^18 buckets only moves the time into k_window_sum
+    if (p.seg > p.NB) p.seg = p.NB;
     p.J = (p.NB + p.seg - 1) / p.seg;
     const size_t avg = (n + p.NB - 1) / p.NB;
     size_t T = 2 * avg;   // uniformly random digits never reach 2x the mean once the mean is >= 64
@@ -66,7 +86,8 @@ static MsmPlan make_plan(size_t n, int c_override) {
 // ---------------------------------------------------------------------------------------------------------------------
 // input preparation / validation
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void k_points_prepare(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, size_t n, int format, int check,
+// `endo` != 0: out has room for 2 n points and also receives phi(P_i) = (beta x_i, y_i) at index n + i (glv.cuh).
+__global__ void k_points_prepare(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, size_t n, int format, int check, int endo,
                                  int* __restrict__ status) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         G1Affine p = g1_affine_load(in, i);
@@ -77,6 +98,14 @@ __global__ void k_points_prepare(const uint8_t* __restrict__ in, uint8_t* __rest
         }
         if (check && !g1_affine_is_on_curve(p)) atomicCAS(status, 0, SNARKV_ERR_BAD_POINT);
         if (out) g1_affine_store(out, i, p);
+        if (endo) {
+            constexpr uint32_t beta_limbs[8] = SNARKV_GLV_BETA_MONT_LIMBS;
+            Fq beta;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) beta.v[j] = beta_limbs[j];
+            p.x = fp_mul(p.x, beta);          // the identity (0, 0) maps to (0, 0)
+            g1_affine_store(out, n + i, p);
+        }
     }
 }
 
@@ -112,6 +141,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // The scalar stream is staged through shared memory by TMA bulk copies: one elected thread issues an 8 KB
 // cp.async.bulk per 256-scalar tile into a double buffer while the block decomposes the previous tile.
 #define SNARKV_DIGIT_TILE 256
+template <bool GLV>
 __global__ void __launch_bounds__(SNARKV_DIGIT_TILE) k_digits(const uint8_t* __restrict__ scalars, size_t n, int format, int check, uint32_t c,
                                                               uint32_t W, uint32_t NB, uint32_t* __restrict__ counters,
                                                               uint32_t* __restrict__ digits, int* __restrict__ status) {
@@ -148,21 +178,46 @@ __global__ void __launch_bounds__(SNARKV_DIGIT_TILE) k_digits(const uint8_t* __r
             }
             if (format == SNARKV_MONTGOMERY) s = fp_from_mont(s);
             else if (check && !fp_is_canonical(s)) atomicCAS(status, 0, SNARKV_ERR_BAD_SCALAR);
-            uint32_t carry = 0;
-            for (uint32_t w = 0; w < W; ++w) {
-                uint32_t d = (s.v[0] & mask) + carry;
-                // s >>= c  (c < 32)
+            if (!GLV) {
+                uint32_t carry = 0;
+                for (uint32_t w = 0; w < W; ++w) {
+                    uint32_t d = (s.v[0] & mask) + carry;
+                    // s >>= c  (c < 32)
 #pragma unroll
-                for (int j = 0; j < 7; ++j) s.v[j] = __funnelshift_r(s.v[j], s.v[j + 1], c);
-                s.v[7] >>= c;
-                uint32_t neg = 0;
-                if (d > NB) {
-                    d = (mask + 1u) - d;
-                    neg = 1u;
-                    carry = 1u;
-                } else carry = 0u;
-                digits[(size_t)w * n + i] = d | (neg << 31);
-                if (d != 0) atomicAdd(&counters[w * NB + (d - 1u)], 1u);
+                    for (int j = 0; j < 7; ++j) s.v[j] = __funnelshift_r(s.v[j], s.v[j + 1], c);
+                    s.v[7] >>= c;
+                    uint32_t neg = 0;
+                    if (d > NB) {
+                        d = (mask + 1u) - d;
+                        neg = 1u;
+                        carry = 1u;
+                    } else carry = 0u;
+                    digits[(size_t)w * n + i] = d | (neg << 31);
+                    if (d != 0) atomicAdd(&counters[w * NB + (d - 1u)], 1u);
+                }
+            } else {
+                // two half-length virtual terms: index i carries |k1| (sign neg1) for P_i, index n + i carries |k2| for phi(P_i)
+                uint32_t mag[2][5], sgn[2];
+                glv::decompose(s.v, mag[0], sgn[0], mag[1], sgn[1]);
+                const size_t nv = 2 * n;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t m0 = mag[h][0], m1 = mag[h][1], m2 = mag[h][2], m3 = mag[h][3], m4 = mag[h][4];
+                    uint32_t carry = 0;
+                    for (uint32_t w = 0; w < W; ++w) {
+                        uint32_t d = (m0 & mask) + carry;
+                        m0 = __funnelshift_r(m0, m1, c); m1 = __funnelshift_r(m1, m2, c); m2 = __funnelshift_r(m2, m3, c);
+                        m3 = __funnelshift_r(m3, m4, c); m4 >>= c;
+                        uint32_t neg = 0;
+                        if (d > NB) {
+                            d = (mask + 1u) - d;
+                            neg = 1u;
+                            carry = 1u;
+                        } else carry = 0u;
+                        digits[(size_t)w * nv + i + (size_t)h * n] = d | ((neg ^ sgn[h]) << 31);
+                        if (d != 0) atomicAdd(&counters[w * NB + (d - 1u)], 1u);
+                    }
+                }
             }
         }
         __syncthreads();
@@ -496,10 +551,10 @@ struct MsmWork {
     uint8_t *task_out, *buckets, *segpart, *winsum;
 };
 
-static int msm_alloc(snarkv_ctx* ctx, size_t n, void* d_status, MsmWork& wk, int B = 1) {
+static int msm_alloc(snarkv_ctx* ctx, size_t n, void* d_status, MsmWork& wk, int B = 1, int glv_mode = -1) {
     if (n == 0) return ctx->fail(SNARKV_ERR_EMPTY, "multi_scalar_multiplication on an empty slice");
     if (n >= (1ull << 31)) return ctx->fail(SNARKV_ERR_USAGE, "n must be < 2^31");
-    wk.pl = make_plan(n, ctx->window_bits);
+    wk.pl = make_plan(n, ctx->window_bits, glv_mode >= 0 ? glv_mode : ctx->glv_mode);
     const MsmPlan& pl = wk.pl;
     const size_t nbk = (size_t)pl.W * pl.NB;
     wk.status = (int*)d_status;
@@ -507,8 +562,9 @@ static int msm_alloc(snarkv_ctx* ctx, size_t n, void* d_status, MsmWork& wk, int
     wk.counts = (uint32_t*)ctx->wsget(WS_COUNTS, nbk * 4);
     wk.offsets = (uint32_t*)ctx->wsget(WS_OFFSETS, nbk * 4);
     wk.cursor = (uint32_t*)ctx->wsget(WS_CURSOR, nbk * 4);
-    wk.sorted = (uint32_t*)ctx->wsget(WS_SORTED, (size_t)pl.W * n * 4);
-    wk.digits = (uint32_t*)ctx->wsget(WS_DIGITS, (size_t)pl.W * n * 4);
+    const size_t nv = plan_virtual_terms(pl, n);
+    wk.sorted = (uint32_t*)ctx->wsget(WS_SORTED, (size_t)pl.W * nv * 4);
+    wk.digits = (uint32_t*)ctx->wsget(WS_DIGITS, (size_t)pl.W * nv * 4);
     wk.buckets = (uint8_t*)ctx->wsget(WS_BUCKETS, (size_t)B * nbk * 128);
     wk.segpart = (uint8_t*)ctx->wsget(WS_SEGPART, (size_t)B * pl.W * pl.J * 128);
     wk.winsum = (uint8_t*)ctx->wsget(WS_WINSUM, (size_t)B * pl.W * 128);
@@ -535,8 +591,12 @@ static int msm_sort_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* d_scal
         Stage sg(ctx, "msm_digits_count");
         SNARKV_CUDA_TRY(ctx, cudaMemsetAsync(wk.status, 0, 4, st));
         SNARKV_CUDA_TRY(ctx, cudaMemsetAsync(wk.counts, 0, nbk * 4, st));
-        k_digits<<<dig_blocks, 256, 0, st>>>((const uint8_t*)d_scalars, n, scalar_format, check, pl.c, pl.W, pl.NB, wk.counts, wk.digits,
-                                             wk.status);
+        if (pl.glv)
+            k_digits<true><<<dig_blocks, 256, 0, st>>>((const uint8_t*)d_scalars, n, scalar_format, check, pl.c, pl.W, pl.NB, wk.counts,
+                                                       wk.digits, wk.status);
+        else
+            k_digits<false><<<dig_blocks, 256, 0, st>>>((const uint8_t*)d_scalars, n, scalar_format, check, pl.c, pl.W, pl.NB, wk.counts,
+                                                        wk.digits, wk.status);
         SNARKV_LAUNCH_CHECK(ctx, "k_digits");
         sg.launched();
     }
@@ -554,8 +614,9 @@ static int msm_sort_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* d_scal
     }
     {
         Stage sg(ctx, "msm_digits_scatter");
-        const size_t tot = (size_t)pl.W * n, wantb = (tot + 255) / 256, capb = (size_t)ctx->sm_count * 16;
-        k_scatter<<<(unsigned)(wantb < capb ? wantb : capb), 256, 0, st>>>(wk.digits, n, pl.W, pl.NB, wk.cursor, wk.sorted);
+        const size_t nv = plan_virtual_terms(pl, n);
+        const size_t tot = (size_t)pl.W * nv, wantb = (tot + 255) / 256, capb = (size_t)ctx->sm_count * 16;
+        k_scatter<<<(unsigned)(wantb < capb ? wantb : capb), 256, 0, st>>>(wk.digits, nv, pl.W, pl.NB, wk.cursor, wk.sorted);
         SNARKV_LAUNCH_CHECK(ctx, "k_scatter");
         sg.launched();
     }
@@ -572,18 +633,19 @@ static int msm_accumulate_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* 
     cudaStream_t st = ctx->stream;
     const size_t nbk = (size_t)pl.W * pl.NB;
     const int B = d_points1 ? 2 : 1;
+    const size_t nv = plan_virtual_terms(pl, n);
     const uint8_t* pts[2] = {(const uint8_t*)d_points, (const uint8_t*)d_points1};
-    if (point_format == SNARKV_CANONICAL || check) {
+    if (point_format == SNARKV_CANONICAL || check || pl.glv) {
         Stage sg(ctx, "msm_points_prepare");
         uint8_t* conv = nullptr;
-        if (point_format == SNARKV_CANONICAL) {
-            conv = conv_dst ? conv_dst : (uint8_t*)ctx->wsget(WS_POINTS_MONT, (size_t)B * n * 64);
+        if (point_format == SNARKV_CANONICAL || pl.glv) {   // GLV gathers from one array [P | phi(P)] of nv points per base set
+            conv = conv_dst ? conv_dst : (uint8_t*)ctx->wsget(WS_POINTS_MONT, (size_t)B * nv * 64);
             if (!conv) return SNARKV_ERR_CUDA;
         }
         const size_t want = (n + 255) / 256, cap = (size_t)ctx->sm_count * 8;
         for (int z = 0; z < B; ++z) {
-            uint8_t* cz = conv ? conv + (size_t)z * n * 64 : nullptr;
-            k_points_prepare<<<(int)(want < cap ? want : cap), 256, 0, st>>>(pts[z], cz, n, point_format, check, wk.status);
+            uint8_t* cz = conv ? conv + (size_t)z * nv * 64 : nullptr;
+            k_points_prepare<<<(int)(want < cap ? want : cap), 256, 0, st>>>(pts[z], cz, n, point_format, check, (int)pl.glv, wk.status);
             SNARKV_LAUNCH_CHECK(ctx, "k_points_prepare");
             sg.launched();
             if (cz) pts[z] = cz;
@@ -592,8 +654,8 @@ static int msm_accumulate_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* 
     {
         Stage sg(ctx, "msm_bucket_accumulate");
         dim3 grid((pl.cap + 127) / 128, pl.W, B);
-        k_bucket_accumulate<<<grid, 128, 0, st>>>(pts[0], pts[1], wk.sorted, wk.offsets, wk.counts, wk.tasks, wk.window_tasks, wk.order, n, pl.NB,
-                                                 pl.T, pl.cap, wk.task_out);
+        k_bucket_accumulate<<<grid, 128, 0, st>>>(pts[0], pts[1], wk.sorted, wk.offsets, wk.counts, wk.tasks, wk.window_tasks, wk.order, nv,
+                                                 pl.NB, pl.T, pl.cap, wk.task_out);
         SNARKV_LAUNCH_CHECK(ctx, "k_bucket_accumulate");
         sg.launched();
     }
@@ -691,7 +753,7 @@ int msm_run_host(snarkv_ctx* ctx, const uint8_t* scalars, const uint8_t* points,
     int status[SNARKV_HOST_CHUNKS] = {};
     int* d_status = (int*)(d_o + 512);
     MsmWork wk;
-    int rc = msm_alloc(ctx, n, d_status, wk);   // plan (window bits, buckets, task length, slots) from the TOTAL size
+    int rc = msm_alloc(ctx, n, d_status, wk, 1, K > 1 ? 2 : -1);   // plan from the TOTAL size; the chunk pipeline runs without GLV
     if (rc) return rc;
     if (K == 1) {
         SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_s, scalars, n * 32, cudaMemcpyHostToDevice, st));
@@ -750,7 +812,7 @@ int msm_run_host(snarkv_ctx* ctx, const uint8_t* scalars, const uint8_t* points,
 }
 
 void msm_plan_query(snarkv_ctx* ctx, size_t n, uint32_t out[4]) {
-    const MsmPlan pl = make_plan(n ? n : 1, ctx->window_bits);
+    const MsmPlan pl = make_plan(n ? n : 1, ctx->window_bits, ctx->glv_mode);
     out[0] = pl.c; out[1] = pl.W; out[2] = pl.NB; out[3] = pl.T;
 }
 

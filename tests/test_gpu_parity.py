@@ -533,3 +533,36 @@ def test_msm_batch_validation_and_empty_segment(loader):
     bad = bytearray(p); bad[64 * 2:64 * 3] = le(1) + le(3)
     with pytest.raises(sv.Error):
         loader.msm_batch(s, bytes(bad), [0, 4, 8], flags=sv.CHECK_INPUTS)
+
+
+@pytest.mark.parametrize("glv_mode", [1, 2], ids=["glv_always", "glv_never"])
+@pytest.mark.parametrize("n", [1, 2, 21, 256, 5000, 70000])
+def test_msm_glv_on_off_agree_with_oracle(loader, glv_mode, n):
+    """The endomorphism split (csrc/glv.cuh) is an internal choice: forced on and forced off must both reproduce the oracle."""
+    s = bytearray(oracle.synth_scalars(81, 0, n)); p = oracle.synth_points(81, 0, n, 8)
+    for j, val in enumerate((0, 1, m.R - 1, (m.R - 1) // 2, 0x30644E72E131A029048B6E193FD84104CC37A73FEC2BC5E9B8CA0B2D36636F23)):
+        if j < n:
+            s[32 * j:32 * j + 32] = le(val)            # 0, 1, r-1, (r-1)/2, lambda itself
+    s = bytes(s)
+    exp = oracle.msm_pippenger(s, p, n, 8)
+    loader.set_glv_mode(glv_mode)
+    try:
+        assert loader.msm(s, p, n) == exp
+    finally:
+        loader.set_glv_mode(0)
+
+
+def test_msm_glv_forced_at_large_size_matches_checksum(loader):
+    import torch
+    n = 1 << 22
+    ds = torch.empty(n * 32, dtype=torch.uint8, device="cuda"); dp = torch.empty(n * 64, dtype=torch.uint8, device="cuda")
+    out = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    loader.synth_scalars_device(83, 0, n, ds.data_ptr()); loader.synth_points_device(83, 0, n, dp.data_ptr())
+    loader.set_glv_mode(1)
+    loader.msm_device(ds.data_ptr(), dp.data_ptr(), n, d_out_affine=out.data_ptr())
+    loader.set_glv_mode(2)
+    loader.msm_device(ds.data_ptr(), dp.data_ptr(), n, d_out_affine=out.data_ptr() + 64)
+    loader.set_glv_mode(0)
+    torch.cuda.synchronize()
+    o = bytes(out.cpu().numpy())
+    assert o[:64] == o[64:] == oracle.msm_expected_from_dlogs(ds.cpu().numpy(), oracle.synth_point_scalars(83, 0, n), n)
