@@ -566,3 +566,34 @@ def test_msm_glv_forced_at_large_size_matches_checksum(loader):
     torch.cuda.synchronize()
     o = bytes(out.cpu().numpy())
     assert o[:64] == o[64:] == oracle.msm_expected_from_dlogs(ds.cpu().numpy(), oracle.synth_point_scalars(83, 0, n), n)
+
+
+def test_context_recovers_after_rejected_input(loader):
+    """A call that fails validation must leave the context usable (grow-only workspace, stream, status words)."""
+    n = 300
+    s = oracle.synth_scalars(90, 0, n); p = oracle.synth_points(90, 0, n, 4)
+    bad = bytearray(p); bad[64 * 17 + 5] ^= 0x40
+    for _ in range(2):
+        with pytest.raises(sv.Error):
+            loader.msm(s, bytes(bad), n, flags=sv.CHECK_INPUTS)
+        assert loader.msm(s, p, n, flags=sv.CHECK_INPUTS) == oracle.msm_pippenger(s, p, n, 4)
+    with pytest.raises(sv.Error):
+        loader.msm(s, p, 0)
+    assert loader.msm(s, p, n) == oracle.msm_pippenger(s, p, n, 4)
+
+
+def test_instrumentation_api(loader):
+    n = 4096
+    s = oracle.synth_scalars(91, 0, n); p = oracle.synth_points(91, 0, n, 4)
+    before = loader.launch_count
+    loader.profile(True)
+    try:
+        loader.msm(s, p, n)
+        stages = loader.stage_times()
+    finally:
+        loader.profile(False)
+    names = [a for a, _, _ in stages]
+    assert "msm_bucket_accumulate" in names and "msm_final" in names
+    assert all(ms >= 0 for _, ms, _ in stages) and sum(k for _, _, k in stages) == loader.launch_count - before
+    plan = loader.msm_plan(n)
+    assert plan["buckets_per_window"] == 1 << (plan["window_bits"] - 1) and plan["windows"] * plan["window_bits"] >= 130
