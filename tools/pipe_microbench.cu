@@ -1,3 +1,5 @@
+// NOTE: only the DFMA / IADD3 / 32-bit IMAD rows are meaningful; ptxas moves the IMAD.WIDE row onto the uniform datapath
+// (UIMAD.WIDE) because its operands are warp-uniform.  The IMAD.WIDE cost used in DESIGN.md comes from the ncu capture.
 // Microbenchmark (developer tool): warp-instruction throughput of IMAD.WIDE.U32, IMAD, DFMA, IADD3 on sm_100a, alone and mixed.
 #include <cstdio>
 #include <cstdint>
@@ -12,8 +14,12 @@ __global__ void k(uint64_t* out, uint32_t a0, double d0) {
     uint32_t i0 = a, i1 = b, i2 = a ^ b, i3 = a + b;
     for (int it = 0; it < ITERS; ++it) {
         if (MODE == 0 || MODE == 3 || MODE == 5) {   // 8 independent IMAD.WIDE
-            asm volatile("mad.wide.u32 %0, %8, %9, %0; mad.wide.u32 %1, %8, %9, %1; mad.wide.u32 %2, %8, %9, %2; mad.wide.u32 %3, %8, %9, %3;"
-                         "mad.wide.u32 %4, %8, %9, %4; mad.wide.u32 %5, %8, %9, %5; mad.wide.u32 %6, %8, %9, %6; mad.wide.u32 %7, %8, %9, %7;"
+            // loop-carried multiplicand (low word of the accumulator) so that the product cannot be hoisted out of the loop
+            asm volatile("{ .reg .u32 t0,t1,t2,t3,t4,t5,t6,t7;\n\t"
+                         "cvt.u32.u64 t0, %0; cvt.u32.u64 t1, %1; cvt.u32.u64 t2, %2; cvt.u32.u64 t3, %3;\n\t"
+                         "cvt.u32.u64 t4, %4; cvt.u32.u64 t5, %5; cvt.u32.u64 t6, %6; cvt.u32.u64 t7, %7;\n\t"
+                         "mad.wide.u32 %0, t0, %9, %0; mad.wide.u32 %1, t1, %9, %1; mad.wide.u32 %2, t2, %9, %2; mad.wide.u32 %3, t3, %9, %3;\n\t"
+                         "mad.wide.u32 %4, t4, %9, %4; mad.wide.u32 %5, t5, %9, %5; mad.wide.u32 %6, t6, %9, %6; mad.wide.u32 %7, t7, %9, %7; }"
                          : "+l"(x0), "+l"(x1), "+l"(x2), "+l"(x3), "+l"(x4), "+l"(x5), "+l"(x6), "+l"(x7) : "r"(a), "r"(b));
         }
         if (MODE == 1 || MODE == 3 || MODE == 4) {   // 8 independent DFMA
