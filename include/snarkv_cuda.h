@@ -151,6 +151,15 @@ int snarkv_kzg_decide_batch_device(snarkv_ctx* ctx, const void* d_lhs, const voi
 int snarkv_kzg_decide_all_fused(snarkv_ctx* ctx, const uint8_t* lhs, const uint8_t* rhs, size_t N, const uint8_t rho[32], int format,
                                 uint8_t* accept, uint8_t out_lhs[64], uint8_t out_rhs[64]);
 
+/* ---- (next row f1) Fr scalar preparation — the step right before the MSM -----------------------------------------------------
+ * `LoadedScalar::powers(n)` (loader.rs:71-78): out[i] = r^i, i < n.   n x 32 B, `format` in and out. */
+int snarkv_fr_powers(snarkv_ctx* ctx, const uint8_t r[32], size_t n, int format, uint8_t* out);
+/* `ScalarLoader::batch_invert` (loader.rs:255-262) / `batch_invert_and_mul` (util/arithmetic.rs:47-69), in place: every non-zero
+ * value v becomes coeff / v (coeff = 1 when NULL); zeros are left untouched, exactly as the reference does. */
+int snarkv_fr_batch_invert(snarkv_ctx* ctx, uint8_t* values, size_t n, const uint8_t* coeff, int format);
+/* Element-wise product out[i] = a[i] * b[i] (the RLC scalars rho^i * s_i of the fused batch paths). */
+int snarkv_fr_mul_vec(snarkv_ctx* ctx, const uint8_t* a, const uint8_t* b, size_t n, int format, uint8_t* out);
+
 /* ---- synthetic workload (bench / tests) ----------------------------------------------------------------------------------
  * Deterministic inputs (the test suite restates the same definition independently):
  *   scalar_i: 4 x splitmix64 limbs, top limb masked to 62 bits, one conditional subtraction of r;

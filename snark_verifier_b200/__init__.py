@@ -64,6 +64,9 @@ C_ABI = {
     "snarkv_g1_fold_partials_device": (_i, [_vp, _vp, _sz, _i, _vp]),
     "snarkv_g1_msm_batch": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _vp]),
     "snarkv_g1_msm_batch_rlc": (_i, [_vp, _vp, _vp, _vp, _sz, _vp, _i, _i, _vp]),
+    "snarkv_fr_powers": (_i, [_vp, _vp, _sz, _i, _vp]),
+    "snarkv_fr_batch_invert": (_i, [_vp, _vp, _sz, _vp, _i]),
+    "snarkv_fr_mul_vec": (_i, [_vp, _vp, _vp, _sz, _i, _vp]),
     "snarkv_kzg_accumulate": (_i, [_vp, _vp, _vp, _sz, _vp, _i, _vp, _vp]),
     "snarkv_kzg_set_deciding_key": (_i, [_vp, _vp, _vp, _vp]),
     "snarkv_kzg_decide_batch": (_i, [_vp, _vp, _vp, _sz, _i, _vp, _vp]),
@@ -238,6 +241,24 @@ class CudaLoader:
         out = ctypes.create_string_buffer(64)
         self._check(self.lib.snarkv_g1_msm_batch_rlc(self.h, _addr(scalars), _addr(points), _addr(off), m, bytes(rho),
                                                      self.fmt, flags, out), "msm_batch_rlc")
+        return out.raw
+
+    # -- ScalarLoader helpers (Fr vectors) --------------------------------------------------------------------------------
+    def powers(self, r, n):
+        """LoadedScalar::powers (loader.rs:71-78): [1, r, ..., r^(n-1)] as n x 32 B."""
+        out = ctypes.create_string_buffer(32 * n)
+        self._check(self.lib.snarkv_fr_powers(self.h, bytes(r), n, self.fmt, out), "powers")
+        return out.raw
+
+    def batch_invert(self, values, n, coeff=None):
+        """ScalarLoader::batch_invert / batch_invert_and_mul: non-zero v -> coeff / v, zeros untouched.  Returns new bytes."""
+        buf = ctypes.create_string_buffer(bytes(values), 32 * n)
+        self._check(self.lib.snarkv_fr_batch_invert(self.h, buf, n, bytes(coeff) if coeff is not None else None, self.fmt), "batch_invert")
+        return buf.raw
+
+    def fr_mul_vec(self, a, b, n):
+        out = ctypes.create_string_buffer(32 * n)
+        self._check(self.lib.snarkv_fr_mul_vec(self.h, _addr(a), _addr(b), n, self.fmt, out), "fr_mul_vec")
         return out.raw
 
     # -- synthetic workload ---------------------------------------------------------------------------------------

@@ -330,6 +330,62 @@ int snarkv_kzg_decide_all_fused(snarkv_ctx* ctx, const uint8_t* lhs, const uint8
     return SNARKV_OK;
 }
 
+// ---- (f1) Fr scalar preparation ------------------------------------------------------------------------------------------------
+int snarkv_fr_powers(snarkv_ctx* ctx, const uint8_t r[32], size_t n, int format, uint8_t* out) {
+    CTX_GUARD(ctx);
+    if (!r || !out || bad_format(format)) return ctx->fail(SNARKV_ERR_USAGE, "snarkv_fr_powers: bad argument");
+    if (n == 0) return SNARKV_OK;
+    uint8_t* d = (uint8_t*)ctx->wsget(WS_IO_A, n * 32 + 32);
+    if (!d) return SNARKV_ERR_CUDA;
+    cudaStream_t st = ctx->stream;
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d, r, 32, cudaMemcpyHostToDevice, st));
+    int rc = fr_powers_device(ctx, d, format, n, d + 32);
+    if (rc) return rc;
+    if (format == SNARKV_CANONICAL) {
+        rc = fr_from_mont_device(ctx, d + 32, n);
+        if (rc) return rc;
+    }
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(out, d + 32, n * 32, cudaMemcpyDeviceToHost, st));
+    SNARKV_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return SNARKV_OK;
+}
+
+int snarkv_fr_batch_invert(snarkv_ctx* ctx, uint8_t* values, size_t n, const uint8_t* coeff, int format) {
+    CTX_GUARD(ctx);
+    if (!values || bad_format(format)) return ctx->fail(SNARKV_ERR_USAGE, "snarkv_fr_batch_invert: bad argument");
+    if (n == 0) return SNARKV_OK;
+    uint8_t* d_v = (uint8_t*)ctx->wsget(WS_IO_A, n * 32);
+    uint8_t* d_s = (uint8_t*)ctx->wsget(WS_IO_B, n * 32);
+    uint8_t* d_c = (uint8_t*)ctx->wsget(WS_IO_C, 32);
+    if (!d_v || !d_s || !d_c) return SNARKV_ERR_CUDA;
+    cudaStream_t st = ctx->stream;
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_v, values, n * 32, cudaMemcpyHostToDevice, st));
+    if (coeff) SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_c, coeff, 32, cudaMemcpyHostToDevice, st));
+    int rc = fr_batch_invert_device(ctx, d_v, n, format, coeff ? d_c : nullptr, d_s);
+    if (rc) return rc;
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(values, d_v, n * 32, cudaMemcpyDeviceToHost, st));
+    SNARKV_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return SNARKV_OK;
+}
+
+int snarkv_fr_mul_vec(snarkv_ctx* ctx, const uint8_t* a, const uint8_t* b, size_t n, int format, uint8_t* out) {
+    CTX_GUARD(ctx);
+    if (!a || !b || !out || bad_format(format)) return ctx->fail(SNARKV_ERR_USAGE, "snarkv_fr_mul_vec: bad argument");
+    if (n == 0) return SNARKV_OK;
+    uint8_t* d_a = (uint8_t*)ctx->wsget(WS_IO_A, n * 32);
+    uint8_t* d_b = (uint8_t*)ctx->wsget(WS_IO_B, n * 32);
+    uint8_t* d_o = (uint8_t*)ctx->wsget(WS_IO_C, n * 32);
+    if (!d_a || !d_b || !d_o) return SNARKV_ERR_CUDA;
+    cudaStream_t st = ctx->stream;
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_a, a, n * 32, cudaMemcpyHostToDevice, st));
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_b, b, n * 32, cudaMemcpyHostToDevice, st));
+    int rc = fr_mul_vec_device(ctx, d_a, d_b, n, format, d_o);
+    if (rc) return rc;
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(out, d_o, n * 32, cudaMemcpyDeviceToHost, st));
+    SNARKV_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return SNARKV_OK;
+}
+
 // ---- test support ---------------------------------------------------------------------------------------------------------
 int snarkv_debug_field_op(snarkv_ctx* ctx, int field, int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) {
     CTX_GUARD(ctx);

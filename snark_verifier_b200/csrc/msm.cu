@@ -911,6 +911,82 @@ int fr_powers_device(snarkv_ctx* ctx, const void* d_r, int format, size_t n, voi
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Fr vector helpers of the scalar-preparation step that precedes the MSM:
+//   ScalarLoader::batch_invert (snark-verifier/src/loader.rs:255-262: zero stays zero) and util::arithmetic::
+//   batch_invert_and_mul (util/arithmetic.rs:47-69: non-zero v -> coeff / v), element-wise products (RLC scalars rho^i * s_i).
+// Batch inversion is Montgomery's trick per thread over a chunk of CHUNK values: prefix products of the non-zero values are parked
+// in `scratch`, ONE inversion per chunk, then the backward sweep — 3 multiplications per value + 1/CHUNK of an inversion.
+// ---------------------------------------------------------------------------------------------------------------------
+#define SNARKV_INV_CHUNK 64
+__global__ void __launch_bounds__(128) k_fr_batch_invert(uint8_t* __restrict__ values, size_t n, int format, const uint8_t* __restrict__ coeff,
+                                                         uint8_t* __restrict__ scratch) {
+    const size_t chunk = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t lo = chunk * SNARKV_INV_CHUNK;
+    if (lo >= n) return;
+    const size_t hi = (lo + SNARKV_INV_CHUNK < n) ? lo + SNARKV_INV_CHUNK : n;
+    Fr acc = fp_one<FR>();
+    for (size_t i = lo; i < hi; ++i) {
+        Fr v = fp_load<FR>(values + i * 32);
+        if (format == SNARKV_CANONICAL) v = fp_to_mont(v);
+        fp_store<FR>(scratch + i * 32, acc);             // product of the non-zero values before i
+        if (!fp_is_zero(v)) acc = fp_mul(acc, v);
+    }
+    Fr inv = fp_inv(acc);                                // acc != 0: product of non-zero field elements
+    if (coeff) {
+        Fr c = fp_load<FR>(coeff);
+        if (format == SNARKV_CANONICAL) c = fp_to_mont(c);
+        inv = fp_mul(inv, c);
+    }
+    for (size_t i = hi; i-- > lo;) {
+        Fr v = fp_load<FR>(values + i * 32);
+        if (format == SNARKV_CANONICAL) v = fp_to_mont(v);
+        if (fp_is_zero(v)) continue;                     // `unwrap_or_else(|| value.clone())`: zero is left as it is
+        Fr out = fp_mul(inv, fp_load<FR>(scratch + i * 32));
+        inv = fp_mul(inv, v);
+        if (format == SNARKV_CANONICAL) out = fp_from_mont(out);
+        fp_store<FR>(values + i * 32, out);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_fr_mul_vec(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, size_t n, int format,
+                                                    uint8_t* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr x = fp_load<FR>(a + i * 32), y = fp_load<FR>(b + i * 32);
+    // canonical: (x R^-1-free) product needs one conversion: mont_mul(x, to_mont(y)) = x*y
+    if (format == SNARKV_CANONICAL) y = fp_to_mont(y);
+    fp_store<FR>(out + i * 32, fp_mul(x, y));            // Montgomery in -> Montgomery out; canonical in -> canonical out
+}
+
+__global__ void k_fr_from_mont(uint8_t* __restrict__ v, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) fp_store<FR>(v + i * 32, fp_from_mont(fp_load<FR>(v + i * 32)));
+}
+
+int fr_batch_invert_device(snarkv_ctx* ctx, void* d_values, size_t n, int format, const void* d_coeff, void* d_scratch) {
+    Stage sg(ctx, "fr_batch_invert");
+    const size_t chunks = (n + SNARKV_INV_CHUNK - 1) / SNARKV_INV_CHUNK;
+    k_fr_batch_invert<<<(unsigned)((chunks + 127) / 128), 128, 0, ctx->stream>>>((uint8_t*)d_values, n, format, (const uint8_t*)d_coeff,
+                                                                              (uint8_t*)d_scratch);
+    SNARKV_LAUNCH_CHECK(ctx, "k_fr_batch_invert");
+    sg.launched();
+    return SNARKV_OK;
+}
+int fr_mul_vec_device(snarkv_ctx* ctx, const void* d_a, const void* d_b, size_t n, int format, void* d_out) {
+    Stage sg(ctx, "fr_mul_vec");
+    k_fr_mul_vec<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const uint8_t*)d_a, (const uint8_t*)d_b, n, format, (uint8_t*)d_out);
+    SNARKV_LAUNCH_CHECK(ctx, "k_fr_mul_vec");
+    sg.launched();
+    return SNARKV_OK;
+}
+int fr_from_mont_device(snarkv_ctx* ctx, void* d_v, size_t n) {
+    k_fr_from_mont<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((uint8_t*)d_v, n);
+    SNARKV_LAUNCH_CHECK(ctx, "k_fr_from_mont");
+    ctx->launches++;
+    return SNARKV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // RLC fusion of many MSMs into one (the batching of pcs/kzg/decider.rs:146-185 applied before the MSM instead of after it):
 //   sum_j rho^j * MSM_j  =  one MSM over all terms with scalars  rho^j * s_ij .
 // k_fr_scale_segments multiplies every scalar of segment j by rho^j (powers from k_fr_powers) and leaves Montgomery form.

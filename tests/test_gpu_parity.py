@@ -597,3 +597,28 @@ def test_instrumentation_api(loader):
     assert all(ms >= 0 for _, ms, _ in stages) and sum(k for _, _, k in stages) == loader.launch_count - before
     plan = loader.msm_plan(n)
     assert plan["buckets_per_window"] == 1 << (plan["window_bits"] - 1) and plan["windows"] * plan["window_bits"] >= 130
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# SURVEY §8 f1 (first "next" row): Fr scalar preparation on the device
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("which", ["canonical", "montgomery"])
+def test_fr_powers_batch_invert_mul_vec(loader, mont_loader, which):
+    L = loader if which == "canonical" else mont_loader
+    enc = (lambda v: le(v)) if which == "canonical" else (lambda v: le(v * (1 << 256) % m.R))
+    rng = np.random.default_rng(12)
+    r = int.from_bytes(rng.bytes(31), "little")
+    n = 1000
+    assert L.powers(enc(r), n) == b"".join(enc(pow(r, i, m.R)) for i in range(n))                 # loader.rs:71-78
+    vals = [int.from_bytes(rng.bytes(32), "little") % m.R for _ in range(n)]
+    for j in (0, 5, 63, 64, 999):
+        vals[j] = 0                                                                                # zeros stay zero (loader.rs:261)
+    vals[1], vals[2] = 1, m.R - 1
+    got = L.batch_invert(b"".join(map(enc, vals)), n)
+    assert got == b"".join(enc(pow(v, -1, m.R) if v else 0) for v in vals)
+    coeff = int.from_bytes(rng.bytes(31), "little")
+    got = L.batch_invert(b"".join(map(enc, vals)), n, coeff=enc(coeff))                           # util/arithmetic.rs:47-69
+    assert got == b"".join(enc(coeff * pow(v, -1, m.R) % m.R if v else 0) for v in vals)
+    a = [int.from_bytes(rng.bytes(32), "little") % m.R for _ in range(n)]
+    assert L.fr_mul_vec(b"".join(map(enc, a)), b"".join(map(enc, vals)), n) == b"".join(enc(x * y % m.R) for x, y in zip(a, vals))
+    assert L.batch_invert(enc(0) * 3, 3) == enc(0) * 3                                             # all-zero input
