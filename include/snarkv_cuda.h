@@ -160,6 +160,15 @@ int snarkv_fr_batch_invert(snarkv_ctx* ctx, uint8_t* values, size_t n, const uin
 /* Element-wise product out[i] = a[i] * b[i] (the RLC scalars rho^i * s_i of the fused batch paths). */
 int snarkv_fr_mul_vec(snarkv_ctx* ctx, const uint8_t* a, const uint8_t* b, size_t n, int format, uint8_t* out);
 
+/* ---- (next row f2) Fiat-Shamir challenges of the Keccak `EvmTranscript` for m proofs of one transcript shape -------------------
+ * Replaces system/halo2/transcript/evm.rs:184-222 + loader/evm/util.rs:61-67 for a batch.  `streams`: m x stream_len bytes, the
+ * 32-byte big-endian words each proof absorbs, in order (common_scalar: 1 word, common_ec_point: x then y).  `seg_end[i]`: byte
+ * offset (multiple of 32, non-decreasing) after which the i-th challenge is squeezed.  Semantics per proof:
+ *   H_i = Keccak256( H_{i-1} || stream[seg_end[i-1] .. seg_end[i]) [|| 0x01 when that is exactly 32 bytes] ),  challenge_i = be(H_i) mod r.
+ * `challenges`: m x k x 32 B scalars in `format`. */
+int snarkv_evm_transcript_challenges(snarkv_ctx* ctx, const uint8_t* streams, size_t stream_len, const uint32_t* seg_end, size_t k, size_t m,
+                                     int format, uint8_t* challenges);
+
 /* ---- synthetic workload (bench / tests) ----------------------------------------------------------------------------------
  * Deterministic inputs (the test suite restates the same definition independently):
  *   scalar_i: 4 x splitmix64 limbs, top limb masked to 62 bits, one conditional subtraction of r;

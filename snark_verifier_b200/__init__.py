@@ -67,6 +67,7 @@ C_ABI = {
     "snarkv_fr_powers": (_i, [_vp, _vp, _sz, _i, _vp]),
     "snarkv_fr_batch_invert": (_i, [_vp, _vp, _sz, _vp, _i]),
     "snarkv_fr_mul_vec": (_i, [_vp, _vp, _vp, _sz, _i, _vp]),
+    "snarkv_evm_transcript_challenges": (_i, [_vp, _vp, _sz, _vp, _sz, _sz, _i, _vp]),
     "snarkv_kzg_accumulate": (_i, [_vp, _vp, _vp, _sz, _vp, _i, _vp, _vp]),
     "snarkv_kzg_set_deciding_key": (_i, [_vp, _vp, _vp, _vp]),
     "snarkv_kzg_decide_batch": (_i, [_vp, _vp, _vp, _sz, _i, _vp, _vp]),
@@ -259,6 +260,15 @@ class CudaLoader:
     def fr_mul_vec(self, a, b, n):
         out = ctypes.create_string_buffer(32 * n)
         self._check(self.lib.snarkv_fr_mul_vec(self.h, _addr(a), _addr(b), n, self.fmt, out), "fr_mul_vec")
+        return out.raw
+
+    def evm_transcript_challenges(self, streams, stream_len, seg_end, m):
+        """Keccak EvmTranscript challenges (transcript/evm.rs:184-222) for m proofs sharing one transcript shape -> m*k*32 bytes."""
+        k = len(seg_end)
+        se = (ctypes.c_uint32 * k)(*seg_end)
+        out = ctypes.create_string_buffer(32 * k * m)
+        self._check(self.lib.snarkv_evm_transcript_challenges(self.h, _addr(streams) if stream_len else None, stream_len,
+                                                              ctypes.cast(se, ctypes.c_void_p), k, m, self.fmt, out), "evm_transcript")
         return out.raw
 
     # -- synthetic workload ---------------------------------------------------------------------------------------

@@ -386,6 +386,32 @@ int snarkv_fr_mul_vec(snarkv_ctx* ctx, const uint8_t* a, const uint8_t* b, size_
     return SNARKV_OK;
 }
 
+// ---- (f2) EvmTranscript challenges for a batch of proofs ----------------------------------------------------------------------
+int snarkv_evm_transcript_challenges(snarkv_ctx* ctx, const uint8_t* streams, size_t stream_len, const uint32_t* seg_end, size_t k, size_t m,
+                                     int format, uint8_t* challenges) {
+    CTX_GUARD(ctx);
+    if (!seg_end || !challenges || bad_format(format) || k == 0 || (stream_len && !streams) || (stream_len & 31))
+        return ctx->fail(SNARKV_ERR_USAGE, "snarkv_evm_transcript_challenges: bad argument");
+    uint32_t prev = 0;
+    for (size_t i = 0; i < k; ++i) {
+        if (seg_end[i] < prev || (seg_end[i] & 31) || seg_end[i] > stream_len) return ctx->fail(SNARKV_ERR_USAGE, "seg_end must be non-decreasing multiples of 32 within the stream");
+        prev = seg_end[i];
+    }
+    if (m == 0) return SNARKV_OK;
+    uint8_t* d_s = (uint8_t*)ctx->wsget(WS_IO_A, m * stream_len);
+    uint32_t* d_e = (uint32_t*)ctx->wsget(WS_IO_B, k * 4);
+    uint8_t* d_o = (uint8_t*)ctx->wsget(WS_IO_C, m * k * 32);
+    if (!d_s || !d_e || !d_o) return SNARKV_ERR_CUDA;
+    cudaStream_t st = ctx->stream;
+    if (stream_len) SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_s, streams, m * stream_len, cudaMemcpyHostToDevice, st));
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_e, seg_end, k * 4, cudaMemcpyHostToDevice, st));
+    int rc = evm_transcript_device(ctx, d_s, stream_len, d_e, k, m, format, d_o);
+    if (rc) return rc;
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(challenges, d_o, m * k * 32, cudaMemcpyDeviceToHost, st));
+    SNARKV_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return SNARKV_OK;
+}
+
 // ---- test support ---------------------------------------------------------------------------------------------------------
 int snarkv_debug_field_op(snarkv_ctx* ctx, int field, int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) {
     CTX_GUARD(ctx);

@@ -172,6 +172,8 @@ int msm_batch_rlc_device(snarkv_ctx* ctx, const void* d_scalars, const void* d_p
 int fr_batch_invert_device(snarkv_ctx* ctx, void* d_values, size_t n, int format, const void* d_coeff, void* d_scratch);
 int fr_mul_vec_device(snarkv_ctx* ctx, const void* d_a, const void* d_b, size_t n, int format, void* d_out);
 int fr_from_mont_device(snarkv_ctx* ctx, void* d_v, size_t n);
+int evm_transcript_device(snarkv_ctx* ctx, const void* d_streams, size_t stream_len, const void* d_seg_end, size_t k, size_t m, int format,
+                          void* d_out);
 int fr_powers_device(snarkv_ctx* ctx, const void* d_r, int format, size_t n, void* d_out_mont);
 int field_op_device(snarkv_ctx* ctx, int field, int op, const void* d_a, const void* d_b, size_t n, void* d_out);
 int synth_scalars_device(snarkv_ctx* ctx, uint64_t seed, uint64_t start, size_t n, int format, void* d_out);
