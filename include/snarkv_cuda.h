@@ -73,6 +73,11 @@ int snarkv_set_window_bits(snarkv_ctx* ctx, int c);
  * 1 = always, 2 = never.  Results are identical. */
 int snarkv_set_glv_mode(snarkv_ctx* ctx, int mode);
 
+/* MSM tuning: bucket accumulation kernel (util/msm.rs:291-296).  0 = choose from the mean bucket load (default), 1 = XYZZ mixed
+ * additions (10 multiplications per point), 2 = batched affine additions with a shared inversion per <= 4096 additions (6 per
+ * point), 3 = run both and compare every task result on the device (debugging aid; synchronous).  Results are identical. */
+int snarkv_set_accumulate_mode(snarkv_ctx* ctx, int mode);
+
 /* KZG decide tuning: 0 = choose from N (default), 1 = one thread per check (largest batches), 2 = cooperative (block or warp
  * per check, chosen from N), 3 = one 160-thread block per check (lowest latency), 4 = one warp per check.  Results are identical. */
 int snarkv_set_pairing_mode(snarkv_ctx* ctx, int mode);

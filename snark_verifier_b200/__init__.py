@@ -58,6 +58,7 @@ C_ABI = {
     "snarkv_set_window_bits": (_i, [_vp, _i]),
     "snarkv_set_pairing_mode": (_i, [_vp, _i]),
     "snarkv_set_glv_mode": (_i, [_vp, _i]),
+    "snarkv_set_accumulate_mode": (_i, [_vp, _i]),
     "snarkv_g1_msm": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp]),
     "snarkv_g1_msm_partial": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp]),
     "snarkv_g1_msm_device": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp, _vp, _vp]),
@@ -162,6 +163,9 @@ class CudaLoader:
 
     def set_glv_mode(self, mode):
         self._check(self.lib.snarkv_set_glv_mode(self.h, mode), "set_glv_mode")
+
+    def set_accumulate_mode(self, mode):
+        self._check(self.lib.snarkv_set_accumulate_mode(self.h, mode), "set_accumulate_mode")
 
     def set_pairing_mode(self, mode):
         self._check(self.lib.snarkv_set_pairing_mode(self.h, mode), "set_pairing_mode")

@@ -94,6 +94,12 @@ int snarkv_set_pairing_mode(snarkv_ctx* ctx, int mode) {
     return SNARKV_OK;
 }
 
+int snarkv_set_accumulate_mode(snarkv_ctx* ctx, int mode) {
+    if (!ctx || mode < 0 || mode > 3) return SNARKV_ERR_USAGE;
+    ctx->accumulate_mode = mode;
+    return SNARKV_OK;
+}
+
 int snarkv_g1_msm_plan(snarkv_ctx* ctx, size_t n, uint32_t out[4]) {
     if (!ctx || !out) return SNARKV_ERR_USAGE;
     msm_plan_query(ctx, n, out);

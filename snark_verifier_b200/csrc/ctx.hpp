@@ -46,6 +46,11 @@ enum WsSlot : int {
     WS_BATCH_TERMS,       // batch-MSM per-term XYZZ
     WS_PAIR_A,
     WS_PAIR_B,
+    WS_BA_REGION_A,       // batched-affine accumulation: level-1/3/.. scratch, B x W x ((n + cap) / 2 + 2) x 64 B
+    WS_BA_REGION_B,       // level-2/4/.. scratch, half of that
+    WS_BA_PREFIX,         // per resident block: K x 128 x 32 B prefix products
+    WS_BA_COUNTER,        // [group counter | self-check mismatch record x 4]
+    WS_TASK_OUT_CHECK,    // second task-result array (accumulate mode 3)
     WS_SLOTS
 };
 
@@ -61,6 +66,8 @@ struct snarkv_ctx {
     int window_bits = 0;
     int glv_mode = 0;       // 0 = GLV for n < 2^22 (default), 1 = always, 2 = never
     int pairing_mode = 0;   // 0 = choose from N, 1 = one thread per check, 2 = one block per check
+    int accumulate_mode = 0;   // 0 = choose from the bucket load, 1 = XYZZ, 2 = batched affine, 3 = both + task-level self-check
+    int ba_blocks_per_sm = 0;  // occupancy of k_bucket_accumulate_affine (queried once)
     uint64_t launches = 0;
     int sm_count = 148;
 

@@ -20,6 +20,7 @@
 #include "ctx.hpp"
 #include "g1.cuh"
 #include "glv.cuh"
+#include "bucket_affine.cuh"
 
 namespace snarkv {
 
@@ -651,13 +652,60 @@ static int msm_accumulate_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* 
             if (cz) pts[z] = cz;
         }
     }
-    {
+    // accumulate mode: batched affine pays once the lists are long enough for a few full pair levels (mean bucket load >= 64)
+    const int mode = ctx->accumulate_mode;
+    const bool affine = mode >= 2 || (mode == 0 && nv / pl.NB >= 64);
+    if (!affine || mode == 3) {
         Stage sg(ctx, "msm_bucket_accumulate");
+        uint8_t* dst = wk.task_out;
+        if (mode == 3) {
+            dst = (uint8_t*)ctx->wsget(WS_TASK_OUT_CHECK, (size_t)B * pl.W * pl.cap * 128);
+            if (!dst) return SNARKV_ERR_CUDA;
+        }
         dim3 grid((pl.cap + 127) / 128, pl.W, B);
         k_bucket_accumulate<<<grid, 128, 0, st>>>(pts[0], pts[1], wk.sorted, wk.offsets, wk.counts, wk.tasks, wk.window_tasks, wk.order, nv,
-                                                 pl.NB, pl.T, pl.cap, wk.task_out);
+                                                 pl.NB, pl.T, pl.cap, dst);
         SNARKV_LAUNCH_CHECK(ctx, "k_bucket_accumulate");
         sg.launched();
+    }
+    if (affine) {
+        Stage sg(ctx, "msm_bucket_accumulate_affine");
+        if (ctx->ba_blocks_per_sm == 0) {
+            int per_sm = 0;
+            SNARKV_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bucket_accumulate_affine, SNARKV_BA_THREADS, 0));
+            ctx->ba_blocks_per_sm = per_sm > 0 ? per_sm : 1;
+        }
+        const size_t stride_a = (nv + pl.cap) / 2 + 2, stride_b = (stride_a + pl.cap) / 2 + 2;
+        const uint32_t groups = ((pl.cap + SNARKV_BA_THREADS - 1) / SNARKV_BA_THREADS) * pl.W * (uint32_t)B;
+        uint32_t blocks = (uint32_t)(ctx->sm_count * ctx->ba_blocks_per_sm);
+        if (blocks > groups) blocks = groups;
+        uint8_t* reg_a = (uint8_t*)ctx->wsget(WS_BA_REGION_A, (size_t)B * pl.W * stride_a * 64);
+        uint8_t* reg_b = (uint8_t*)ctx->wsget(WS_BA_REGION_B, (size_t)B * pl.W * stride_b * 64);
+        uint8_t* slab = (uint8_t*)ctx->wsget(WS_BA_PREFIX, (size_t)ctx->sm_count * ctx->ba_blocks_per_sm * SNARKV_BA_K * SNARKV_BA_THREADS * 32);
+        uint32_t* ctr = (uint32_t*)ctx->wsget(WS_BA_COUNTER, 32);
+        if (!reg_a || !reg_b || !slab || !ctr) return SNARKV_ERR_CUDA;
+        SNARKV_CUDA_TRY(ctx, cudaMemsetAsync(ctr, 0, 32, st));
+        k_bucket_accumulate_affine<<<blocks, SNARKV_BA_THREADS, 0, st>>>(pts[0], pts[1], wk.sorted, wk.offsets, wk.counts, wk.tasks, wk.window_tasks,
+                                                                        wk.order, nv, pl.NB, pl.T, pl.cap, pl.W, (uint32_t)B, wk.task_out, reg_a,
+                                                                        reg_b, stride_a, stride_b, slab, ctr);
+        SNARKV_LAUNCH_CHECK(ctx, "k_bucket_accumulate_affine");
+        sg.launched();
+        if (mode == 3) {   // debugging aid: both kernels ran; compare every task result as a group element (synchronous)
+            dim3 grid((pl.cap + 127) / 128, pl.W, B);
+            k_compare_task_results<<<grid, 128, 0, st>>>(wk.task_out, (const uint8_t*)ctx->ws[WS_TASK_OUT_CHECK], wk.window_tasks, wk.order, pl.cap,
+                                                        pl.W, ctr + 1);
+            SNARKV_LAUNCH_CHECK(ctx, "k_compare_task_results");
+            sg.launched();
+            uint32_t rec[4] = {};
+            SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(rec, ctr + 1, 16, cudaMemcpyDeviceToHost, st));
+            SNARKV_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+            if (rec[0] != 0) {
+                char msg[160];
+                snprintf(msg, sizeof msg, "batched-affine self-check: %u task result(s) differ from the XYZZ kernel; first: window %u, slot %u, set %u",
+                         rec[0], rec[1], rec[2], rec[3]);
+                return ctx->fail(SNARKV_ERR_CUDA, msg);
+            }
+        }
     }
     {
         Stage sg(ctx, "msm_bucket_merge");
