@@ -23,8 +23,10 @@
 namespace snarkv {
 
 #define SNARKV_BA_THREADS 128
-#define SNARKV_BA_K 32          // pair-additions per thread per shared inversion
-#define SNARKV_BA_PAIRS_MIN 12  // run another affine level while the longest list of the block still has this many pairs
+#define SNARKV_BA_K_MAX 64      // largest batch: pair-additions per thread per shared inversion (sizes the prefix slab)
+#define SNARKV_BA_K 32          // default batch
+#define SNARKV_BA_PAIRS_MIN 12  // default: run another affine level while the longest list of the block still has this many pairs
+
 
 // plain (coherent) 128-bit loads: the scratch regions are written by this kernel, so the read-only path (__ldg) is not allowed
 __device__ __forceinline__ Fq fq_load_rw(const void* p) {
@@ -58,7 +60,32 @@ struct BaSource {
         }
         return g1_affine_load_rw(region, j);
     }
+    // addresses of the two operands of pair i (items 2i, 2i + 1) and their sign bits (bit 0: negate a, bit 1: negate b)
+    __device__ __forceinline__ void pair_addr(uint32_t i, const uint8_t*& pa, const uint8_t*& pb, uint32_t& signs) const {
+        if (refs) {
+            const uint32_t e0 = list[2 * i], e1 = list[2 * i + 1];
+            pa = points + (size_t)(e0 & 0x7fffffffu) * 64;
+            pb = points + (size_t)(e1 & 0x7fffffffu) * 64;
+            signs = (e0 >> 31) | ((e1 >> 31) << 1);
+        } else {
+            pa = region + (size_t)(2 * i) * 64;
+            pb = pa + 64;
+            signs = 0;
+        }
+    }
+    // one coordinate (32 B): the caller's array goes through the read-only path, this kernel's scratch through coherent loads
+    __device__ __forceinline__ Fq load_coord(const uint8_t* p) const { return refs ? fp_load<FQ>(p) : fq_load_rw(p); }
 };
+
+// branch-free conditional negation (the point loads of a pair stay back to back instead of being split by a branch)
+__device__ __forceinline__ Fq fq_cneg(const Fq& y, uint32_t neg) {
+    const Fq ny = fp_neg(y);
+    const uint32_t mask = 0u - neg;
+    Fq r;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r.v[k] = (ny.v[k] & mask) | (y.v[k] & ~mask);
+    return r;
+}
 
 // kind of a pair addition a + b: 0 = chord (d = x2 - x1), 1 = tangent (d = 2 y1), 2 = a is the identity (result b),
 // 3 = b is the identity (result a), 4 = result is the identity.  Only kinds 0 and 1 need 1 / d.
@@ -105,13 +132,13 @@ k_bucket_accumulate_affine(const uint8_t* __restrict__ points0, const uint8_t* _
                            const uint32_t* __restrict__ window_tasks, const uint32_t* __restrict__ order, size_t n, uint32_t NB,
                            uint32_t T, uint32_t cap, uint32_t W, uint32_t Z, uint8_t* __restrict__ task_out, uint8_t* region_a,
                            uint8_t* region_b, size_t region_a_stride, size_t region_b_stride, uint8_t* prefix_slab,
-                           uint32_t* __restrict__ group_counter) {
+                           uint32_t* __restrict__ group_counter, uint32_t K, uint32_t pairs_min) {
     __shared__ Fq tree[2 * SNARKV_BA_THREADS];
     __shared__ uint32_t s_group, s_max[SNARKV_BA_THREADS / 32];
     const uint32_t t = threadIdx.x;
     const uint32_t groups_per_window = (cap + SNARKV_BA_THREADS - 1) / SNARKV_BA_THREADS;
     const uint32_t total_groups = groups_per_window * W * Z;
-    uint8_t* pref = prefix_slab + (size_t)blockIdx.x * SNARKV_BA_K * SNARKV_BA_THREADS * 32 + (size_t)t * 32;
+    uint8_t* pref = prefix_slab + (size_t)blockIdx.x * SNARKV_BA_K_MAX * SNARKV_BA_THREADS * 32 + (size_t)t * 32;
     uint32_t batch_no = blockIdx.x;   // rotates the inverting thread over the four schedulers
     for (;;) {
         __syncthreads();
@@ -152,36 +179,62 @@ k_bucket_accumulate_affine(const uint8_t* __restrict__ points0, const uint8_t* _
 
         uint32_t level = 0;
 #pragma unroll 1
-        while ((mmax >> 1) >= SNARKV_BA_PAIRS_MIN) {
+        while ((mmax >> 1) >= pairs_min) {
             const uint32_t pairs = m >> 1, maxpairs = mmax >> 1;
             uint8_t* dst = (level & 1u) ? reg_b : reg_a;
 #pragma unroll 1
-            for (uint32_t cb = 0; cb < maxpairs; cb += SNARKV_BA_K, ++batch_no) {
-                const uint32_t lo = min(cb, pairs), hi = min(cb + SNARKV_BA_K, pairs);
-                // forward: exclusive prefix products of the denominators
+            for (uint32_t cb = 0; cb < maxpairs; cb += K, ++batch_no) {
+                const uint32_t lo = min(cb, pairs), hi = min(cb + K, pairs);
+                // forward: exclusive prefix products of the denominators.  Only the x coordinates are needed unless the pair is
+                // exceptional; the loads of pair i + 1 are issued before the multiplication of pair i, its addresses one pair earlier.
                 Fq run = fp_one<FQ>();
+                const uint8_t *pa_n = nullptr, *pb_n = nullptr;
+                uint32_t sg_n = 0;
+                Fq axn = fp_zero<FQ>(), bxn = fp_zero<FQ>();
+                if (lo < hi) {
+                    src.pair_addr(lo, pa_n, pb_n, sg_n);
+                    axn = src.load_coord(pa_n);
+                    bxn = src.load_coord(pb_n);
+                    if (lo + 1 < hi) src.pair_addr(lo + 1, pa_n, pb_n, sg_n);
+                }
 #pragma unroll 1
                 for (uint32_t i = lo; i < hi; ++i) {
-                    const G1Affine a = src.get(2 * i), b = src.get(2 * i + 1);
-                    Fq d;
-                    const int kind = ba_classify(a, b, d);
-                    if (kind <= 1) {
-                        fp_store<FQ>(pref + (size_t)(i - lo) * SNARKV_BA_THREADS * 32, run);
-                        run = fp_mul(run, d);
+                    const Fq ax = axn, bx = bxn;
+                    if (i + 1 < hi) {
+                        axn = src.load_coord(pa_n);
+                        bxn = src.load_coord(pb_n);
+                        if (i + 2 < hi) src.pair_addr(i + 2, pa_n, pb_n, sg_n);
                     }
+                    Fq d = fp_sub(bx, ax);
+                    if (fp_is_zero(ax) || fp_is_zero(bx) || fp_is_zero(d)) {   // rare: identity operand, equal or opposite points
+                        const G1Affine a = src.get(2 * i), b = src.get(2 * i + 1);
+                        if (ba_classify(a, b, d) > 1) continue;
+                    }
+                    fp_store<FQ>(pref + (size_t)(i - lo) * SNARKV_BA_THREADS * 32, run);
+                    run = fp_mul(run, d);
                 }
                 tree[SNARKV_BA_THREADS + t] = run;
                 ba_block_invert(tree, t, (batch_no & 3u) * 32u);
                 Fq acc = tree[SNARKV_BA_THREADS + t];
-                // backward: 1 / d_i = acc * prefix_i, acc *= d_i; then the chord / tangent formula
+                // backward: 1 / d_i = acc * prefix_i, acc *= d_i; then the chord / tangent formula.  All five operands of a pair
+                // are requested at the top of its iteration and the prefix (L2-resident slab) is consumed first, so that the
+                // multiplication acc * prefix_i runs while the gathered coordinates are still in flight.
+                if (lo < hi) src.pair_addr(hi - 1, pa_n, pb_n, sg_n);
 #pragma unroll 1
                 for (uint32_t i = hi; i-- > lo;) {
-                    const G1Affine a = src.get(2 * i), b = src.get(2 * i + 1);
+                    const Fq pf = fq_load_rw(pref + (size_t)(i - lo) * SNARKV_BA_THREADS * 32);
+                    G1Affine a, b;
+                    a.x = src.load_coord(pa_n); a.y = src.load_coord(pa_n + 32);
+                    b.x = src.load_coord(pb_n); b.y = src.load_coord(pb_n + 32);
+                    const uint32_t sg = sg_n;
+                    if (i > lo) src.pair_addr(i - 1, pa_n, pb_n, sg_n);
+                    const Fq inv = fp_mul(acc, pf);          // unused (and pf undefined) for pairs that need no division
+                    a.y = fq_cneg(a.y, sg & 1u);
+                    b.y = fq_cneg(b.y, sg >> 1);
                     Fq d;
                     const int kind = ba_classify(a, b, d);
                     G1Affine o;
                     if (kind <= 1) {
-                        const Fq inv = fp_mul(acc, fq_load_rw(pref + (size_t)(i - lo) * SNARKV_BA_THREADS * 32));
                         acc = fp_mul(acc, d);
                         Fq num;
                         if (kind == 0) num = fp_sub(b.y, a.y);

@@ -6,6 +6,8 @@
 // INTEGRATION.md.  There is no CPU arithmetic here — only copies, launches and status decoding.
 #include <new>
 
+#include <cstdlib>
+
 #include "ctx.hpp"
 
 using namespace snarkv;
@@ -49,6 +51,15 @@ int snarkv_init(int device, snarkv_ctx** out) {
             return SNARKV_ERR_CUDA;
         }
     c->stream = c->own_stream;
+    // developer tuning knobs of the batched-affine accumulation (bucket_affine.cuh); the defaults are the measured optimum
+    auto env_int = [](const char* name, int lo, int hi, int dflt) {
+        const char* v = getenv(name);
+        if (!v || !*v) return dflt;
+        const int x = atoi(v);
+        return x < lo ? lo : (x > hi ? hi : x);
+    };
+    c->ba_k = env_int("SNARKV_BA_K", 1, 64, c->ba_k);
+    c->ba_pairs_min = env_int("SNARKV_BA_PAIRS_MIN", 1, 1 << 20, c->ba_pairs_min);
     *out = c;
     return SNARKV_OK;
 }

@@ -681,13 +681,14 @@ static int msm_accumulate_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* 
         if (blocks > groups) blocks = groups;
         uint8_t* reg_a = (uint8_t*)ctx->wsget(WS_BA_REGION_A, (size_t)B * pl.W * stride_a * 64);
         uint8_t* reg_b = (uint8_t*)ctx->wsget(WS_BA_REGION_B, (size_t)B * pl.W * stride_b * 64);
-        uint8_t* slab = (uint8_t*)ctx->wsget(WS_BA_PREFIX, (size_t)ctx->sm_count * ctx->ba_blocks_per_sm * SNARKV_BA_K * SNARKV_BA_THREADS * 32);
+        uint8_t* slab = (uint8_t*)ctx->wsget(WS_BA_PREFIX, (size_t)ctx->sm_count * ctx->ba_blocks_per_sm * SNARKV_BA_K_MAX * SNARKV_BA_THREADS * 32);
         uint32_t* ctr = (uint32_t*)ctx->wsget(WS_BA_COUNTER, 32);
         if (!reg_a || !reg_b || !slab || !ctr) return SNARKV_ERR_CUDA;
         SNARKV_CUDA_TRY(ctx, cudaMemsetAsync(ctr, 0, 32, st));
         k_bucket_accumulate_affine<<<blocks, SNARKV_BA_THREADS, 0, st>>>(pts[0], pts[1], wk.sorted, wk.offsets, wk.counts, wk.tasks, wk.window_tasks,
                                                                         wk.order, nv, pl.NB, pl.T, pl.cap, pl.W, (uint32_t)B, wk.task_out, reg_a,
-                                                                        reg_b, stride_a, stride_b, slab, ctr);
+                                                                        reg_b, stride_a, stride_b, slab, ctr, (uint32_t)ctx->ba_k,
+                                                                        (uint32_t)ctx->ba_pairs_min);
         SNARKV_LAUNCH_CHECK(ctx, "k_bucket_accumulate_affine");
         sg.launched();
         if (mode == 3) {   // debugging aid: both kernels ran; compare every task result as a group element (synchronous)
