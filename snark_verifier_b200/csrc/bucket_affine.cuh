@@ -28,6 +28,36 @@ namespace snarkv {
 #define SNARKV_BA_PAIRS_MIN 12  // default: run another affine level while the longest list of the block still has this many pairs
 
 
+// ONE copy of the Montgomery multiplication for this kernel (a call costs ~12 register moves on top of ~170 instructions): its
+// warps sit in different phases (forward pass, backward pass, inversion, tail), and with the multiplication inlined at all ~45
+// sites the code outgrows the instruction caches (measured: "no instruction" became the top stall reason).
+static __device__ __noinline__ Fq fq_mul_call(const Fq a, const Fq b) { return fp_mul(a, b); }
+
+// acc += (x2, y2) exactly like xyzz_madd (g1.cuh), through the shared multiplication
+static __device__ __noinline__ void ba_xyzz_madd(G1Xyzz& acc, const Fq& x2, const Fq& y2) {
+    if (xyzz_is_identity(acc)) {
+        acc.x = x2; acc.y = y2; acc.zz = fp_one<FQ>(); acc.zzz = fp_one<FQ>();
+        return;
+    }
+    const Fq u2 = fq_mul_call(x2, acc.zz);
+    const Fq s2 = fq_mul_call(y2, acc.zzz);
+    const Fq p = fp_sub(u2, acc.x);
+    const Fq r = fp_sub(s2, acc.y);
+    if (fp_is_zero(p)) {
+        if (fp_is_zero(r)) acc = xyzz_dbl_affine(x2, y2);
+        else acc = xyzz_identity();
+        return;
+    }
+    const Fq pp = fq_mul_call(p, p);
+    const Fq ppp = fq_mul_call(p, pp);
+    const Fq q = fq_mul_call(acc.x, pp);
+    const Fq x3 = fp_sub(fp_sub(fq_mul_call(r, r), ppp), fp_dbl(q));
+    acc.y = fp_sub(fq_mul_call(r, fp_sub(q, x3)), fq_mul_call(acc.y, ppp));
+    acc.x = x3;
+    acc.zz = fq_mul_call(acc.zz, pp);
+    acc.zzz = fq_mul_call(acc.zzz, ppp);
+}
+
 // plain (coherent) 128-bit loads: the scratch regions are written by this kernel, so the read-only path (__ldg) is not allowed
 __device__ __forceinline__ Fq fq_load_rw(const void* p) {
     const uint4* q = reinterpret_cast<const uint4*>(p);
@@ -46,11 +76,16 @@ __device__ __forceinline__ G1Affine g1_affine_load_rw(const uint8_t* base, size_
 
 // item j of the current level: level 0 = sorted reference (index | sign << 31) into the caller's point array, later levels =
 // materialised affine points in the task's scratch region
+struct BaTask;
 struct BaSource {
     const uint8_t* points;    // level 0
     const uint32_t* list;     // level 0
     const uint8_t* region;    // level >= 1
     bool refs;
+    __device__ __forceinline__ void make(const BaTask& tk, uint32_t level, const uint8_t* pts, uint8_t* region_a, uint8_t* region_b,
+                                         size_t stride_a, size_t stride_b, uint32_t W);
+    __device__ __forceinline__ uint8_t* dest(const BaTask& tk, uint32_t level, uint8_t* region_a, uint8_t* region_b, size_t stride_a,
+                                             size_t stride_b, uint32_t W) const;
     __device__ __forceinline__ G1Affine get(uint32_t j) const {
         if (refs) {
             const uint32_t e = list[j];
@@ -60,10 +95,14 @@ struct BaSource {
         }
         return g1_affine_load_rw(region, j);
     }
-    // addresses of the two operands of pair i (items 2i, 2i + 1) and their sign bits (bit 0: negate a, bit 1: negate b)
-    __device__ __forceinline__ void pair_addr(uint32_t i, const uint8_t*& pa, const uint8_t*& pb, uint32_t& signs) const {
+    // Operands of pair i (items 2i, 2i + 1) in two steps, so that the level-0 index loads get a whole iteration to complete:
+    // pair_ref requests the two sorted references, pair_addr turns them into addresses + sign bits (bit 0: negate a, bit 1: b).
+    __device__ __forceinline__ void pair_ref(uint32_t i, uint32_t& e0, uint32_t& e1) const {
+        if (refs) { e0 = list[2 * i]; e1 = list[2 * i + 1]; }
+    }
+    __device__ __forceinline__ void pair_addr(uint32_t i, uint32_t e0, uint32_t e1, const uint8_t*& pa, const uint8_t*& pb,
+                                              uint32_t& signs) const {
         if (refs) {
-            const uint32_t e0 = list[2 * i], e1 = list[2 * i + 1];
             pa = points + (size_t)(e0 & 0x7fffffffu) * 64;
             pb = points + (size_t)(e1 & 0x7fffffffu) * 64;
             signs = (e0 >> 31) | ((e1 >> 31) << 1);
@@ -101,173 +140,272 @@ __device__ __forceinline__ int ba_classify(const G1Affine& a, const G1Affine& b,
     return 4;
 }
 
-// tree[1] = product of the 128 leaves tree[128 + t]; afterwards tree[128 + t] = 1 / leaf_t.  Heap layout, in place.
-// Called by all SNARKV_BA_THREADS threads; `inverter` is the thread that performs the single field inversion.
-__device__ __forceinline__ void ba_block_invert(Fq* tree, uint32_t t, uint32_t inverter) {
-    __syncthreads();
+// ---- warp-wide Montgomery trick -----------------------------------------------------------------------------------------
+__device__ __forceinline__ Fq fq_shfl(const Fq& a, int src_lane) {
+    Fq r;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r.v[k] = __shfl_sync(0xffffffffu, a.v[k], src_lane);
+    return r;
+}
+__device__ __forceinline__ Fq fq_shfl_up(const Fq& a, uint32_t delta) {
+    Fq r;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r.v[k] = __shfl_up_sync(0xffffffffu, a.v[k], delta);
+    return r;
+}
+__device__ __forceinline__ Fq fq_shfl_down(const Fq& a, uint32_t delta) {
+    Fq r;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r.v[k] = __shfl_down_sync(0xffffffffu, a.v[k], delta);
+    return r;
+}
+__device__ __forceinline__ Fq fq_select(bool c, const Fq& a, const Fq& b) {
+    Fq r;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r.v[k] = c ? a.v[k] : b.v[k];
+    return r;
+}
+// Every lane passes a non-zero `run`; returns 1 / run with ONE field inversion for the warp: inclusive prefix and suffix
+// products by shuffle scans (5 steps each), lane 0 inverts the total, 1 / run_l = inv * (prefix before l) * (suffix after l).
+// The inversion is integer-ALU work of one lane; the other warps of the scheduler keep the multiplier busy meanwhile.
+static __device__ __noinline__ Fq ba_warp_invert(const Fq& run, uint32_t lane) {
+    __syncwarp();
+    Fq pre = run, suf = run;
 #pragma unroll 1
-    for (uint32_t s = SNARKV_BA_THREADS / 2; s >= 1; s >>= 1) {
-        if (t < s) tree[s + t] = fp_mul(tree[2 * (s + t)], tree[2 * (s + t) + 1]);
-        __syncthreads();
+    for (uint32_t o = 1; o < 32; o <<= 1) {
+        const Fq mp = fq_mul_call(pre, fq_shfl_up(pre, o));
+        const Fq ms = fq_mul_call(suf, fq_shfl_down(suf, o));
+        pre = fq_select(lane >= o, mp, pre);
+        suf = fq_select(lane + o < 32, ms, suf);
     }
-    if (t == inverter) tree[1] = fp_inv_serial(tree[1]);
-    __syncthreads();
-#pragma unroll 1
-    for (uint32_t s = 1; s < SNARKV_BA_THREADS; s <<= 1) {
-        if (t < s) {
-            const uint32_t i = s + t;
-            const Fq inv = tree[i], l = tree[2 * i], r = tree[2 * i + 1];
-            tree[2 * i] = fp_mul(inv, r);
-            tree[2 * i + 1] = fp_mul(inv, l);
-        }
-        __syncthreads();
-    }
+    Fq inv = fq_shfl(pre, 31);
+    if (lane == 0) inv = fp_inv_serial(inv);
+    __syncwarp();
+    inv = fq_shfl(inv, 0);
+    const Fq before = fq_select(lane > 0, fq_shfl_up(pre, 1), fp_one<FQ>());
+    const Fq after = fq_select(lane < 31, fq_shfl_down(suf, 1), fp_one<FQ>());
+    return fq_mul_call(fq_mul_call(inv, before), after);
 }
 
-// Persistent kernel: blocks pull groups of 128 length-ordered tasks from a global counter.  Group g -> (rank group gi, window
-// w, base set z) with the rank group outermost, so the longest tasks of all windows are started first.
+// per-task state, parked in shared memory between the phases of a group (one entry per lane and task slot q)
+struct BaTask {
+    const uint32_t* list;   // the task's run of sorted references
+    uint32_t sa, sb;        // first item of its level-1/3/.. and level-2/4/.. scratch regions (within window w of base set z)
+    uint32_t m0;            // list length; 0 = no task
+    uint32_t slot;          // task slot within the window (where the result goes)
+    uint32_t w, z;
+};
+
+#define SNARKV_BA_Q_MAX 4   // tasks per lane that share one inversion
+
+// level 0 reads the sorted references; level l >= 1 reads what level l - 1 wrote: region A after even levels, B after odd ones
+__device__ __forceinline__ void BaSource::make(const BaTask& tk, uint32_t level, const uint8_t* pts, uint8_t* region_a, uint8_t* region_b,
+                                               size_t stride_a, size_t stride_b, uint32_t W) {
+    points = pts;
+    list = tk.list;
+    refs = level == 0;
+    const size_t win = (size_t)tk.z * W + tk.w;
+    region = (level & 1u) ? region_a + (win * stride_a + tk.sa) * 64 : region_b + (win * stride_b + tk.sb) * 64;
+}
+__device__ __forceinline__ uint8_t* BaSource::dest(const BaTask& tk, uint32_t level, uint8_t* region_a, uint8_t* region_b, size_t stride_a,
+                                                   size_t stride_b, uint32_t W) const {
+    const size_t win = (size_t)tk.z * W + tk.w;
+    return (level & 1u) ? region_b + (win * stride_b + tk.sb) * 64 : region_a + (win * stride_a + tk.sa) * 64;
+}
+
+// Persistent kernel of independent warps.  Work is handed out in units of 32 length-ordered tasks (unit u -> rank group
+// gi = u / (W Z), then base set z and window w, so that the longest tasks of all windows come first); a warp takes Q units at a
+// time (fewer near the end of the queue, for balance) and runs their 32 Q lists level by level, one shared inversion per batch
+// of up to K pairs of each list.
 __global__ void __launch_bounds__(SNARKV_BA_THREADS, 4)
 k_bucket_accumulate_affine(const uint8_t* __restrict__ points0, const uint8_t* __restrict__ points1, const uint32_t* __restrict__ sorted,
                            const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts, const uint2* __restrict__ tasks,
                            const uint32_t* __restrict__ window_tasks, const uint32_t* __restrict__ order, size_t n, uint32_t NB,
                            uint32_t T, uint32_t cap, uint32_t W, uint32_t Z, uint8_t* __restrict__ task_out, uint8_t* region_a,
                            uint8_t* region_b, size_t region_a_stride, size_t region_b_stride, uint8_t* prefix_slab,
-                           uint32_t* __restrict__ group_counter, uint32_t K, uint32_t pairs_min) {
-    __shared__ Fq tree[2 * SNARKV_BA_THREADS];
-    __shared__ uint32_t s_group, s_max[SNARKV_BA_THREADS / 32];
-    const uint32_t t = threadIdx.x;
-    const uint32_t groups_per_window = (cap + SNARKV_BA_THREADS - 1) / SNARKV_BA_THREADS;
-    const uint32_t total_groups = groups_per_window * W * Z;
-    uint8_t* pref = prefix_slab + (size_t)blockIdx.x * SNARKV_BA_K_MAX * SNARKV_BA_THREADS * 32 + (size_t)t * 32;
-    uint32_t batch_no = blockIdx.x;   // rotates the inverting thread over the four schedulers
+                           uint32_t* group_counter, uint32_t K, uint32_t pairs_min, uint32_t Qmax) {
+    __shared__ BaTask s_task[SNARKV_BA_Q_MAX][SNARKV_BA_THREADS];
+    const uint32_t t = threadIdx.x, lane = t & 31u;
+    const uint32_t warp_global = (blockIdx.x * SNARKV_BA_THREADS + t) >> 5, n_warps = (gridDim.x * SNARKV_BA_THREADS) >> 5;
+    // units beyond the longest window's task count are empty: the queue ends at gi_end
+    uint32_t wt_max = 0;
+    for (uint32_t w = lane; w < W; w += 32) wt_max = max(wt_max, window_tasks[w]);
+    wt_max = __reduce_max_sync(0xffffffffu, wt_max);
+    const uint32_t total_units = ((wt_max + 31u) >> 5) * W * Z;
+    uint8_t* pref = prefix_slab + ((size_t)warp_global * SNARKV_BA_Q_MAX * SNARKV_BA_K_MAX * 32 + lane) * 32;
     for (;;) {
-        __syncthreads();
-        if (t == 0) s_group = atomicAdd(group_counter, 1u);
-        __syncthreads();
-        const uint32_t g = s_group;
-        if (g >= total_groups) break;
-        const uint32_t gi = g / (W * Z), rem = g - gi * (W * Z);
-        const uint32_t z = rem / W, w = rem - z * W;
-        const uint32_t rank = gi * SNARKV_BA_THREADS + t;
-        if (gi * SNARKV_BA_THREADS >= window_tasks[w]) continue;   // block-uniform
-        const bool active = rank < window_tasks[w];
-        const uint8_t* __restrict__ points = z == 0 ? points0 : points1;
-        uint32_t slot = 0, m = 0;
-        BaSource src;
-        src.points = points; src.list = sorted; src.region = nullptr; src.refs = true;
-        uint8_t *reg_a = nullptr, *reg_b = nullptr;
-        if (active) {
-            slot = order[(size_t)w * cap + rank];
-            const uint2 task = tasks[(size_t)w * cap + slot];
-            const uint32_t bucket = w * NB + task.x;
-            const uint32_t first = task.y * T;
-            m = min(T, counts[bucket] - first);
-            const uint32_t pos = offsets[bucket] + first;
-            src.list = sorted + (size_t)w * n + pos;
-            // level-1 region: items [sa, sa + ceil(m/2)); level-2 region: [sb, sb + ceil(ceil(m/2)/2)).  Consecutive tasks
-            // (pos' = pos + m, slot' = slot + 1) get disjoint regions: floor((X + m + 1) / 2) - floor(X / 2) >= ceil(m / 2).
-            const uint32_t sa = (pos + slot + 1u) >> 1;
-            const uint32_t sb = (sa + slot + 1u) >> 1;
-            reg_a = region_a + ((size_t)(z * W + w) * region_a_stride + sa) * 64;
-            reg_b = region_b + ((size_t)(z * W + w) * region_b_stride + sb) * 64;
+        // take Q units: Qmax while the queue holds that many per warp, fewer in the last round (balance)
+        uint32_t u0 = 0, Q = 0;
+        if (lane == 0) {
+            const uint32_t seen = *(volatile uint32_t*)group_counter;
+            const uint32_t left = seen < total_units ? total_units - seen : 0u;
+            Q = min(Qmax, max(1u, left / n_warps));
+            u0 = atomicAdd(group_counter, Q);
         }
-        // block-wide maximum list length
-        uint32_t mmax = __reduce_max_sync(0xffffffffu, m);
-        if ((t & 31u) == 0) s_max[t >> 5] = mmax;
-        __syncthreads();
-        mmax = max(max(s_max[0], s_max[1]), max(s_max[2], s_max[3]));
+        u0 = __shfl_sync(0xffffffffu, u0, 0);
+        Q = __shfl_sync(0xffffffffu, Q, 0);
+        if (u0 >= total_units) break;
+        // ---- task set-up ----
+        uint32_t mmax = 0;
+        for (uint32_t q = 0; q < Q; ++q) {
+            BaTask tk;
+            tk.list = sorted; tk.sa = tk.sb = tk.m0 = tk.slot = tk.w = tk.z = 0;
+            const uint32_t u = u0 + q;
+            if (u < total_units) {
+                const uint32_t gi = u / (W * Z), rem = u - gi * (W * Z);
+                tk.z = rem / W;
+                tk.w = rem - tk.z * W;
+                const uint32_t rank = gi * 32u + lane;
+                if (rank < window_tasks[tk.w]) {
+                    tk.slot = order[(size_t)tk.w * cap + rank];
+                    const uint2 task = tasks[(size_t)tk.w * cap + tk.slot];
+                    const uint32_t bucket = tk.w * NB + task.x;
+                    const uint32_t first = task.y * T;
+                    tk.m0 = min(T, counts[bucket] - first);
+                    const uint32_t pos = offsets[bucket] + first;
+                    tk.list = sorted + (size_t)tk.w * n + pos;
+                    // level-1 region: items [sa, sa + ceil(m/2)); level-2 region: [sb, sb + ceil(ceil(m/2)/2)).  Consecutive tasks
+                    // (pos' = pos + m, slot' = slot + 1) get disjoint regions: floor((X + m + 1) / 2) - floor(X / 2) >= ceil(m / 2).
+                    tk.sa = (pos + tk.slot + 1u) >> 1;
+                    tk.sb = (tk.sa + tk.slot + 1u) >> 1;
+                }
+            }
+            s_task[q][t] = tk;
+            mmax = max(mmax, tk.m0);
+        }
+        mmax = __reduce_max_sync(0xffffffffu, mmax);
 
         uint32_t level = 0;
 #pragma unroll 1
-        while ((mmax >> 1) >= pairs_min) {
-            const uint32_t pairs = m >> 1, maxpairs = mmax >> 1;
-            uint8_t* dst = (level & 1u) ? reg_b : reg_a;
+        for (;; ++level) {
+            const uint32_t mmax_l = (mmax + (1u << level) - 1u) >> level;
+            const uint32_t maxpairs = mmax_l >> 1;
+            if (maxpairs < pairs_min || level >= 31) break;
 #pragma unroll 1
-            for (uint32_t cb = 0; cb < maxpairs; cb += K, ++batch_no) {
-                const uint32_t lo = min(cb, pairs), hi = min(cb + K, pairs);
+            for (uint32_t cb = 0; cb < maxpairs; cb += K) {
                 // forward: exclusive prefix products of the denominators.  Only the x coordinates are needed unless the pair is
-                // exceptional; the loads of pair i + 1 are issued before the multiplication of pair i, its addresses one pair earlier.
+                // exceptional; the loads of pair i + 1 are issued before the multiplication of pair i, its references one earlier.
                 Fq run = fp_one<FQ>();
-                const uint8_t *pa_n = nullptr, *pb_n = nullptr;
-                uint32_t sg_n = 0;
-                Fq axn = fp_zero<FQ>(), bxn = fp_zero<FQ>();
-                if (lo < hi) {
-                    src.pair_addr(lo, pa_n, pb_n, sg_n);
-                    axn = src.load_coord(pa_n);
-                    bxn = src.load_coord(pb_n);
-                    if (lo + 1 < hi) src.pair_addr(lo + 1, pa_n, pb_n, sg_n);
-                }
 #pragma unroll 1
-                for (uint32_t i = lo; i < hi; ++i) {
-                    const Fq ax = axn, bx = bxn;
-                    if (i + 1 < hi) {
-                        axn = src.load_coord(pa_n);
-                        bxn = src.load_coord(pb_n);
-                        if (i + 2 < hi) src.pair_addr(i + 2, pa_n, pb_n, sg_n);
+                for (uint32_t q = 0; q < Q; ++q) {
+                    const BaTask tk = s_task[q][t];
+                    const uint32_t m = (tk.m0 + (1u << level) - 1u) >> level, pairs = m >> 1;
+                    const uint32_t lo = min(cb, pairs), hi = min(cb + K, pairs);
+                    BaSource src;
+                    src.make(tk, level, tk.z == 0 ? points0 : points1, region_a, region_b, region_a_stride, region_b_stride, W);
+                    uint8_t* pq = pref + (size_t)q * K * 1024;
+                    const uint8_t *pa = nullptr, *pb = nullptr;
+                    uint32_t sg = 0, e0 = 0, e1 = 0;
+                    Fq axn = fp_zero<FQ>(), bxn = fp_zero<FQ>();
+                    if (lo < hi) {
+                        src.pair_ref(lo, e0, e1);
+                        src.pair_addr(lo, e0, e1, pa, pb, sg);
+                        axn = src.load_coord(pa);
+                        bxn = src.load_coord(pb);
+                        if (lo + 1 < hi) src.pair_ref(lo + 1, e0, e1);
                     }
-                    Fq d = fp_sub(bx, ax);
-                    if (fp_is_zero(ax) || fp_is_zero(bx) || fp_is_zero(d)) {   // rare: identity operand, equal or opposite points
-                        const G1Affine a = src.get(2 * i), b = src.get(2 * i + 1);
-                        if (ba_classify(a, b, d) > 1) continue;
-                    }
-                    fp_store<FQ>(pref + (size_t)(i - lo) * SNARKV_BA_THREADS * 32, run);
-                    run = fp_mul(run, d);
-                }
-                tree[SNARKV_BA_THREADS + t] = run;
-                ba_block_invert(tree, t, (batch_no & 3u) * 32u);
-                Fq acc = tree[SNARKV_BA_THREADS + t];
-                // backward: 1 / d_i = acc * prefix_i, acc *= d_i; then the chord / tangent formula.  All five operands of a pair
-                // are requested at the top of its iteration and the prefix (L2-resident slab) is consumed first, so that the
-                // multiplication acc * prefix_i runs while the gathered coordinates are still in flight.
-                if (lo < hi) src.pair_addr(hi - 1, pa_n, pb_n, sg_n);
 #pragma unroll 1
-                for (uint32_t i = hi; i-- > lo;) {
-                    const Fq pf = fq_load_rw(pref + (size_t)(i - lo) * SNARKV_BA_THREADS * 32);
-                    G1Affine a, b;
-                    a.x = src.load_coord(pa_n); a.y = src.load_coord(pa_n + 32);
-                    b.x = src.load_coord(pb_n); b.y = src.load_coord(pb_n + 32);
-                    const uint32_t sg = sg_n;
-                    if (i > lo) src.pair_addr(i - 1, pa_n, pb_n, sg_n);
-                    const Fq inv = fp_mul(acc, pf);          // unused (and pf undefined) for pairs that need no division
-                    a.y = fq_cneg(a.y, sg & 1u);
-                    b.y = fq_cneg(b.y, sg >> 1);
-                    Fq d;
-                    const int kind = ba_classify(a, b, d);
-                    G1Affine o;
-                    if (kind <= 1) {
-                        acc = fp_mul(acc, d);
-                        Fq num;
-                        if (kind == 0) num = fp_sub(b.y, a.y);
-                        else {
-                            const Fq xx = fp_sqr(a.x);
-                            num = fp_add(fp_dbl(xx), xx);
+                    for (uint32_t i = lo; i < hi; ++i) {
+                        const Fq ax = axn, bx = bxn;
+                        if (i + 1 < hi) {
+                            src.pair_addr(i + 1, e0, e1, pa, pb, sg);
+                            axn = src.load_coord(pa);
+                            bxn = src.load_coord(pb);
+                            if (i + 2 < hi) src.pair_ref(i + 2, e0, e1);
                         }
-                        const Fq lam = fp_mul(num, inv);
-                        o.x = fp_sub(fp_sub(fp_sqr(lam), a.x), b.x);
-                        o.y = fp_sub(fp_mul(lam, fp_sub(a.x, o.x)), a.y);
-                    } else if (kind == 2) o = b;
-                    else if (kind == 3) o = a;
-                    else { o.x = fp_zero<FQ>(); o.y = fp_zero<FQ>(); }
-                    g1_affine_store(dst, i, o);
+                        Fq d = fp_sub(bx, ax);
+                        if (fp_is_zero(ax) || fp_is_zero(bx) || fp_is_zero(d)) {   // rare: identity operand, equal or opposite points
+                            const G1Affine a = src.get(2 * i), b = src.get(2 * i + 1);
+                            if (ba_classify(a, b, d) > 1) continue;
+                        }
+                        fp_store<FQ>(pq + (size_t)(i - lo) * 1024, run);
+                        run = fq_mul_call(run, d);
+                    }
+                }
+                Fq acc = ba_warp_invert(run, lane);
+                // backward: 1 / d_i = acc * prefix_i, acc *= d_i; then the chord / tangent formula.  The four coordinates of a pair
+                // are requested at the top of its iteration, its prefix and its sorted references one iteration earlier, so that
+                // the multiplication acc * prefix_i runs while the gathered coordinates are still in flight.
+#pragma unroll 1
+                for (uint32_t q = Q; q-- > 0;) {
+                    const BaTask tk = s_task[q][t];
+                    const uint32_t m = (tk.m0 + (1u << level) - 1u) >> level, pairs = m >> 1;
+                    const uint32_t lo = min(cb, pairs), hi = min(cb + K, pairs);
+                    BaSource src;
+                    src.make(tk, level, tk.z == 0 ? points0 : points1, region_a, region_b, region_a_stride, region_b_stride, W);
+                    uint8_t* dst = src.dest(tk, level, region_a, region_b, region_a_stride, region_b_stride, W);
+                    const uint8_t* pq = pref + (size_t)q * K * 1024;
+                    const uint8_t *pa = nullptr, *pb = nullptr;
+                    uint32_t sg = 0, e0 = 0, e1 = 0;
+                    Fq pfn = fp_zero<FQ>();
+                    if (lo < hi) {
+                        src.pair_ref(hi - 1, e0, e1);
+                        pfn = fq_load_rw(pq + (size_t)(hi - 1 - lo) * 1024);
+                    }
+#pragma unroll 1
+                    for (uint32_t i = hi; i-- > lo;) {
+                        const Fq pf = pfn;
+                        src.pair_addr(i, e0, e1, pa, pb, sg);
+                        G1Affine a, b;
+                        a.x = src.load_coord(pa); a.y = src.load_coord(pa + 32);
+                        b.x = src.load_coord(pb); b.y = src.load_coord(pb + 32);
+                        if (i > lo) {
+                            src.pair_ref(i - 1, e0, e1);
+                            pfn = fq_load_rw(pq + (size_t)(i - 1 - lo) * 1024);
+                        }
+                        const Fq inv = fq_mul_call(acc, pf);          // unused (and pf undefined) for pairs that need no division
+                        a.y = fq_cneg(a.y, sg & 1u);
+                        b.y = fq_cneg(b.y, sg >> 1);
+                        Fq d;
+                        const int kind = ba_classify(a, b, d);
+                        G1Affine o;
+                        if (kind <= 1) {
+                            acc = fq_mul_call(acc, d);
+                            Fq num;
+                            if (kind == 0) num = fp_sub(b.y, a.y);
+                            else {
+                                const Fq xx = fq_mul_call(a.x, a.x);
+                                num = fp_add(fp_dbl(xx), xx);
+                            }
+                            const Fq lam = fq_mul_call(num, inv);
+                            o.x = fp_sub(fp_sub(fq_mul_call(lam, lam), a.x), b.x);
+                            o.y = fp_sub(fq_mul_call(lam, fp_sub(a.x, o.x)), a.y);
+                        } else if (kind == 2) o = b;
+                        else if (kind == 3) o = a;
+                        else { o.x = fp_zero<FQ>(); o.y = fp_zero<FQ>(); }
+                        g1_affine_store(dst, i, o);
+                    }
                 }
             }
-            if (m & 1u) g1_affine_store(dst, pairs, src.get(m - 1));
-            if (active) { src.refs = false; src.region = dst; }
-            m = pairs + (m & 1u);
-            mmax = (mmax >> 1) + (mmax & 1u);
-            ++level;
+            // an odd item out moves up unchanged
+            for (uint32_t q = 0; q < Q; ++q) {
+                const BaTask tk = s_task[q][t];
+                const uint32_t m = (tk.m0 + (1u << level) - 1u) >> level;
+                if (m & 1u) {
+                    BaSource src;
+                    src.make(tk, level, tk.z == 0 ? points0 : points1, region_a, region_b, region_a_stride, region_b_stride, W);
+                    g1_affine_store(src.dest(tk, level, region_a, region_b, region_a_stride, region_b_stride, W), m >> 1, src.get(m - 1));
+                }
+            }
         }
-        // tail: fold what is left with the XYZZ mixed addition (k_bucket_accumulate's loop) and emit the task result
-        if (active) {
+        // tail: fold what is left with the XYZZ mixed addition (k_bucket_accumulate's loop) and emit the task results
+#pragma unroll 1
+        for (uint32_t q = 0; q < Q; ++q) {
+            const BaTask tk = s_task[q][t];
+            if (tk.m0 == 0) continue;
+            const uint32_t m = (tk.m0 + (1u << level) - 1u) >> level;
+            BaSource src;
+            src.make(tk, level, tk.z == 0 ? points0 : points1, region_a, region_b, region_a_stride, region_b_stride, W);
             G1Xyzz acc = xyzz_identity();
 #pragma unroll 1
             for (uint32_t k = 0; k < m; ++k) {
                 const G1Affine cur = src.get(k);
                 if (g1_affine_is_identity(cur)) continue;
-                xyzz_madd(acc, cur.x, cur.y);
+                ba_xyzz_madd(acc, cur.x, cur.y);
             }
-            xyzz_store(task_out + (size_t)z * W * cap * 128, (size_t)w * cap + slot, acc);
+            xyzz_store(task_out + (size_t)tk.z * W * cap * 128, (size_t)tk.w * cap + tk.slot, acc);
         }
+        __syncwarp();
     }
 }
 
@@ -283,7 +421,7 @@ __global__ void __launch_bounds__(128) k_compare_task_results(const uint8_t* __r
     const G1Xyzz p = xyzz_load(a, idx), q = xyzz_load(b, idx);
     bool same;
     if (xyzz_is_identity(p) || xyzz_is_identity(q)) same = xyzz_is_identity(p) && xyzz_is_identity(q);
-    else same = fp_eq(fp_mul(p.x, q.zz), fp_mul(q.x, p.zz)) && fp_eq(fp_mul(p.y, q.zzz), fp_mul(q.y, p.zzz));
+    else same = fp_eq(fq_mul_call(p.x, q.zz), fq_mul_call(q.x, p.zz)) && fp_eq(fq_mul_call(p.y, q.zzz), fq_mul_call(q.y, p.zzz));
     if (!same) {
         const uint32_t k = atomicAdd(&mismatch[0], 1u);
         if (k == 0) { mismatch[1] = w; mismatch[2] = slot; mismatch[3] = z; }

@@ -60,6 +60,7 @@ int snarkv_init(int device, snarkv_ctx** out) {
     };
     c->ba_k = env_int("SNARKV_BA_K", 1, 64, c->ba_k);
     c->ba_pairs_min = env_int("SNARKV_BA_PAIRS_MIN", 1, 1 << 20, c->ba_pairs_min);
+    c->ba_q = env_int("SNARKV_BA_Q", 1, 4, c->ba_q);
     *out = c;
     return SNARKV_OK;
 }

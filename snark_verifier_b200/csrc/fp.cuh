@@ -169,7 +169,7 @@ template <Field F> __device__ __noinline__ Fp<F> fp_inv_serial(const Fp<F>& a) {
     U256 x, p;
 #pragma unroll
     for (int i = 0; i < 8; ++i) { x.v[i] = a.v[i]; p.v[i] = fp_mod_limb<F>(i); }
-    U256 y = u256_inv_mod(x, p);
+    U256 y = u256_inv_mod_fast(x, p);   // fp_inv.cuh: 31 binary-GCD steps at a time (the bit-at-a-time u256_inv_mod gives the same value)
     Fp<F> t;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t.v[i] = y.v[i];

@@ -676,19 +676,19 @@ static int msm_accumulate_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* 
             ctx->ba_blocks_per_sm = per_sm > 0 ? per_sm : 1;
         }
         const size_t stride_a = (nv + pl.cap) / 2 + 2, stride_b = (stride_a + pl.cap) / 2 + 2;
-        const uint32_t groups = ((pl.cap + SNARKV_BA_THREADS - 1) / SNARKV_BA_THREADS) * pl.W * (uint32_t)B;
+        const uint32_t units = ((pl.cap + 31) / 32) * pl.W * (uint32_t)B;   // 32 tasks each; one warp takes up to Q at a time
         uint32_t blocks = (uint32_t)(ctx->sm_count * ctx->ba_blocks_per_sm);
-        if (blocks > groups) blocks = groups;
+        if (blocks > (units + 3) / 4) blocks = (units + 3) / 4;
         uint8_t* reg_a = (uint8_t*)ctx->wsget(WS_BA_REGION_A, (size_t)B * pl.W * stride_a * 64);
         uint8_t* reg_b = (uint8_t*)ctx->wsget(WS_BA_REGION_B, (size_t)B * pl.W * stride_b * 64);
-        uint8_t* slab = (uint8_t*)ctx->wsget(WS_BA_PREFIX, (size_t)ctx->sm_count * ctx->ba_blocks_per_sm * SNARKV_BA_K_MAX * SNARKV_BA_THREADS * 32);
+        uint8_t* slab = (uint8_t*)ctx->wsget(WS_BA_PREFIX, (size_t)ctx->sm_count * ctx->ba_blocks_per_sm * SNARKV_BA_Q_MAX * SNARKV_BA_K_MAX * SNARKV_BA_THREADS * 32);
         uint32_t* ctr = (uint32_t*)ctx->wsget(WS_BA_COUNTER, 32);
         if (!reg_a || !reg_b || !slab || !ctr) return SNARKV_ERR_CUDA;
         SNARKV_CUDA_TRY(ctx, cudaMemsetAsync(ctr, 0, 32, st));
         k_bucket_accumulate_affine<<<blocks, SNARKV_BA_THREADS, 0, st>>>(pts[0], pts[1], wk.sorted, wk.offsets, wk.counts, wk.tasks, wk.window_tasks,
                                                                         wk.order, nv, pl.NB, pl.T, pl.cap, pl.W, (uint32_t)B, wk.task_out, reg_a,
                                                                         reg_b, stride_a, stride_b, slab, ctr, (uint32_t)ctx->ba_k,
-                                                                        (uint32_t)ctx->ba_pairs_min);
+                                                                        (uint32_t)ctx->ba_pairs_min, (uint32_t)ctx->ba_q);
         SNARKV_LAUNCH_CHECK(ctx, "k_bucket_accumulate_affine");
         sg.launched();
         if (mode == 3) {   // debugging aid: both kernels ran; compare every task result as a group element (synchronous)

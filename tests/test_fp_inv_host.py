@@ -17,20 +17,24 @@ def test_binary_gcd_inverse_matches_python(tmp_path):
     src = tmp_path / "t.cpp"
     src.write_text('#include "fp_inv.cuh"\n#include <cstring>\nusing namespace snarkv;\n'
                    'extern "C" void inv_mod(const uint32_t* a, const uint32_t* p, uint32_t* out) {\n'
-                   '  U256 x, m; memcpy(x.v, a, 32); memcpy(m.v, p, 32); U256 r = u256_inv_mod(x, m); memcpy(out, r.v, 32); }\n')
+                   '  U256 x, m; memcpy(x.v, a, 32); memcpy(m.v, p, 32); U256 r = u256_inv_mod(x, m); memcpy(out, r.v, 32); }\n'
+                   'extern "C" void inv_mod_fast(const uint32_t* a, const uint32_t* p, uint32_t* out) {\n'
+                   '  U256 x, m; memcpy(x.v, a, 32); memcpy(m.v, p, 32); U256 r = u256_inv_mod_fast(x, m); memcpy(out, r.v, 32); }\n')
     so = tmp_path / "libt.so"
     subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-I", CSRC, "-o", str(so), str(src)])
     lib = ctypes.CDLL(str(so))
     rnd = random.Random(11)
     for mod in (P, R):
         cases = [1, 2, 3, mod - 1, mod - 2, (mod + 1) // 2, 1 << 253] + [rnd.randrange(1, mod) for _ in range(500)]
-        for a in cases:
+        cases += [1 << k for k in range(1, 254)] + [mod - (1 << k) for k in range(1, 253)] + [rnd.randrange(1, 1 << 64) for _ in range(100)]
+        for fn in (lib.inv_mod, lib.inv_mod_fast):      # bit-at-a-time loop and the 31-steps-at-a-time variant (Pornin)
+            for a in cases:
+                out = ctypes.create_string_buffer(32)
+                fn(a.to_bytes(32, "little"), mod.to_bytes(32, "little"), out)
+                assert int.from_bytes(out.raw, "little") == pow(a, -1, mod)
             out = ctypes.create_string_buffer(32)
-            lib.inv_mod(a.to_bytes(32, "little"), mod.to_bytes(32, "little"), out)
-            assert int.from_bytes(out.raw, "little") == pow(a, -1, mod)
-        out = ctypes.create_string_buffer(32)
-        lib.inv_mod(bytes(32), mod.to_bytes(32, "little"), out)
-        assert out.raw == bytes(32)          # inverse of zero is zero (halo2curves' CtOption::None is handled by callers)
+            fn(bytes(32), mod.to_bytes(32, "little"), out)
+            assert out.raw == bytes(32)          # inverse of zero is zero (halo2curves' CtOption::None is handled by callers)
 
 
 def test_generated_ptx_blocks_pass_cpu_emulation():
