@@ -2,30 +2,29 @@
 // snark-verifier/src/util/msm.rs:291-296 as k_bucket_accumulate (msm.cu), with 6 instead of 10 Montgomery multiplications
 // per point addition.
 //
-// A task is a run of <= T sorted point references of one bucket (msm.cu K2b).  One thread owns a task and reduces its list as a
+// A task is a run of <= T sorted point references of one bucket (msm.cu K2b).  One LANE owns a task and reduces its list as a
 // binary tree, level by level: level l turns m items into ceil(m / 2) by adding neighbours (2i, 2i + 1) in AFFINE coordinates,
 //     lambda = (y2 - y1) / (x2 - x1),  x3 = lambda^2 - x1 - x2,  y3 = lambda (x1 - x3) - y1,
-// where the division is shared: the 128 threads of a block each run K pair-additions per batch, multiply their K denominators
-// into a running product (exclusive prefixes parked in an L2-resident slab), the 128 thread products are combined in a
-// shared-memory product tree, ONE field inversion is done per batch (<= 128 K additions), and the inverse is distributed back
-// down the tree and along every thread's prefixes (Montgomery's trick): 3 multiplications per denominator + 3 for the formula.
-// Levels alternate between two scratch regions owned by the task (positions derived arithmetically from the task's place in
-// the sorted array, no extra scan).  When fewer than PAIRS_MIN pairs per thread remain, the rest of the list is folded with the
-// XYZZ mixed addition exactly like k_bucket_accumulate and the task result is written in the same place and format, so every
-// later kernel of the pipeline is unchanged.
+// where the division is shared (Montgomery's trick): in one batch every lane walks up to K pairs of each of its Q tasks, multiplies
+// the denominators into a running product (exclusive prefixes parked in a per-warp slab, 1 KB rows = one entry per lane), the 32
+// lane products are combined by shuffle scans, ONE field inversion is done per warp and batch (<= 32 Q K additions), and the
+// inverse is distributed back along every lane's prefixes: 3 multiplications per denominator + 3 for the formula.
+// Warps are independent (no block barrier): while one lane of a warp runs the inversion — integer-ALU work — the other warps of
+// the scheduler keep the multiplier busy.  Levels alternate between two scratch regions owned by the task (positions derived
+// arithmetically from the task's place in the sorted array, no extra scan).  When fewer than PAIRS_MIN pairs per list remain, the
+// rest is folded with the XYZZ mixed addition exactly like k_bucket_accumulate and the task result is written in the same place
+// and format, so every later kernel of the pipeline is unchanged.
 //
-// Exceptional pairs are exact: P + identity, P + P (tangent slope, denominator 2 y), P + (-P) = identity; such pairs that need
-// no division do not enter the product.  All control flow that reaches a __syncthreads is block-uniform (derived from the
-// block-wide maximum list length).
+// Exceptional pairs are exact: P + identity, P + P (tangent slope, denominator 2 y), P + (-P) = identity; pairs that need no
+// division do not enter the product.  Everything that reaches a shuffle is warp-uniform (derived from the warp-wide maximum
+// list length).  Tuning (K, PAIRS_MIN, Q, resident blocks) is in snarkv_ctx (ctx.hpp); measured sweeps: profiles/r01_ba_*.txt.
 #pragma once
 #include "g1.cuh"
 
 namespace snarkv {
 
 #define SNARKV_BA_THREADS 128
-#define SNARKV_BA_K_MAX 64      // largest batch: pair-additions per thread per shared inversion (sizes the prefix slab)
-#define SNARKV_BA_K 32          // default batch
-#define SNARKV_BA_PAIRS_MIN 12  // default: run another affine level while the longest list of the block still has this many pairs
+#define SNARKV_BA_K_MAX 128     // largest K: pairs of one list per batch (with SNARKV_BA_Q_MAX it sizes the prefix slab)
 
 
 // ONE copy of the Montgomery multiplication for this kernel (a call costs ~12 register moves on top of ~170 instructions): its
@@ -115,16 +114,6 @@ struct BaSource {
     // one coordinate (32 B): the caller's array goes through the read-only path, this kernel's scratch through coherent loads
     __device__ __forceinline__ Fq load_coord(const uint8_t* p) const { return refs ? fp_load<FQ>(p) : fq_load_rw(p); }
 };
-
-// branch-free conditional negation (the point loads of a pair stay back to back instead of being split by a branch)
-__device__ __forceinline__ Fq fq_cneg(const Fq& y, uint32_t neg) {
-    const Fq ny = fp_neg(y);
-    const uint32_t mask = 0u - neg;
-    Fq r;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) r.v[k] = (ny.v[k] & mask) | (y.v[k] & ~mask);
-    return r;
-}
 
 // kind of a pair addition a + b: 0 = chord (d = x2 - x1), 1 = tangent (d = 2 y1), 2 = a is the identity (result b),
 // 3 = b is the identity (result a), 4 = result is the identity.  Only kinds 0 and 1 need 1 / d.
@@ -217,7 +206,8 @@ __device__ __forceinline__ uint8_t* BaSource::dest(const BaTask& tk, uint32_t le
 // gi = u / (W Z), then base set z and window w, so that the longest tasks of all windows come first); a warp takes Q units at a
 // time (fewer near the end of the queue, for balance) and runs their 32 Q lists level by level, one shared inversion per batch
 // of up to K pairs of each list.
-__global__ void __launch_bounds__(SNARKV_BA_THREADS, 4)
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(SNARKV_BA_THREADS, MIN_BLOCKS)
 k_bucket_accumulate_affine(const uint8_t* __restrict__ points0, const uint8_t* __restrict__ points1, const uint32_t* __restrict__ sorted,
                            const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts, const uint2* __restrict__ tasks,
                            const uint32_t* __restrict__ window_tasks, const uint32_t* __restrict__ order, size_t n, uint32_t NB,
@@ -232,7 +222,7 @@ k_bucket_accumulate_affine(const uint8_t* __restrict__ points0, const uint8_t* _
     for (uint32_t w = lane; w < W; w += 32) wt_max = max(wt_max, window_tasks[w]);
     wt_max = __reduce_max_sync(0xffffffffu, wt_max);
     const uint32_t total_units = ((wt_max + 31u) >> 5) * W * Z;
-    uint8_t* pref = prefix_slab + ((size_t)warp_global * SNARKV_BA_Q_MAX * SNARKV_BA_K_MAX * 32 + lane) * 32;
+    uint8_t* pref = prefix_slab + ((size_t)warp_global * Qmax * K * 32 + lane) * 32;   // Qmax K rows of 32 lanes x 32 B
     for (;;) {
         // take Q units: Qmax while the queue holds that many per warp, fewer in the last round (balance)
         uint32_t u0 = 0, Q = 0;
@@ -319,7 +309,7 @@ k_bucket_accumulate_affine(const uint8_t* __restrict__ points0, const uint8_t* _
                             if (ba_classify(a, b, d) > 1) continue;
                         }
                         fp_store<FQ>(pq + (size_t)(i - lo) * 1024, run);
-                        run = fq_mul_call(run, d);
+                        run = fp_mul(run, d);   // inlined: a call would first wait for the loads of pair i + 1 issued above
                     }
                 }
                 Fq acc = ba_warp_invert(run, lane);
@@ -353,9 +343,11 @@ k_bucket_accumulate_affine(const uint8_t* __restrict__ points0, const uint8_t* _
                             src.pair_ref(i - 1, e0, e1);
                             pfn = fq_load_rw(pq + (size_t)(i - 1 - lo) * 1024);
                         }
-                        const Fq inv = fq_mul_call(acc, pf);          // unused (and pf undefined) for pairs that need no division
-                        a.y = fq_cneg(a.y, sg & 1u);
-                        b.y = fq_cneg(b.y, sg >> 1);
+                        // inlined (a call would first wait for the coordinate loads issued above); unused, and pf undefined, for
+                        // pairs that need no division
+                        const Fq inv = fp_mul(acc, pf);
+                        if (sg & 1u) a.y = fp_neg(a.y);   // level 0 only (the loads above are already in flight)
+                        if (sg >> 1) b.y = fp_neg(b.y);
                         Fq d;
                         const int kind = ba_classify(a, b, d);
                         G1Affine o;

@@ -652,9 +652,13 @@ static int msm_accumulate_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* 
             if (cz) pts[z] = cz;
         }
     }
-    // accumulate mode: batched affine pays once the lists are long enough for a few full pair levels (mean bucket load >= 64)
+    // accumulate mode.  Batched affine (6 instead of 10 multiplications per addition, but one inversion per batch, prefix traffic
+    // and whole 32-task units of work per warp) pays once the bucket lists are long and there are enough of them to keep every
+    // warp busy for several rounds — measured on B200 (tools/accumulate_probe.py): mean load 256 at 2^22 terms 10.5 vs 11.3 ms,
+    // 128 at 2^23 18.3 vs 20.6 ms, 256 at 2^24 33.9 vs 41.2 ms; mean load 128 at 2^21 or 64 at 2^20 lose (6.1 vs 5.6, 3.4 vs 2.9 ms).
     const int mode = ctx->accumulate_mode;
-    const bool affine = mode >= 2 || (mode == 0 && nv / pl.NB >= 64);
+    const size_t mean_load = nv / pl.NB;
+    const bool affine = mode >= 2 || (mode == 0 && (mean_load >= 256 || (mean_load >= 128 && nbk >= ((size_t)1 << 19))));
     if (!affine || mode == 3) {
         Stage sg(ctx, "msm_bucket_accumulate");
         uint8_t* dst = wk.task_out;
@@ -670,9 +674,11 @@ static int msm_accumulate_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* 
     }
     if (affine) {
         Stage sg(ctx, "msm_bucket_accumulate_affine");
+        auto kernel = ctx->ba_min_blocks >= 6 ? k_bucket_accumulate_affine<6>
+                      : ctx->ba_min_blocks == 5 ? k_bucket_accumulate_affine<5> : k_bucket_accumulate_affine<4>;
         if (ctx->ba_blocks_per_sm == 0) {
             int per_sm = 0;
-            SNARKV_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bucket_accumulate_affine, SNARKV_BA_THREADS, 0));
+            SNARKV_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SNARKV_BA_THREADS, 0));
             ctx->ba_blocks_per_sm = per_sm > 0 ? per_sm : 1;
         }
         const size_t stride_a = (nv + pl.cap) / 2 + 2, stride_b = (stride_a + pl.cap) / 2 + 2;
@@ -681,11 +687,11 @@ static int msm_accumulate_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* 
         if (blocks > (units + 3) / 4) blocks = (units + 3) / 4;
         uint8_t* reg_a = (uint8_t*)ctx->wsget(WS_BA_REGION_A, (size_t)B * pl.W * stride_a * 64);
         uint8_t* reg_b = (uint8_t*)ctx->wsget(WS_BA_REGION_B, (size_t)B * pl.W * stride_b * 64);
-        uint8_t* slab = (uint8_t*)ctx->wsget(WS_BA_PREFIX, (size_t)ctx->sm_count * ctx->ba_blocks_per_sm * SNARKV_BA_Q_MAX * SNARKV_BA_K_MAX * SNARKV_BA_THREADS * 32);
+        uint8_t* slab = (uint8_t*)ctx->wsget(WS_BA_PREFIX, (size_t)ctx->sm_count * ctx->ba_blocks_per_sm * ctx->ba_q * ctx->ba_k * SNARKV_BA_THREADS * 32);
         uint32_t* ctr = (uint32_t*)ctx->wsget(WS_BA_COUNTER, 32);
         if (!reg_a || !reg_b || !slab || !ctr) return SNARKV_ERR_CUDA;
         SNARKV_CUDA_TRY(ctx, cudaMemsetAsync(ctr, 0, 32, st));
-        k_bucket_accumulate_affine<<<blocks, SNARKV_BA_THREADS, 0, st>>>(pts[0], pts[1], wk.sorted, wk.offsets, wk.counts, wk.tasks, wk.window_tasks,
+        kernel<<<blocks, SNARKV_BA_THREADS, 0, st>>>(pts[0], pts[1], wk.sorted, wk.offsets, wk.counts, wk.tasks, wk.window_tasks,
                                                                         wk.order, nv, pl.NB, pl.T, pl.cap, pl.W, (uint32_t)B, wk.task_out, reg_a,
                                                                         reg_b, stride_a, stride_b, slab, ctr, (uint32_t)ctx->ba_k,
                                                                         (uint32_t)ctx->ba_pairs_min, (uint32_t)ctx->ba_q);
