@@ -9,7 +9,7 @@ every rank folds them and normalises (util/msm.rs:333-335 + native.rs:70).  Tota
   value      whole-job throughput with operands already resident in HBM (CUDA events, max over ranks)
   e2e        the same job through the C-ABI host entry points with pinned HOST buffers: H2D of scalars+points and D2H of the
              result inside the timed region
-  roofline   dominant kernel (msm_bucket_accumulate): algorithmic bytes (96 B/term) / its live CUDA-event duration vs the
+  roofline   dominant kernel (msm_bucket_accumulate[_affine]): algorithmic bytes (96 B/term) / its live CUDA-event duration vs the
              measured HBM peak — plus the integer-pipe view, because this kernel is IMAD-bound, not HBM-bound
   cpu_baseline / --impl reference
              the oracle's restatement of the reference's chunk-parallel Pippenger (util/msm.rs:308-343) on all host cores,
@@ -30,6 +30,7 @@ LOG_N_DEFAULT = 24
 SEED = 2024
 ALG_BYTES_PER_TERM = 96            # 64 B affine point + 32 B scalar, each read once
 MADD_MULMODS = 10                  # XYZZ mixed addition: 8M + 2S (csrc/g1.cuh)
+AFFINE_MULMODS = 6                 # batched-affine addition: 3 for the shared inversion + 1M + 1S + 1M (csrc/bucket_affine.cuh)
 IMAD_PER_MULMOD = 170              # IMAD-pipe instructions per Montgomery multiplication (cuobjdump: 150 IMAD.WIDE + 20 IMAD)
 
 
@@ -336,7 +337,12 @@ def main():
                 a[0] += ms; a[1] += k
     L.profile(False)
     stages = {k: v[0] / args.steps for k, v in stage_acc.items()}
-    acc_ms = stages.get("msm_bucket_accumulate", float("nan"))
+    # the dominant kernel is whichever bucket-accumulation kernel the library chose for this size (batched affine for long
+    # bucket lists, XYZZ otherwise — msm.cu msm_accumulate_phase)
+    if "msm_bucket_accumulate_affine" in stages:
+        acc_kernel, acc_ms, acc_mulmods = "k_bucket_accumulate_affine", stages["msm_bucket_accumulate_affine"], AFFINE_MULMODS
+    else:
+        acc_kernel, acc_ms, acc_mulmods = "k_bucket_accumulate", stages.get("msm_bucket_accumulate", float("nan")), MADD_MULMODS
 
     # ---- end to end: pinned host buffers through the C-ABI host entry points ------------------------------------------
     h_s = torch.empty(n_local * 32, dtype=torch.uint8).pin_memory()
@@ -382,8 +388,8 @@ def main():
         achieved = alg_bytes / (acc_ms / 1e3) / 1e9
         plan = L.msm_plan(n_local)
         c_bits, windows = plan["window_bits"], plan["windows"]
-        cap = ncu_capture("k_bucket_accumulate", args.log_n if world == 1 else -1, c_bits)
-        mulmods_per_s = n_local * windows * MADD_MULMODS / (acc_ms / 1e3)
+        cap = ncu_capture(acc_kernel, args.log_n if world == 1 else -1, c_bits)
+        mulmods_per_s = n_local * windows * acc_mulmods / (acc_ms / 1e3)
         line = {
             "metric": "BN254 G1 MSM throughput", "value": value, "unit": "Mscalar-mults/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong",
@@ -398,12 +404,13 @@ def main():
                     "api": "snarkv_g1_msm (N=1) / snarkv_g1_msm_partial + all_gather + fold (N>1), pinned host buffers",
                     "result_matches_device_path": res_e2e == res_dev},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "k_bucket_accumulate", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+            "roofline": {"kernel": acc_kernel, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": cap["dram_bytes_per_launch"] if cap else None,
                          "peak_source": peak_src, "kernel_ms": acc_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                         "note": "this kernel is bound by the integer multiplier (FMA-heavy pipe), not by HBM: %d mixed additions x 10 "
-                                 "Montgomery multiplications x ~%d IMAD per term; 'traffic' is each 64-byte point gathered once per window"
-                                 % (windows, IMAD_PER_MULMOD),
+                         "note": "this kernel is bound by the integer multiplier (FMA-heavy pipe), not by HBM: %d point additions x %d "
+                                 "Montgomery multiplications x ~%d IMAD per term; 'traffic' is each 64-byte point gathered once per window "
+                                 "(plus, for the batched-affine kernel, the intermediate tree levels and the inversion prefixes)"
+                                 % (windows, acc_mulmods, IMAD_PER_MULMOD),
                          "alu": {"mulmods_per_s": mulmods_per_s,
                                  "fmaheavy_pipe_pct_of_peak_ncu": cap["fmaheavy_pct"] if cap else None,
                                  "source": cap["source"] if cap else "no ncu capture for this configuration"}},

@@ -17,7 +17,11 @@
 //
 // Exceptional pairs are exact: P + identity, P + P (tangent slope, denominator 2 y), P + (-P) = identity; pairs that need no
 // division do not enter the product.  Everything that reaches a shuffle is warp-uniform (derived from the warp-wide maximum
-// list length).  Tuning (K, PAIRS_MIN, Q, resident blocks) is in snarkv_ctx (ctx.hpp); measured sweeps: profiles/r01_ba_*.txt.
+// list length).  Tuning (K, PAIRS_MIN, Q) is in snarkv_ctx (ctx.hpp); measured sweeps: profiles/r01_ba_*.txt.
+//
+// The kernel is co-limited: 79 % of the integer-multiplier pipe and 3.5 TB/s of DRAM traffic (gathers, tree levels, prefixes) at
+// 2^24 terms (profiles/r01_ncu_bucket_accumulate_affine_2p24.txt).  Measured and rejected: prefetch.global.L2 of the next pair's
+// operands (adds traffic: 34.3 -> 35.3 .. 37.4 ms), 5 or 6 resident blocks per SM (spills), K < 64 (more inversions).
 #pragma once
 #include "g1.cuh"
 
@@ -206,8 +210,7 @@ __device__ __forceinline__ uint8_t* BaSource::dest(const BaTask& tk, uint32_t le
 // gi = u / (W Z), then base set z and window w, so that the longest tasks of all windows come first); a warp takes Q units at a
 // time (fewer near the end of the queue, for balance) and runs their 32 Q lists level by level, one shared inversion per batch
 // of up to K pairs of each list.
-template <int MIN_BLOCKS>
-__global__ void __launch_bounds__(SNARKV_BA_THREADS, MIN_BLOCKS)
+__global__ void __launch_bounds__(SNARKV_BA_THREADS, 4)
 k_bucket_accumulate_affine(const uint8_t* __restrict__ points0, const uint8_t* __restrict__ points1, const uint32_t* __restrict__ sorted,
                            const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts, const uint2* __restrict__ tasks,
                            const uint32_t* __restrict__ window_tasks, const uint32_t* __restrict__ order, size_t n, uint32_t NB,

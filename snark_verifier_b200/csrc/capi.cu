@@ -61,7 +61,7 @@ int snarkv_init(int device, snarkv_ctx** out) {
     c->ba_k = env_int("SNARKV_BA_K", 1, 128, c->ba_k);
     c->ba_pairs_min = env_int("SNARKV_BA_PAIRS_MIN", 1, 1 << 20, c->ba_pairs_min);
     c->ba_q = env_int("SNARKV_BA_Q", 1, 4, c->ba_q);
-    c->ba_min_blocks = env_int("SNARKV_BA_BLOCKS", 4, 6, c->ba_min_blocks);
+    c->ba_min_load = env_int("SNARKV_BA_MIN_LOAD", 1, 1 << 20, c->ba_min_load);
     *out = c;
     return SNARKV_OK;
 }

@@ -656,9 +656,11 @@ static int msm_accumulate_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* 
     // and whole 32-task units of work per warp) pays once the bucket lists are long and there are enough of them to keep every
     // warp busy for several rounds — measured on B200 (tools/accumulate_probe.py): mean load 256 at 2^22 terms 10.5 vs 11.3 ms,
     // 128 at 2^23 18.3 vs 20.6 ms, 256 at 2^24 33.9 vs 41.2 ms; mean load 128 at 2^21 or 64 at 2^20 lose (6.1 vs 5.6, 3.4 vs 2.9 ms).
+    // With >= 2^19 buckets (c = 17, or c = 16 without GLV: the term-chunks of the host entry point) it wins from a mean load of
+    // ~48 on (64 at 2^22 terms, c = 17: 10.5 vs 11.8 ms; e2e 2^24 from host memory 53.1 -> 51.5 ms).
     const int mode = ctx->accumulate_mode;
     const size_t mean_load = nv / pl.NB;
-    const bool affine = mode >= 2 || (mode == 0 && (mean_load >= 256 || (mean_load >= 128 && nbk >= ((size_t)1 << 19))));
+    const bool affine = mode >= 2 || (mode == 0 && (mean_load >= 256 || (mean_load >= (size_t)ctx->ba_min_load && nbk >= ((size_t)1 << 19))));
     if (!affine || mode == 3) {
         Stage sg(ctx, "msm_bucket_accumulate");
         uint8_t* dst = wk.task_out;
@@ -674,8 +676,7 @@ static int msm_accumulate_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* 
     }
     if (affine) {
         Stage sg(ctx, "msm_bucket_accumulate_affine");
-        auto kernel = ctx->ba_min_blocks >= 6 ? k_bucket_accumulate_affine<6>
-                      : ctx->ba_min_blocks == 5 ? k_bucket_accumulate_affine<5> : k_bucket_accumulate_affine<4>;
+        auto kernel = k_bucket_accumulate_affine;
         if (ctx->ba_blocks_per_sm == 0) {
             int per_sm = 0;
             SNARKV_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SNARKV_BA_THREADS, 0));

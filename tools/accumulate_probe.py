@@ -1,6 +1,6 @@
 """Developer probe (not part of the bench contract): A/B of the bucket-accumulation kernels (accumulate mode 1 = XYZZ,
 2 = batched affine) with stage timings.
-usage: accumulate_probe.py [log2 sizes, comma separated] [window bits or 0] ["K,PAIRS_MIN,Q,BLOCKS;..."]
+usage: accumulate_probe.py [log2 sizes, comma separated] [window bits or 0] ["K,PAIRS_MIN,Q,MIN_LOAD;..."]
 The optional third argument sweeps the batched-affine tuning knobs (the library reads SNARKV_BA_* at snarkv_init)."""
 import os
 import sys
@@ -49,11 +49,11 @@ def run(L, n, mode):
 base = {}
 for k, cfg in enumerate(sweep):
     if cfg is not None:
-        os.environ["SNARKV_BA_K"], os.environ["SNARKV_BA_PAIRS_MIN"], os.environ["SNARKV_BA_Q"], os.environ["SNARKV_BA_BLOCKS"] = cfg
+        os.environ["SNARKV_BA_K"], os.environ["SNARKV_BA_PAIRS_MIN"], os.environ["SNARKV_BA_Q"], os.environ["SNARKV_BA_MIN_LOAD"] = cfg
         L.close()
         L = sv.CudaLoader(0)
         L.set_stream(stream.cuda_stream)
-        print("--- K,PAIRS_MIN,Q,BLOCKS = %s" % (cfg,), flush=True)
+        print("--- K,PAIRS_MIN,Q,MIN_LOAD = %s" % (cfg,), flush=True)
     L.set_window_bits(cbits)
     for lg in sizes:
         n = 1 << lg
