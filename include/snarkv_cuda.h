@@ -174,6 +174,27 @@ int snarkv_fr_mul_vec(snarkv_ctx* ctx, const uint8_t* a, const uint8_t* b, size_
 int snarkv_evm_transcript_challenges(snarkv_ctx* ctx, const uint8_t* streams, size_t stream_len, const uint32_t* seg_end, size_t k, size_t m,
                                      int format, uint8_t* challenges);
 
+/* ---- (next row f3) per-proof PLONK scalar evaluation for m proofs of one protocol -----------------------------------------
+ * Replaces verifier/plonk/protocol.rs:211-283 (CommonPolynomialEvaluation), :333-392 (Expression::evaluate) and
+ * verifier/plonk/proof.rs:298-349 (instance evaluations, quotient evaluation) for a batch: the protocol — hence the expression
+ * tree — is the same for every proof, so the host flattens it ONCE into a straight-line register program and one GPU thread per
+ * proof runs it.  Instruction (op, dst, a, b), registers hold Fr values:
+ *   INPUT dst <- inputs[proof][a]   CONST dst <- consts[a]   ADD/SUB/MUL dst <- reg[a] (op) reg[b]   NEG dst <- -reg[a]
+ *   INV   dst <- 1 / reg[a], a zero stays zero (ScalarLoader::batch_invert, loader.rs:255-262 / util/arithmetic.rs:47-74).
+ * `inputs`: m x n_inputs x 32 B, `consts`: n_consts x 32 B, `outputs`: m x n_out x 32 B (register out_regs[k] of every proof),
+ * all in `format`.  Every register must be written before it is read (checked); dst, a, b < n_regs. */
+enum { SNARKV_FR_OP_INPUT = 0, SNARKV_FR_OP_CONST = 1, SNARKV_FR_OP_ADD = 2, SNARKV_FR_OP_SUB = 3, SNARKV_FR_OP_MUL = 4,
+       SNARKV_FR_OP_NEG = 5, SNARKV_FR_OP_INV = 6 };
+typedef struct snarkv_fr_instr { uint32_t op, dst, a, b; } snarkv_fr_instr;
+int snarkv_fr_program_eval_batch(snarkv_ctx* ctx, const snarkv_fr_instr* program, size_t n_instr, uint32_t n_regs, const uint8_t* consts,
+                                 size_t n_consts, const uint8_t* inputs, size_t n_inputs, size_t m, const uint32_t* out_regs, size_t n_out,
+                                 int format, uint8_t* outputs);
+/* The same with inputs and outputs resident in device memory (program, consts and out_regs are still host arrays: they are small
+ * and validated on the host). */
+int snarkv_fr_program_eval_batch_device(snarkv_ctx* ctx, const snarkv_fr_instr* program, size_t n_instr, uint32_t n_regs,
+                                        const uint8_t* consts, size_t n_consts, const void* d_inputs, size_t n_inputs, size_t m,
+                                        const uint32_t* out_regs, size_t n_out, int format, void* d_outputs);
+
 /* ---- synthetic workload (bench / tests) ----------------------------------------------------------------------------------
  * Deterministic inputs (the test suite restates the same definition independently):
  *   scalar_i: 4 x splitmix64 limbs, top limb masked to 62 bits, one conditional subtraction of r;

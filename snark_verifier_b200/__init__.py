@@ -69,6 +69,8 @@ C_ABI = {
     "snarkv_fr_batch_invert": (_i, [_vp, _vp, _sz, _vp, _i]),
     "snarkv_fr_mul_vec": (_i, [_vp, _vp, _vp, _sz, _i, _vp]),
     "snarkv_evm_transcript_challenges": (_i, [_vp, _vp, _sz, _vp, _sz, _sz, _i, _vp]),
+    "snarkv_fr_program_eval_batch": (_i, [_vp, _vp, _sz, ctypes.c_uint32, _vp, _sz, _vp, _sz, _sz, _vp, _sz, _i, _vp]),
+    "snarkv_fr_program_eval_batch_device": (_i, [_vp, _vp, _sz, ctypes.c_uint32, _vp, _sz, _vp, _sz, _sz, _vp, _sz, _i, _vp]),
     "snarkv_kzg_accumulate": (_i, [_vp, _vp, _vp, _sz, _vp, _i, _vp, _vp]),
     "snarkv_kzg_set_deciding_key": (_i, [_vp, _vp, _vp, _vp]),
     "snarkv_kzg_decide_batch": (_i, [_vp, _vp, _vp, _sz, _i, _vp, _vp]),
@@ -274,6 +276,25 @@ class CudaLoader:
         self._check(self.lib.snarkv_evm_transcript_challenges(self.h, _addr(streams) if stream_len else None, stream_len,
                                                               ctypes.cast(se, ctypes.c_void_p), k, m, self.fmt, out), "evm_transcript")
         return out.raw
+
+    def fr_program_eval(self, program, inputs, m, d_inputs=None, d_outputs=None):
+        """Run a plonk_eval.Program for m proofs (protocol.rs:211-283, 333-392; proof.rs:298-349 for a batch).  `inputs`:
+        m * n_inputs * 32 bytes -> m * n_out * 32 bytes; with d_inputs / d_outputs (device pointers) nothing crosses PCIe but
+        the program."""
+        from .plonk_eval import pack_program
+        ins, consts, outs = pack_program(program)
+        if self.fmt == MONTGOMERY:   # constants travel in the loader's format like every other scalar
+            consts = b"".join(((c << 256) % R_MODULUS).to_bytes(32, "little") for c in program.consts)
+        n_out = len(program.outputs)
+        args = (ins.ctypes.data, ins.shape[0], program.n_regs, consts if consts else None, len(program.consts))
+        if d_inputs is not None:
+            self._check(self.lib.snarkv_fr_program_eval_batch_device(self.h, *args, _addr(d_inputs), program.n_inputs, m, outs.ctypes.data, n_out,
+                                                                     self.fmt, _addr(d_outputs)), "fr_program_eval")
+            return None
+        out = ctypes.create_string_buffer(max(32 * n_out * m, 1))
+        self._check(self.lib.snarkv_fr_program_eval_batch(self.h, *args, _addr(inputs) if program.n_inputs and m else None, program.n_inputs, m,
+                                                          outs.ctypes.data, n_out, self.fmt, out), "fr_program_eval")
+        return out.raw[: 32 * n_out * m]
 
     # -- synthetic workload ---------------------------------------------------------------------------------------
     def synth_scalars_device(self, seed, start, n, d_out):

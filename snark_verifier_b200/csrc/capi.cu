@@ -8,6 +8,7 @@
 
 #include <cstdlib>
 
+#include <vector>
 #include "ctx.hpp"
 
 using namespace snarkv;
@@ -401,6 +402,82 @@ int snarkv_fr_mul_vec(snarkv_ctx* ctx, const uint8_t* a, const uint8_t* b, size_
     int rc = fr_mul_vec_device(ctx, d_a, d_b, n, format, d_o);
     if (rc) return rc;
     SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(out, d_o, n * 32, cudaMemcpyDeviceToHost, st));
+    SNARKV_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return SNARKV_OK;
+}
+
+// ---- (f3) straight-line Fr program for a batch of proofs (protocol.rs:211-283, 333-392; proof.rs:298-349) -------------------------
+// The program is small and comes from the host compiler: validate it here (opcodes, register bounds, write-before-read), then stage
+// instructions | consts | out_regs in one device buffer.
+static int fr_program_stage(snarkv_ctx* ctx, const snarkv_fr_instr* program, size_t n_instr, uint32_t n_regs, const uint8_t* consts,
+                            size_t n_consts, size_t n_inputs, size_t m, const uint32_t* out_regs, size_t n_out, int format,
+                            uint8_t** d_prog, uint8_t** d_consts, uint8_t** d_out_regs) {
+    if (!program || n_instr == 0 || n_instr > (1u << 24) || n_regs == 0 || n_regs > (1u << 20) || !out_regs || n_out == 0 || bad_format(format) ||
+        (n_consts && !consts) || n_consts > (1u << 24) || n_inputs > (1u << 24) || m > ((size_t)1 << 31))
+        return ctx->fail(SNARKV_ERR_USAGE, "snarkv_fr_program_eval_batch: bad argument");
+    std::vector<uint8_t> written(n_regs, 0);
+    for (size_t i = 0; i < n_instr; ++i) {
+        const snarkv_fr_instr& in = program[i];
+        bool ok = in.dst < n_regs;
+        auto src = [&](uint32_t r) { return r < n_regs && written[r]; };
+        switch (in.op) {
+            case SNARKV_FR_OP_INPUT: ok = ok && in.a < n_inputs; break;
+            case SNARKV_FR_OP_CONST: ok = ok && in.a < n_consts; break;
+            case SNARKV_FR_OP_ADD: case SNARKV_FR_OP_SUB: case SNARKV_FR_OP_MUL: ok = ok && src(in.a) && src(in.b); break;
+            case SNARKV_FR_OP_NEG: case SNARKV_FR_OP_INV: ok = ok && src(in.a); break;
+            default: ok = false;
+        }
+        if (!ok) return ctx->fail(SNARKV_ERR_USAGE, "snarkv_fr_program_eval_batch: invalid instruction (opcode, operand out of range, or register read before it is written)");
+        written[in.dst] = 1;
+    }
+    for (size_t k = 0; k < n_out; ++k)
+        if (out_regs[k] >= n_regs || !written[out_regs[k]]) return ctx->fail(SNARKV_ERR_USAGE, "snarkv_fr_program_eval_batch: output register never written");
+    const size_t prog_bytes = n_instr * sizeof(snarkv_fr_instr), const_bytes = n_consts * 32, out_bytes = n_out * 4;
+    uint8_t* buf = (uint8_t*)ctx->wsget(WS_FR_PROG, prog_bytes + const_bytes + out_bytes + 64);
+    if (!buf) return SNARKV_ERR_CUDA;
+    cudaStream_t st = ctx->stream;
+    *d_prog = buf;
+    *d_consts = buf + prog_bytes;          // 16-byte aligned: prog_bytes is a multiple of 16
+    *d_out_regs = *d_consts + const_bytes;
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(*d_prog, program, prog_bytes, cudaMemcpyHostToDevice, st));
+    if (n_consts) SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(*d_consts, consts, const_bytes, cudaMemcpyHostToDevice, st));
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(*d_out_regs, out_regs, out_bytes, cudaMemcpyHostToDevice, st));
+    return SNARKV_OK;
+}
+
+int snarkv_fr_program_eval_batch_device(snarkv_ctx* ctx, const snarkv_fr_instr* program, size_t n_instr, uint32_t n_regs,
+                                        const uint8_t* consts, size_t n_consts, const void* d_inputs, size_t n_inputs, size_t m,
+                                        const uint32_t* out_regs, size_t n_out, int format, void* d_outputs) {
+    CTX_GUARD(ctx);
+    if (!d_outputs || (n_inputs && !d_inputs)) return ctx->fail(SNARKV_ERR_USAGE, "snarkv_fr_program_eval_batch_device: bad argument");
+    uint8_t *d_prog, *d_consts, *d_out_regs;
+    int rc = fr_program_stage(ctx, program, n_instr, n_regs, consts, n_consts, n_inputs, m, out_regs, n_out, format, &d_prog, &d_consts, &d_out_regs);
+    if (rc) return rc;
+    if (m == 0) return SNARKV_OK;
+    rc = fr_program_device(ctx, d_prog, n_instr, d_consts, n_consts, d_inputs, n_inputs, m, format, n_regs, d_out_regs, n_out, d_outputs);
+    if (rc) return rc;
+    // the staged program is pageable host memory handed to cudaMemcpyAsync: make sure it has left the caller's buffers
+    SNARKV_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return SNARKV_OK;
+}
+
+int snarkv_fr_program_eval_batch(snarkv_ctx* ctx, const snarkv_fr_instr* program, size_t n_instr, uint32_t n_regs, const uint8_t* consts,
+                                 size_t n_consts, const uint8_t* inputs, size_t n_inputs, size_t m, const uint32_t* out_regs, size_t n_out,
+                                 int format, uint8_t* outputs) {
+    CTX_GUARD(ctx);
+    if (!outputs || (n_inputs && !inputs)) return ctx->fail(SNARKV_ERR_USAGE, "snarkv_fr_program_eval_batch: bad argument");
+    uint8_t *d_prog, *d_consts, *d_out_regs;
+    int rc = fr_program_stage(ctx, program, n_instr, n_regs, consts, n_consts, n_inputs, m, out_regs, n_out, format, &d_prog, &d_consts, &d_out_regs);
+    if (rc) return rc;
+    if (m == 0) return SNARKV_OK;
+    uint8_t* d_in = (uint8_t*)ctx->wsget(WS_IO_A, m * n_inputs * 32 + 32);
+    uint8_t* d_o = (uint8_t*)ctx->wsget(WS_IO_B, m * n_out * 32);
+    if (!d_in || !d_o) return SNARKV_ERR_CUDA;
+    cudaStream_t st = ctx->stream;
+    if (n_inputs) SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_in, inputs, m * n_inputs * 32, cudaMemcpyHostToDevice, st));
+    rc = fr_program_device(ctx, d_prog, n_instr, d_consts, n_consts, d_in, n_inputs, m, format, n_regs, d_out_regs, n_out, d_o);
+    if (rc) return rc;
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(outputs, d_o, m * n_out * 32, cudaMemcpyDeviceToHost, st));
     SNARKV_CUDA_TRY(ctx, cudaStreamSynchronize(st));
     return SNARKV_OK;
 }

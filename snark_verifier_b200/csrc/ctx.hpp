@@ -51,6 +51,8 @@ enum WsSlot : int {
     WS_BA_PREFIX,         // per resident block: K x 128 x 32 B prefix products
     WS_BA_COUNTER,        // [group counter | self-check mismatch record x 4]
     WS_TASK_OUT_CHECK,    // second task-result array (accumulate mode 3)
+    WS_FR_REGS,           // fr_program register file: n_regs x m x 32 B
+    WS_FR_PROG,           // fr_program: instructions | consts | out_regs
     WS_SLOTS
 };
 
@@ -178,6 +180,8 @@ int msm_batch_device(snarkv_ctx* ctx, const void* d_scalars, const void* d_point
 int msm_batch_rlc_device(snarkv_ctx* ctx, const void* d_scalars, const void* d_points, const void* d_offsets, size_t m, size_t total,
                          const void* d_rho, int format, int flags, void* d_scaled, void* d_powers, void* d_out_affine, void* d_status);
 int fr_batch_invert_device(snarkv_ctx* ctx, void* d_values, size_t n, int format, const void* d_coeff, void* d_scratch);
+int fr_program_device(snarkv_ctx* ctx, const void* d_prog, size_t n_instr, void* d_consts, size_t n_consts, const void* d_inputs,
+                      size_t n_inputs, size_t m, int format, uint32_t n_regs, const void* d_out_regs, size_t n_out, void* d_outputs);
 int fr_mul_vec_device(snarkv_ctx* ctx, const void* d_a, const void* d_b, size_t n, int format, void* d_out);
 int fr_from_mont_device(snarkv_ctx* ctx, void* d_v, size_t n);
 int evm_transcript_device(snarkv_ctx* ctx, const void* d_streams, size_t stream_len, const void* d_seg_end, size_t k, size_t m, int format,

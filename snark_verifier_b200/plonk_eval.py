@@ -1,0 +1,448 @@
+"""Host mirror of the per-proof PLONK scalar evaluation of snark-verifier and its compiler to the
+straight-line Fr register program that `snarkv_fr_program_eval_batch` (csrc/fr_program.cu) runs for a whole batch of proofs.
+
+Mirrored reference items (paths relative to snark-verifier/src):
+  util/arithmetic.rs:83-160        root_of_unity, Rotation, Domain::{new, rotate_scalar}
+  verifier/plonk/protocol.rs:186-197  CommonPolynomial::{Identity, Lagrange(i)}
+  verifier/plonk/protocol.rs:211-283  CommonPolynomialEvaluation::{new, evaluate}: z^n, z^n - 1, 1/(z^n - 1), L_i(z)
+  verifier/plonk/protocol.rs:304-392  Query, Expression and Expression::evaluate (the eight-closure fold, DistributePowers)
+  verifier/plonk/proof.rs:298-303     quotient evaluation = numerator * zn_minus_one_inv (no linearization)
+  verifier/plonk/proof.rs:306-349     PlonkProof::evaluations: instance evaluations sum_j instance[j] * L_{j - rotation}(z)
+  loader.rs:52-69                     LoadedScalar::pow_const (exact square-and-multiply order)
+  loader.rs:255-262                   ScalarLoader::batch_invert (zero stays zero)
+
+The protocol of a batch is fixed, so the expression tree is the same for every proof: `Expression.evaluate` is run ONCE on the
+host with closures that emit instructions instead of computing (exactly how the reference runs it over EVM / Halo2 loaders), and
+the resulting program is executed by one GPU thread per proof.  The linearized (Msm-valued) numerator of
+`LinearizationStrategy::*` stays on the host: this module covers the scalar path (`linearization: None`, what the halo2 system
+produces).
+"""
+from dataclasses import dataclass
+from typing import Dict, List, Sequence, Tuple
+
+R_MODULUS = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+FR_S = 28                                                                          # Fr::S
+FR_ROOT_OF_UNITY = 0x03DDB9F5166D18B798865EA93DD31F743215CF6DD39329C8D34F1ED960C37C9C  # Fr::ROOT_OF_UNITY = 7^((r-1)/2^28)
+
+OP_INPUT, OP_CONST, OP_ADD, OP_SUB, OP_MUL, OP_NEG, OP_INV = range(7)   # include/snarkv_cuda.h SNARKV_FR_OP_*
+
+
+def root_of_unity(k: int) -> int:
+    """util/arithmetic.rs:83-90"""
+    assert k <= FR_S
+    w = FR_ROOT_OF_UNITY
+    for _ in range(FR_S - k):
+        w = w * w % R_MODULUS
+    return w
+
+
+@dataclass(frozen=True, order=True)
+class Rotation:
+    """util/arithmetic.rs:95-120"""
+    value: int = 0
+
+
+class Domain:
+    """util/arithmetic.rs:123-160"""
+
+    def __init__(self, k: int, gen: int = None):
+        self.k = k
+        self.n = 1 << k
+        self.gen = root_of_unity(k) if gen is None else gen
+        self.n_inv = pow(self.n, -1, R_MODULUS)
+        self.gen_inv = pow(self.gen, -1, R_MODULUS)
+
+    def rotate_scalar(self, scalar: int, rotation: Rotation) -> int:
+        r = rotation.value
+        if r == 0:
+            return scalar
+        if r > 0:
+            return scalar * pow(self.gen, r, R_MODULUS) % R_MODULUS
+        return scalar * pow(self.gen_inv, -r, R_MODULUS) % R_MODULUS
+
+
+@dataclass(frozen=True, order=True)
+class Query:
+    """protocol.rs:304-320"""
+    poly: int
+    rotation: Rotation = Rotation(0)
+
+
+@dataclass(frozen=True)
+class CommonPolynomial:
+    """protocol.rs:186-197: Identity, or Lagrange(i)"""
+    kind: str            # "identity" | "lagrange"
+    index: int = 0
+
+    @staticmethod
+    def identity():
+        return CommonPolynomial("identity")
+
+    @staticmethod
+    def lagrange(i: int):
+        return CommonPolynomial("lagrange", i)
+
+
+class Expression:
+    """protocol.rs:322-334.  Variants are built with the static constructors; `evaluate` is the reference's generic fold."""
+
+    __slots__ = ("tag", "args")
+
+    def __init__(self, tag, *args):
+        self.tag, self.args = tag, args
+
+    # -- constructors --------------------------------------------------------------------------------------------------
+    @staticmethod
+    def constant(c: int): return Expression("constant", c % R_MODULUS)
+    @staticmethod
+    def common_polynomial(p: CommonPolynomial): return Expression("common", p)
+    @staticmethod
+    def polynomial(q: Query): return Expression("poly", q)
+    @staticmethod
+    def challenge(i: int): return Expression("challenge", i)
+    @staticmethod
+    def negated(a): return Expression("neg", a)
+    @staticmethod
+    def sum(a, b): return Expression("sum", a, b)
+    @staticmethod
+    def product(a, b): return Expression("product", a, b)
+    @staticmethod
+    def scaled(a, c: int): return Expression("scaled", a, c % R_MODULUS)
+    @staticmethod
+    def distribute_powers(exprs: Sequence["Expression"], scalar: "Expression"): return Expression("powers", tuple(exprs), scalar)
+
+    def __add__(self, o): return Expression.sum(self, o)
+    def __mul__(self, o): return Expression.product(self, o) if isinstance(o, Expression) else Expression.scaled(self, o)
+    def __neg__(self): return Expression.negated(self)
+    def __sub__(self, o): return Expression.sum(self, Expression.negated(o))
+
+    # -- protocol.rs:336-392 -----------------------------------------------------------------------------------------------
+    def evaluate(self, constant, common_poly, poly, challenge, negated, sum, product, scaled):
+        ev = lambda e: e.evaluate(constant, common_poly, poly, challenge, negated, sum, product, scaled)
+        t, a = self.tag, self.args
+        if t == "constant":
+            return constant(a[0])
+        if t == "common":
+            return common_poly(a[0])
+        if t == "poly":
+            return poly(a[0])
+        if t == "challenge":
+            return challenge(a[0])
+        if t == "neg":
+            return negated(ev(a[0]))
+        if t == "sum":
+            x = ev(a[0]); y = ev(a[1])
+            return sum(x, y)
+        if t == "product":
+            x = ev(a[0]); y = ev(a[1])
+            return product(x, y)
+        if t == "scaled":
+            return scaled(ev(a[0]), a[1])
+        exprs, scalar = a                                  # DistributePowers: Horner in `scalar`, first expression = highest power
+        assert len(exprs) > 0
+        if len(exprs) == 1:
+            return ev(exprs[0])
+        acc = ev(exprs[0])
+        s = ev(scalar)
+        for e in exprs[1:]:
+            acc = sum(product(acc, s), ev(e))
+        return acc
+
+    def used_langrange(self) -> set:
+        """protocol.rs:417-435"""
+        return self.evaluate(lambda c: set(), lambda p: {p.index} if p.kind == "lagrange" else set(), lambda q: set(), lambda i: set(),
+                             lambda a: a, lambda a, b: a | b, lambda a, b: a | b, lambda a, c: a)
+
+    def used_query(self) -> set:
+        """protocol.rs:437-455"""
+        return self.evaluate(lambda c: set(), lambda p: set(), lambda q: {q}, lambda i: set(),
+                             lambda a: a, lambda a, b: a | b, lambda a, b: a | b, lambda a, c: a)
+
+    def to_tuple(self):
+        """Plain nested tuples (what the test oracle consumes; it shares no code with this module)."""
+        t, a = self.tag, self.args
+        if t == "common":
+            return ("common", a[0].kind, a[0].index)
+        if t == "poly":
+            return ("poly", a[0].poly, a[0].rotation.value)
+        if t in ("constant", "challenge"):
+            return (t, a[0])
+        if t == "neg":
+            return ("neg", a[0].to_tuple())
+        if t in ("sum", "product"):
+            return (t, a[0].to_tuple(), a[1].to_tuple())
+        if t == "scaled":
+            return ("scaled", a[0].to_tuple(), a[1])
+        return ("powers", tuple(e.to_tuple() for e in a[0]), a[1].to_tuple())
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# program builder: the "loader" whose scalars are virtual registers
+# ----------------------------------------------------------------------------------------------------------------------
+class Program:
+    """A straight-line register program: `instrs` (op, dst, a, b) over `n_regs` registers, `consts` (ints mod r), `n_inputs`
+    per-proof input slots and the `outputs` registers, as snarkv_fr_program_eval_batch takes them."""
+
+    def __init__(self, instrs, n_regs, consts, n_inputs, outputs, output_names):
+        self.instrs, self.n_regs, self.consts, self.n_inputs = instrs, n_regs, consts, n_inputs
+        self.outputs, self.output_names = outputs, output_names
+
+    def op_histogram(self) -> Dict[str, int]:
+        names = ["input", "const", "add", "sub", "mul", "neg", "inv"]
+        h = {k: 0 for k in names}
+        for op, _, _, _ in self.instrs:
+            h[names[op]] += 1
+        return h
+
+
+class ProgramBuilder:
+    """Emits SSA values; `finish` maps them onto a small register file by liveness (a value's register is reused after its last
+    use), which keeps the device register file — n_regs x m x 32 B — L2-sized."""
+
+    def __init__(self):
+        self.ssa: List[Tuple[int, int, int]] = []     # (op, a, b): a, b are SSA ids, or the slot for INPUT / CONST
+        self.consts: List[int] = []
+        self._const_ix: Dict[int, int] = {}
+        self._const_val: Dict[int, int] = {}
+        self._input_val: Dict[int, int] = {}
+        self.n_inputs = 0
+
+    def _emit(self, op, a=0, b=0) -> int:
+        self.ssa.append((op, a, b))
+        return len(self.ssa) - 1
+
+    def input(self, slot: int) -> int:
+        """Per-proof value `slot` of the input row (loaded once)."""
+        if slot not in self._input_val:
+            self._input_val[slot] = self._emit(OP_INPUT, slot)
+            self.n_inputs = max(self.n_inputs, slot + 1)
+        return self._input_val[slot]
+
+    def const(self, c: int) -> int:
+        """ScalarLoader::load_const (loaded once per distinct value)."""
+        c %= R_MODULUS
+        if c not in self._const_ix:
+            self._const_ix[c] = len(self.consts)
+            self.consts.append(c)
+        ix = self._const_ix[c]
+        if ix not in self._const_val:
+            self._const_val[ix] = self._emit(OP_CONST, ix)
+        return self._const_val[ix]
+
+    def add(self, a, b): return self._emit(OP_ADD, a, b)
+    def sub(self, a, b): return self._emit(OP_SUB, a, b)
+    def mul(self, a, b): return self._emit(OP_MUL, a, b)
+    def neg(self, a): return self._emit(OP_NEG, a)
+    def inv(self, a): return self._emit(OP_INV, a)
+
+    def pow_const(self, a: int, exp: int) -> int:
+        """loader.rs:52-69, the same square-and-multiply order."""
+        assert exp > 0
+        base = a
+        while exp & 1 == 0:
+            base = self.mul(base, base)
+            exp >>= 1
+        acc = base
+        while exp > 1:
+            exp >>= 1
+            base = self.mul(base, base)
+            if exp & 1:
+                acc = self.mul(acc, base)
+        return acc
+
+    def finish(self, outputs: Sequence[int], names: Sequence[str] = None) -> Program:
+        n = len(self.ssa)
+        last = list(range(n))                        # last SSA id that reads each value
+        for i, (op, a, b) in enumerate(self.ssa):
+            if op in (OP_ADD, OP_SUB, OP_MUL):
+                last[a] = max(last[a], i); last[b] = max(last[b], i)
+            elif op in (OP_NEG, OP_INV):
+                last[a] = max(last[a], i)
+        for o in outputs:
+            last[o] = n                              # outputs live to the end
+        free: List[int] = []
+        reg = [0] * n
+        n_regs = 0
+        expire: Dict[int, List[int]] = {}
+        instrs = []
+        for i, (op, a, b) in enumerate(self.ssa):
+            if op in (OP_INPUT, OP_CONST):
+                ra, rb = a, 0
+            elif op in (OP_NEG, OP_INV):
+                ra, rb = reg[a], 0
+            else:
+                ra, rb = reg[a], reg[b]
+            # operands whose last use is this instruction release their registers first: dst may reuse them (the kernel reads
+            # both operands before it writes)
+            for v in expire.pop(i, []):
+                free.append(reg[v])
+            if free:
+                r = free.pop()
+            else:
+                r = n_regs
+                n_regs += 1
+            reg[i] = r
+            if last[i] == i:                         # never read (dead value): release at once
+                free.append(r)
+            elif last[i] < n:
+                expire.setdefault(last[i], []).append(i)
+            instrs.append((op, r, ra, rb))
+        return Program(instrs, max(n_regs, 1), list(self.consts), self.n_inputs, [reg[o] for o in outputs],
+                       list(names) if names else ["out%d" % k for k in range(len(outputs))])
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# protocol.rs:211-283 and proof.rs:298-349 over the builder
+# ----------------------------------------------------------------------------------------------------------------------
+class CommonPolynomialEvaluation:
+    """protocol.rs:199-283 with `ProgramBuilder` values.  `new` + `evaluate` are folded into the constructor (the deferred
+    `Fraction` only exists to batch the inversions, which `INV` performs per value with the same zero-stays-zero rule)."""
+
+    def __init__(self, b: ProgramBuilder, domain: Domain, langranges, z: int):
+        self.b = b
+        self.zn = b.pow_const(z, domain.n)
+        lang = sorted(set(langranges))
+        one = b.const(1)
+        self.zn_minus_one = b.sub(self.zn, one)
+        self.zn_minus_one_inv = b.inv(self.zn_minus_one)            # Fraction::one_over(zn_minus_one), evaluated
+        n_inv = b.const(domain.n_inv)
+        numer = b.mul(self.zn_minus_one, n_inv)
+        self.identity = z
+        self.lagrange = {}
+        for i in lang:
+            omega = b.const(domain.rotate_scalar(1, Rotation(i)))
+            num_i = b.mul(numer, omega)                             # Fraction::new(numer * omega, z - omega)
+            den_i = b.sub(z, omega)
+            self.lagrange[i] = b.mul(num_i, b.inv(den_i))           # Fraction::evaluate: numer * denom^-1
+
+    def get(self, poly: CommonPolynomial) -> int:
+        return self.identity if poly.kind == "identity" else self.lagrange[poly.index]
+
+
+@dataclass
+class QuotientProtocol:
+    """The slice of `PlonkProtocol` (protocol.rs:22-67) the scalar path reads."""
+    domain: Domain
+    num_preprocessed: int
+    num_instance: List[int]              # protocol.num_instance
+    evaluations: List[Query]             # protocol.evaluations: the queries whose evaluations the proof carries, in order
+    num_challenge: int                   # sum(protocol.num_challenge)
+    numerator: Expression                # protocol.quotient.numerator
+
+    def input_layout(self) -> Dict[str, int]:
+        """Per-proof input row: [z | challenges | evaluations (protocol.evaluations order) | instances (column-major)]."""
+        off = {"z": 0, "challenges": 1}
+        off["evaluations"] = 1 + self.num_challenge
+        off["instances"] = off["evaluations"] + len(self.evaluations)
+        off["total"] = off["instances"] + sum(self.num_instance)
+        return off
+
+
+def compile_quotient_evaluation(p: QuotientProtocol) -> Program:
+    """The scalar half of PlonkProof::{evaluations, commitments} for `linearization: None` and no instance committing key:
+    outputs [quotient evaluation, z^n, z^n - 1, 1/(z^n - 1), instance evaluations...] per proof."""
+    b = ProgramBuilder()
+    lay = p.input_layout()
+    z = b.input(lay["z"])
+    offset = p.num_preprocessed
+    inst_range = range(offset, offset + len(p.num_instance))
+    inst_queries = sorted(q for q in p.numerator.used_query() if q.poly in inst_range)
+    # PlonkProtocol::langranges (protocol.rs:77-106): the numerator's own Lagrange indices plus ONE range for the instance
+    # evaluations, -max_rotation .. max_instance_len + |min_rotation| (min / max folded from (0, 0) over the instance queries)
+    lang = set(p.numerator.used_langrange())
+    max_inst = max(p.num_instance) if p.num_instance else 0
+    min_rot = max_rot = 0
+    for q in inst_queries:
+        if q.rotation.value < min_rot:
+            min_rot = q.rotation.value
+        elif q.rotation.value > max_rot:
+            max_rot = q.rotation.value
+    lang |= set(range(-max_rot, max_inst + abs(min_rot)))
+    cpe = CommonPolynomialEvaluation(b, p.domain, lang, z)
+    evals: Dict[Query, int] = {}
+    inst_base = [lay["instances"] + sum(p.num_instance[:k]) for k in range(len(p.num_instance))]
+    inst_eval_regs = []
+    for q in inst_queries:                                           # proof.rs:313-334 (loader.sum_products)
+        col = q.poly - offset
+        acc = None
+        for j in range(p.num_instance[col]):
+            term = b.mul(b.input(inst_base[col] + j), cpe.get(CommonPolynomial.lagrange(j - q.rotation.value)))
+            acc = term if acc is None else b.add(acc, term)
+        if acc is None:
+            acc = b.const(0)
+        evals[q] = acc
+        inst_eval_regs.append(acc)
+    for k, q in enumerate(p.evaluations):                           # proof.rs:336-346
+        evals[q] = b.input(lay["evaluations"] + k)
+
+    def poly(q):
+        if q not in evals:
+            raise KeyError("Missing query %r" % (q,))                # Error::InvalidProtocol("Missing query ..")
+        return evals[q]
+
+    def challenge(i):
+        if i >= p.num_challenge:
+            raise KeyError("Missing challenge %d" % i)
+        return b.input(lay["challenges"] + i)
+    numerator = p.numerator.evaluate(lambda c: b.const(c), cpe.get, poly, challenge, b.neg, b.add, b.mul,
+                                     lambda a, c: b.mul(a, b.const(c)))
+    quotient_eval = b.mul(numerator, cpe.zn_minus_one_inv)           # proof.rs:298-303
+    outs = [quotient_eval, cpe.zn, cpe.zn_minus_one, cpe.zn_minus_one_inv] + inst_eval_regs
+    names = ["quotient_eval", "zn", "zn_minus_one", "zn_minus_one_inv"] + ["instance_eval_%d" % k for k in range(len(inst_eval_regs))]
+    b.n_inputs = lay["total"]            # the row stride is the layout's, even when the numerator leaves some slots unread
+    return b.finish(outs, names)
+
+
+def pack_program(prog: Program):
+    """ctypes-ready arrays: (instr uint32[n][4], consts bytes LE canonical, out_regs uint32[n_out])."""
+    import numpy as np
+    ins = np.asarray(prog.instrs, dtype=np.uint32).reshape(-1, 4)
+    consts = b"".join(c.to_bytes(32, "little") for c in prog.consts)
+    outs = np.asarray(prog.outputs, dtype=np.uint32)
+    return ins, consts, outs
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# synthetic protocol of StandardPlonk shape (tests / bench): what system/halo2.rs compiles for the reference's StandardPlonk
+# test circuit, built by hand — gate + permutation argument over (a, b, c) with zero-knowledge rows, no lookups
+# ----------------------------------------------------------------------------------------------------------------------
+FR_DELTA = pow(7, 1 << FR_S, R_MODULUS)   # Fr::DELTA = MULTIPLICATIVE_GENERATOR^(2^S)
+
+
+def standard_plonk_like_protocol(k: int, num_instance: int = 1, blinding_factors: int = 5) -> QuotientProtocol:
+    """Polynomial indices: 0-4 fixed (q_a, q_b, q_c, q_ab, constant), 5-7 permutation sigmas, 8 instance, 9-11 advice (a, b, c),
+    12 permutation z.  Challenges: 0 theta (unused), 1 beta, 2 gamma, 3 alpha.  Constraints as system/halo2.rs:520-660 lays them
+    out: gate; l_0 (1 - z); l_last (z^2 - z); l_active (z(wX) prod(p_i + beta sigma_i + gamma) - z prod(p_i + beta delta^i X + gamma));
+    numerator = DistributePowers(constraints, alpha)."""
+    E, Q, CP = Expression, Query, CommonPolynomial
+    poly = lambda i, r=0: E.polynomial(Q(i, Rotation(r)))
+    q_a, q_b, q_c, q_ab, constant = (poly(i) for i in range(5))
+    sigmas = [poly(5 + i) for i in range(3)]
+    instance = poly(8)
+    advice = [poly(9 + i) for i in range(3)]
+    a, b, c = advice
+    z, z_omega = poly(12), poly(12, 1)
+    beta, gamma, alpha = E.challenge(1), E.challenge(2), E.challenge(3)
+    one = E.constant(1)
+    rotation_last = -(blinding_factors + 1)
+    l_0 = E.common_polynomial(CP.lagrange(0))
+    l_last = E.common_polynomial(CP.lagrange(rotation_last))
+    l_blind = None
+    for i in range(rotation_last + 1, 0):
+        t = E.common_polynomial(CP.lagrange(i))
+        l_blind = t if l_blind is None else l_blind + t
+    l_active = one - (l_last + l_blind)
+    identity = E.common_polynomial(CP.identity())
+    gate = q_a * a + q_b * b + q_c * c + q_ab * a * b + constant + instance
+    left = z_omega
+    for p, s in zip(advice, sigmas):
+        left = left * (p + beta * s + gamma)
+    right = z
+    delta = 1
+    for p in advice:
+        right = right * (p + beta * E.constant(delta) * identity + gamma)
+        delta = delta * FR_DELTA % R_MODULUS
+    constraints = [gate, l_0 * (one - z), l_last * (z * z - z), l_active * (left - right)]
+    evaluations = [Q(i, Rotation(0)) for i in range(8)] + [Q(9 + i, Rotation(0)) for i in range(3)] + [Q(12, Rotation(0)), Q(12, Rotation(1))]
+    return QuotientProtocol(domain=Domain(k), num_preprocessed=8, num_instance=[num_instance], evaluations=evaluations, num_challenge=4,
+                            numerator=E.distribute_powers(constraints, alpha))
