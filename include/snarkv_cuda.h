@@ -174,6 +174,15 @@ int snarkv_fr_mul_vec(snarkv_ctx* ctx, const uint8_t* a, const uint8_t* b, size_
 int snarkv_evm_transcript_challenges(snarkv_ctx* ctx, const uint8_t* streams, size_t stream_len, const uint32_t* seg_end, size_t k, size_t m,
                                      int format, uint8_t* challenges);
 
+/* ---- (row a13) `LimbsEncoding<LIMBS, BITS>::from_repr` for m accumulators -----------------------------------------------------
+ * Replaces pcs/kzg/accumulator.rs:57-81 (+ util/arithmetic.rs:270-282 fe_from_limbs): `limbs` = m x 4 x num_limbs x 32 B scalars in
+ * `format`, per accumulator the limbs of lhs.x, lhs.y, rhs.x, rhs.y (limb i weighs 2^(limb_bits i); the SDK uses 4 x 68).
+ * `lhs`, `rhs`: m x 64 B affine points in `format`; `valid[a]` = 1 iff every coordinate fits 32 bytes, is a canonical base-field
+ * element and both points satisfy `from_xy` (on the curve, or the identity (0,0)) — where the reference panics, valid[a] = 0 and
+ * the points are written as (0,0).  1 <= num_limbs <= 8, limb_bits (num_limbs - 1) <= 256. */
+int snarkv_kzg_accumulators_from_limbs(snarkv_ctx* ctx, const uint8_t* limbs, size_t m, uint32_t num_limbs, uint32_t limb_bits, int format,
+                                       uint8_t* lhs, uint8_t* rhs, uint8_t* valid);
+
 /* ---- (next row f3) per-proof PLONK scalar evaluation for m proofs of one protocol -----------------------------------------
  * Replaces verifier/plonk/protocol.rs:211-283 (CommonPolynomialEvaluation), :333-392 (Expression::evaluate) and
  * verifier/plonk/proof.rs:298-349 (instance evaluations, quotient evaluation) for a batch: the protocol — hence the expression

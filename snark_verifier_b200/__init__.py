@@ -69,6 +69,7 @@ C_ABI = {
     "snarkv_fr_batch_invert": (_i, [_vp, _vp, _sz, _vp, _i]),
     "snarkv_fr_mul_vec": (_i, [_vp, _vp, _vp, _sz, _i, _vp]),
     "snarkv_evm_transcript_challenges": (_i, [_vp, _vp, _sz, _vp, _sz, _sz, _i, _vp]),
+    "snarkv_kzg_accumulators_from_limbs": (_i, [_vp, _vp, _sz, ctypes.c_uint32, ctypes.c_uint32, _i, _vp, _vp, _vp]),
     "snarkv_fr_program_eval_batch": (_i, [_vp, _vp, _sz, ctypes.c_uint32, _vp, _sz, _vp, _sz, _sz, _vp, _sz, _i, _vp]),
     "snarkv_fr_program_eval_batch_device": (_i, [_vp, _vp, _sz, ctypes.c_uint32, _vp, _sz, _vp, _sz, _sz, _vp, _sz, _i, _vp]),
     "snarkv_kzg_accumulate": (_i, [_vp, _vp, _vp, _sz, _vp, _i, _vp, _vp]),
@@ -277,6 +278,13 @@ class CudaLoader:
                                                               ctypes.cast(se, ctypes.c_void_p), k, m, self.fmt, out), "evm_transcript")
         return out.raw
 
+    def accumulators_from_limbs(self, limbs, m, num_limbs=4, limb_bits=68):
+        """LimbsEncoding::from_repr (pcs/kzg/accumulator.rs:57-81) for m accumulators -> (lhs m*64 B, rhs m*64 B, valid m bytes)."""
+        lhs, rhs, valid = ctypes.create_string_buffer(64 * m), ctypes.create_string_buffer(64 * m), ctypes.create_string_buffer(max(m, 1))
+        self._check(self.lib.snarkv_kzg_accumulators_from_limbs(self.h, _addr(limbs), m, num_limbs, limb_bits, self.fmt, lhs, rhs, valid),
+                    "accumulators_from_limbs")
+        return lhs.raw, rhs.raw, valid.raw[:m]
+
     def fr_program_eval(self, program, inputs, m, d_inputs=None, d_outputs=None):
         """Run a plonk_eval.Program for m proofs (protocol.rs:211-283, 333-392; proof.rs:298-349 for a batch).  `inputs`:
         m * n_inputs * 32 bytes -> m * n_out * 32 bytes; with d_inputs / d_outputs (device pointers) nothing crosses PCIe but
@@ -348,6 +356,23 @@ class Msm:
 
     def __mul__(self, k):
         return Msm(self.loader, self.constant, self.scalars, self.bases).scale(k)
+
+    def __neg__(self):  # util/msm.rs:192-204
+        return Msm(self.loader, None if self.constant is None else (-self.constant) % R_MODULUS,
+                   [(-s) % R_MODULUS for s in self.scalars], self.bases)
+
+    def __sub__(self, other):  # util/msm.rs:156-178
+        return self + (-other)
+
+    def size(self):  # util/msm.rs:63-65
+        return len(self.bases)
+
+    @staticmethod
+    def sum(loader, msms):  # util/msm.rs:218-226 (an empty sum is the default, constant-free Msm)
+        acc = Msm(loader)
+        for m in msms:
+            acc = acc + m
+        return acc
 
     def evaluate(self, gen=None):  # util/msm.rs:81-98
         pairs = []

@@ -406,6 +406,31 @@ int snarkv_fr_mul_vec(snarkv_ctx* ctx, const uint8_t* a, const uint8_t* b, size_
     return SNARKV_OK;
 }
 
+// ---- (a13) LimbsEncoding::from_repr for a batch of accumulators (pcs/kzg/accumulator.rs:57-81) ------------------------------------
+int snarkv_kzg_accumulators_from_limbs(snarkv_ctx* ctx, const uint8_t* limbs, size_t m, uint32_t num_limbs, uint32_t limb_bits, int format,
+                                       uint8_t* lhs, uint8_t* rhs, uint8_t* valid) {
+    CTX_GUARD(ctx);
+    if (!limbs || !lhs || !rhs || !valid || bad_format(format) || num_limbs == 0 || num_limbs > 8 || limb_bits == 0 ||
+        (uint64_t)limb_bits * (num_limbs - 1) > 256)
+        return ctx->fail(SNARKV_ERR_USAGE, "snarkv_kzg_accumulators_from_limbs: bad argument");
+    if (m == 0) return SNARKV_OK;
+    const size_t in_bytes = m * 4 * num_limbs * 32;
+    uint8_t* d_in = (uint8_t*)ctx->wsget(WS_IO_A, in_bytes);
+    uint8_t* d_l = (uint8_t*)ctx->wsget(WS_IO_B, m * 64);
+    uint8_t* d_r = (uint8_t*)ctx->wsget(WS_IO_C, m * 64);
+    uint8_t* d_v = (uint8_t*)ctx->wsget(WS_IO_D, m);
+    if (!d_in || !d_l || !d_r || !d_v) return SNARKV_ERR_CUDA;
+    cudaStream_t st = ctx->stream;
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_in, limbs, in_bytes, cudaMemcpyHostToDevice, st));
+    int rc = accumulators_from_limbs_device(ctx, d_in, m, num_limbs, limb_bits, format, d_l, d_r, d_v);
+    if (rc) return rc;
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(lhs, d_l, m * 64, cudaMemcpyDeviceToHost, st));
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(rhs, d_r, m * 64, cudaMemcpyDeviceToHost, st));
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(valid, d_v, m, cudaMemcpyDeviceToHost, st));
+    SNARKV_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return SNARKV_OK;
+}
+
 // ---- (f3) straight-line Fr program for a batch of proofs (protocol.rs:211-283, 333-392; proof.rs:298-349) -------------------------
 // The program is small and comes from the host compiler: validate it here (opcodes, register bounds, write-before-read), then stage
 // instructions | consts | out_regs in one device buffer.

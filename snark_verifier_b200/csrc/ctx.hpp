@@ -180,6 +180,8 @@ int msm_batch_device(snarkv_ctx* ctx, const void* d_scalars, const void* d_point
 int msm_batch_rlc_device(snarkv_ctx* ctx, const void* d_scalars, const void* d_points, const void* d_offsets, size_t m, size_t total,
                          const void* d_rho, int format, int flags, void* d_scaled, void* d_powers, void* d_out_affine, void* d_status);
 int fr_batch_invert_device(snarkv_ctx* ctx, void* d_values, size_t n, int format, const void* d_coeff, void* d_scratch);
+int accumulators_from_limbs_device(snarkv_ctx* ctx, const void* d_limbs, size_t m, uint32_t L, uint32_t bits, int format, void* d_lhs,
+                                   void* d_rhs, void* d_valid);
 int fr_program_device(snarkv_ctx* ctx, const void* d_prog, size_t n_instr, void* d_consts, size_t n_consts, const void* d_inputs,
                       size_t n_inputs, size_t m, int format, uint32_t n_regs, const void* d_out_regs, size_t n_out, void* d_outputs);
 int fr_mul_vec_device(snarkv_ctx* ctx, const void* d_a, const void* d_b, size_t n, int format, void* d_out);
