@@ -196,6 +196,22 @@ def kzg_aux(L, sv, torch, stream, dev):
                "decide_single_latency_ms": ms_one,
                "decide_all_fused": {"proofs_per_s": n / ms_fused * 1e3, "ms": ms_fused, "accept": bool(ok_fused),
                                     "what": "host buffers in; powers of rho + two 4096-term MSMs + one pairing (wall clock incl. H2D)"}}
+        # rows f3 / a13 of SURVEY.md §8: the per-proof scalar evaluation and the limb decoding that sit either side of the path
+        try:
+            from snark_verifier_b200 import plonk_eval as pe
+            proto = pe.standard_plonk_like_protocol(12, num_instance=1)
+            prog = pe.compile_quotient_evaluation(proto)
+            tot = proto.input_layout()["total"]
+            with torch.cuda.stream(stream):
+                d_in = torch.empty(m_proofs * tot * 32, dtype=torch.uint8, device=dev)
+                d_out = torch.zeros(m_proofs * len(prog.outputs) * 32, dtype=torch.uint8, device=dev)
+                L.synth_scalars_device(SEED + 3, 0, m_proofs * tot, d_in.data_ptr())
+                ms_pe = timed(lambda: L.fr_program_eval(prog, None, m_proofs, d_inputs=d_in.data_ptr(), d_outputs=d_out.data_ptr()), 3)
+            out["plonk_scalar_eval"] = {"proofs_per_s": m_proofs / ms_pe * 1e3, "ms": ms_pe, "proofs": m_proofs, "instructions": len(prog.instrs),
+                                        "what": "StandardPlonk-shaped quotient evaluation (protocol.rs:211-283, 336-392; proof.rs:298-349) as one "
+                                                "straight-line Fr program, one thread per proof, operands resident in HBM"}
+        except Exception as e:
+            out["plonk_scalar_eval"] = {"error": repr(e)}
     except Exception as e:  # the headline metric must still print
         out = {"error": repr(e)}
     return out
@@ -243,6 +259,7 @@ def main():
     ap.add_argument("--ref-log-n", type=int, default=20, help="log2 of the per-step CPU sample for --impl reference / cpu_baseline")
     ap.add_argument("--window-bits", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-aux", action="store_true", help="skip the secondary KZG / scalar-evaluation measurements (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
     if args.impl == "reference":
@@ -379,7 +396,7 @@ def main():
 
     # ---- secondary metric of BASELINE.json: "proofs verified/s" (KZG accumulator decisions), rank 0, N = 1 only -------------
     aux = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not args.no_aux:
         aux = kzg_aux(L, sv, torch, stream, dev)
 
     if rank == 0:

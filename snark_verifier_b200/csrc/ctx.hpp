@@ -68,6 +68,7 @@ struct snarkv_ctx {
     int window_bits = 0;
     int glv_mode = 0;       // 0 = GLV for n < 2^22 (default), 1 = always, 2 = never
     int pairing_mode = 0;   // 0 = choose from N, 1 = one thread per check, 2 = one block per check
+    int host_chunks = 7, host_chunk_ratio_pct = 160;   // host entry pipeline: term-chunks of geometrically growing size (SNARKV_HOST_CHUNKS <= 7, SNARKV_HOST_RATIO in percent)
     int accumulate_mode = 0;   // 0 = choose from the bucket load, 1 = XYZZ, 2 = batched affine, 3 = both + task-level self-check
     int ba_blocks_per_sm = 0;  // occupancy of k_bucket_accumulate_affine (queried once)
     int ba_k = 128, ba_pairs_min = 24, ba_q = 4, ba_min_load = 48;   // batched-affine tuning (developer knobs: SNARKV_BA_K, _PAIRS_MIN, _Q, _MIN_LOAD)

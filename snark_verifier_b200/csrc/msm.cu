@@ -24,7 +24,7 @@
 
 namespace snarkv {
 
-#define SNARKV_HOST_CHUNKS 6
+#define SNARKV_HOST_CHUNKS_MAX 7
 
 struct MsmPlan {
     uint32_t c;    // window bits
@@ -229,14 +229,17 @@ __global__ void __launch_bounds__(SNARKV_DIGIT_TILE) k_digits(const uint8_t* __r
 // n x 4 B region (64 MB at 2^24 terms) that stays resident in the 126 MB L2 until its 32-byte sectors are complete.
 __global__ void __launch_bounds__(256) k_scatter(const uint32_t* __restrict__ digits, size_t n, uint32_t W, uint32_t NB,
                                                  uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
-    const size_t total = (size_t)W * n;
-    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
-        const uint32_t e = digits[g];
+    // blockIdx.y = window (blocks are dispatched x-fastest, so neighbouring blocks share a window); no per-element division
+    const uint32_t w = blockIdx.y;
+    const uint32_t* dg = digits + (size_t)w * n;
+    uint32_t* cur = cursor + (size_t)w * NB;
+    uint32_t* out = sorted + (size_t)w * n;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t e = dg[i];
         const uint32_t d = e & 0x7fffffffu;
         if (d == 0) continue;
-        const size_t w = g / n, i = g - w * n;
-        const uint32_t pos = atomicAdd(&cursor[w * NB + (d - 1u)], 1u);
-        sorted[w * n + pos] = (uint32_t)i | (e & 0x80000000u);
+        const uint32_t pos = atomicAdd(&cur[d - 1u], 1u);
+        out[pos] = (uint32_t)i | (e & 0x80000000u);
     }
 }
 
@@ -616,8 +619,10 @@ static int msm_sort_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* d_scal
     {
         Stage sg(ctx, "msm_digits_scatter");
         const size_t nv = plan_virtual_terms(pl, n);
-        const size_t tot = (size_t)pl.W * nv, wantb = (tot + 255) / 256, capb = (size_t)ctx->sm_count * 16;
-        k_scatter<<<(unsigned)(wantb < capb ? wantb : capb), 256, 0, st>>>(wk.digits, nv, pl.W, pl.NB, wk.cursor, wk.sorted);
+        // 8 elements per thread; at most 65535 blocks per window
+        size_t gx = (nv + 2047) / 2048;
+        if (gx > 65535) gx = 65535;
+        k_scatter<<<dim3((unsigned)gx, pl.W), 256, 0, st>>>(wk.digits, nv, pl.W, pl.NB, wk.cursor, wk.sorted);
         SNARKV_LAUNCH_CHECK(ctx, "k_scatter");
         sg.launched();
     }
@@ -790,8 +795,8 @@ int msm_run_device(snarkv_ctx* ctx, const void* d_scalars, const void* d_points,
 }
 
 // snarkv_g1_msm / snarkv_g1_msm_partial: host slices in.  Small inputs: scalars first, the (2x larger) point copy is issued
-// after the sort kernels are queued so copy engine and SMs overlap.  Large inputs (>= 2^22 terms) are cut into term-chunks of
-// geometrically growing size (x1.5): chunk k+1 is copied on the copy stream while chunk k is sorted and accumulated INTO THE SAME
+// after the sort kernels are queued so copy engine and SMs overlap.  Large inputs (>= 2^22 terms) are cut into 7 term-chunks of
+// geometrically growing size (x1.6; measured sweep profiles/r01_host_chunks.txt): chunk k+1 is copied on the copy stream while chunk k is sorted and accumulated INTO THE SAME
 // bucket array (plan fixed from the total n), so the first copy is short, no chunk pays its own reduce / Horner tail, and the
 // copy engine stays ahead of the SMs (96 B/term at ~50 GB/s vs ~2.9 ns/term of compute).
 int msm_run_host(snarkv_ctx* ctx, const uint8_t* scalars, const uint8_t* points, size_t n, int format, int flags, uint8_t* out,
@@ -805,8 +810,8 @@ int msm_run_host(snarkv_ctx* ctx, const uint8_t* scalars, const uint8_t* points,
     cudaStream_t st = ctx->stream;
     // measured: below 2^22 terms the per-chunk fixed costs (scan, merges, launches) eat the copy/compute overlap (2^21: 12.1 ms
     // chunked vs 11.9 ms in one pass), so smaller inputs keep the single-pass path
-    const int K = n >= ((size_t)1 << 22) ? SNARKV_HOST_CHUNKS : 1;
-    int status[SNARKV_HOST_CHUNKS] = {};
+    const int K = n >= ((size_t)1 << 22) ? ctx->host_chunks : 1;
+    int status[SNARKV_HOST_CHUNKS_MAX] = {};
     int* d_status = (int*)(d_o + 512);
     MsmWork wk;
     int rc = msm_alloc(ctx, n, d_status, wk, 1, K > 1 ? 2 : -1);   // plan from the TOTAL size; the chunk pipeline runs without GLV
@@ -821,13 +826,14 @@ int msm_run_host(snarkv_ctx* ctx, const uint8_t* scalars, const uint8_t* points,
         rc = msm_accumulate_phase(ctx, wk, d_p, n, format, check);
         if (rc) return rc;
     } else {
-        size_t lo[SNARKV_HOST_CHUNKS + 1];
+        size_t lo[SNARKV_HOST_CHUNKS_MAX + 1];
+        const double ratio = ctx->host_chunk_ratio_pct / 100.0;
         double total_w = 0, wgt = 1;
-        for (int k = 0; k < K; ++k, wgt *= 1.5) total_w += wgt;
+        for (int k = 0; k < K; ++k, wgt *= ratio) total_w += wgt;
         double acc_w = 0;
         wgt = 1;
         lo[0] = 0;
-        for (int k = 0; k < K; ++k, wgt *= 1.5) {
+        for (int k = 0; k < K; ++k, wgt *= ratio) {
             acc_w += wgt;
             lo[k + 1] = (k == K - 1) ? n : (((size_t)((double)n * (acc_w / total_w))) & ~(size_t)255);
         }

@@ -8,6 +8,8 @@
 //   KzgDecidingKey, KzgAccumulator           <->  pcs/kzg/decider.rs:6-42, pcs/kzg/accumulator.rs:6-26
 //   KzgAs::{decide, decide_all, verify}      <->  pcs/kzg/decider.rs:70-93, pcs/kzg/accumulation.rs:41-63
 //   AssertionFailure                         <->  Error::AssertionFailure (lib.rs:18-28)
+//   LimbsEncoding<LIMBS, BITS>::from_repr    <->  pcs/kzg/accumulator.rs:57-81 (+ util/arithmetic.rs:270-282), also for a batch
+//   FrProgram / CudaLoader::fr_program_eval  <->  verifier/plonk/protocol.rs:211-283, 336-392; proof.rs:298-349 for a batch of proofs
 // Loaded values are plain host values exactly as NativeLoader keeps them (native.rs:44,75): Fr = 32 bytes, G1Affine = 64 bytes,
 // canonical little-endian (SNARKV_CANONICAL).  There is no arithmetic in this header except the Fr bookkeeping of `Msm`, which
 // the caller supplies through the tiny `FrOps` policy (the reference does that part with halo2curves' Fr on the host as well).
@@ -162,6 +164,50 @@ class KzgAs {
 
   private:
     CudaLoader* loader_;
+};
+
+// `LimbsEncoding<LIMBS, BITS>` (pcs/kzg/accumulator.rs:28-82): an accumulator as 4 x LIMBS scalar-field limbs.  The reference
+// panics when the limbs do not encode two curve points; here that is an `Error`.
+template <uint32_t LIMBS, uint32_t BITS>
+struct LimbsEncoding {
+    static std::vector<KzgAccumulator> from_repr_batch(CudaLoader& loader, const std::vector<Fr>& limbs, std::vector<uint8_t>* valid_out = nullptr) {
+        if (limbs.size() % (4 * LIMBS)) throw Error("LimbsEncoding::from_repr: limbs.len() must be a multiple of 4 * LIMBS");
+        const size_t m = limbs.size() / (4 * LIMBS);
+        std::vector<uint8_t> lhs(m * 64), rhs(m * 64), valid(m);
+        loader.check(snarkv_kzg_accumulators_from_limbs(loader.raw(), limbs.empty() ? nullptr : limbs[0].data(), m, LIMBS, BITS, SNARKV_CANONICAL,
+                                                        lhs.data(), rhs.data(), valid.data()), "LimbsEncoding::from_repr");
+        std::vector<KzgAccumulator> out(m);
+        for (size_t a = 0; a < m; ++a) {
+            if (!valid[a] && !valid_out) throw Error("LimbsEncoding::from_repr: limbs do not encode two G1 points");   // from_xy(..).unwrap()
+            memcpy(out[a].lhs.data(), &lhs[64 * a], 64);
+            memcpy(out[a].rhs.data(), &rhs[64 * a], 64);
+        }
+        if (valid_out) *valid_out = valid;
+        return out;
+    }
+    static KzgAccumulator from_repr(CudaLoader& loader, const std::vector<Fr>& limbs) {                           // accumulator.rs:57-81
+        if (limbs.size() != 4 * LIMBS) throw Error("LimbsEncoding::from_repr: expected 4 * LIMBS limbs");        // assert_eq!(limbs.len(), 4 * LIMBS)
+        return from_repr_batch(loader, limbs)[0];
+    }
+};
+
+// A straight-line Fr register program (include/snarkv_cuda.h SNARKV_FR_OP_*): what `Expression::evaluate` +
+// `CommonPolynomialEvaluation` flatten to for ONE protocol (the compiler lives in snark_verifier_b200/plonk_eval.py).
+struct FrProgram {
+    std::vector<snarkv_fr_instr> instrs;
+    uint32_t n_regs = 0;
+    std::vector<Fr> consts;
+    size_t n_inputs = 0;
+    std::vector<uint32_t> outputs;
+    // inputs: m x n_inputs scalars -> m x outputs.size() scalars
+    std::vector<Fr> eval_batch(CudaLoader& loader, const std::vector<Fr>& inputs, size_t m) const {
+        if (inputs.size() != m * n_inputs) throw Error("FrProgram::eval_batch: inputs.len() != m * n_inputs");
+        std::vector<Fr> out(m * outputs.size());
+        loader.check(snarkv_fr_program_eval_batch(loader.raw(), instrs.data(), instrs.size(), n_regs, consts.empty() ? nullptr : consts[0].data(),
+                                                  consts.size(), inputs.empty() ? nullptr : inputs[0].data(), n_inputs, m, outputs.data(),
+                                                  outputs.size(), SNARKV_CANONICAL, out.empty() ? nullptr : out[0].data()), "FrProgram::eval_batch");
+        return out;
+    }
 };
 
 }  // namespace snarkv

@@ -54,6 +54,48 @@ int main(int argc, char** argv) {
     Fr r{}; r[0] = 5;
     KzgAccumulator acc = as.verify({{lhs_ok, rhs_ok}, {lhs_ok, rhs_ok}}, r);
     as.decide(acc);
+    // LimbsEncoding<4, 68>::from_repr (accumulator.rs:57-81): split the valid accumulator into 16 limbs and rebuild it
+    {
+        std::vector<Fr> limbs;
+        for (const G1Affine* pt : {&lhs_ok, &rhs_ok})
+            for (int c = 0; c < 2; ++c)
+                for (int i = 0; i < 4; ++i) {   // limb i = bits [68 i, 68 i + 68) of the coordinate
+                    Fr l{};
+                    for (int b = 0; b < 68; ++b) {
+                        const int src = 68 * i + b;
+                        if (src < 256 && (((*pt)[32 * c + src / 8] >> (src % 8)) & 1)) l[b / 8] |= (uint8_t)(1u << (b % 8));
+                    }
+                    limbs.push_back(l);
+                }
+        KzgAccumulator back = LimbsEncoding<4, 68>::from_repr(loader, limbs);
+        if (back.lhs != lhs_ok || back.rhs != rhs_ok) { fprintf(stderr, "LimbsEncoding round trip failed\n"); return 1; }
+        as.decide(back);
+        limbs[0][0] ^= 1;   // off the curve: the reference panics, the mirror throws
+        threw = false;
+        try { LimbsEncoding<4, 68>::from_repr(loader, limbs); } catch (const Error&) { threw = true; }
+        if (!threw) { fprintf(stderr, "off-curve limbs were accepted\n"); return 1; }
+    }
+    // FrProgram: out = (in0 * in0 + 5) ^ -1 for three proofs; 1 / (x^2 + 5) * (x^2 + 5) must be 1
+    {
+        FrProgram prog;
+        Fr five{}; five[0] = 5;
+        prog.consts = {five};
+        prog.n_inputs = 1;
+        prog.n_regs = 4;
+        prog.instrs = {{SNARKV_FR_OP_INPUT, 0, 0, 0}, {SNARKV_FR_OP_MUL, 1, 0, 0}, {SNARKV_FR_OP_CONST, 2, 0, 0}, {SNARKV_FR_OP_ADD, 1, 1, 2},
+                       {SNARKV_FR_OP_INV, 3, 1, 0}, {SNARKV_FR_OP_MUL, 3, 3, 1}};
+        prog.outputs = {3, 1};
+        std::vector<Fr> in(3);
+        in[0][0] = 2; in[1][0] = 3; in[2][5] = 9;
+        std::vector<Fr> out = prog.eval_batch(loader, in, 3);
+        Fr one{}; one[0] = 1;
+        Fr nine{}; nine[0] = 9;
+        if (out[0] != one || out[2] != one || out[4] != one || out[1] != nine) { fprintf(stderr, "FrProgram mismatch\n"); return 1; }
+        prog.instrs[1].a = 3;   // reads a register before it is written
+        threw = false;
+        try { prog.eval_batch(loader, in, 3); } catch (const Error&) { threw = true; }
+        if (!threw) { fprintf(stderr, "malformed program was accepted\n"); return 1; }
+    }
     printf("host mirror ok\n");
     return 0;
 }
