@@ -190,10 +190,13 @@ int snarkv_kzg_accumulators_from_limbs(snarkv_ctx* ctx, const uint8_t* limbs, si
  * proof runs it.  Instruction (op, dst, a, b), registers hold Fr values:
  *   INPUT dst <- inputs[proof][a]   CONST dst <- consts[a]   ADD/SUB/MUL dst <- reg[a] (op) reg[b]   NEG dst <- -reg[a]
  *   INV   dst <- 1 / reg[a], a zero stays zero (ScalarLoader::batch_invert, loader.rs:255-262 / util/arithmetic.rs:47-74).
+ *   NZ    dst <- reg[a] == 0 ? 1 : reg[a]       KEEPZ dst <- reg[b] == 0 ? 0 : reg[a]
+ *         (the two selects with which the host emits util/arithmetic.rs:47-69 `batch_invert` — skip the zeros, ONE inversion for
+ *         all denominators of a proof — as straight-line code)
  * `inputs`: m x n_inputs x 32 B, `consts`: n_consts x 32 B, `outputs`: m x n_out x 32 B (register out_regs[k] of every proof),
  * all in `format`.  Every register must be written before it is read (checked); dst, a, b < n_regs. */
 enum { SNARKV_FR_OP_INPUT = 0, SNARKV_FR_OP_CONST = 1, SNARKV_FR_OP_ADD = 2, SNARKV_FR_OP_SUB = 3, SNARKV_FR_OP_MUL = 4,
-       SNARKV_FR_OP_NEG = 5, SNARKV_FR_OP_INV = 6 };
+       SNARKV_FR_OP_NEG = 5, SNARKV_FR_OP_INV = 6, SNARKV_FR_OP_NZ = 7, SNARKV_FR_OP_KEEPZ = 8 };
 typedef struct snarkv_fr_instr { uint32_t op, dst, a, b; } snarkv_fr_instr;
 int snarkv_fr_program_eval_batch(snarkv_ctx* ctx, const snarkv_fr_instr* program, size_t n_instr, uint32_t n_regs, const uint8_t* consts,
                                  size_t n_consts, const uint8_t* inputs, size_t n_inputs, size_t m, const uint32_t* out_regs, size_t n_out,

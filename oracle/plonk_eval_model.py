@@ -143,6 +143,10 @@ def run_program(instrs, n_regs, consts, inputs, out_regs):
             v = (-reg[a]) % R
         elif op == 6:
             v = inv_or_zero(reg[a])
+        elif op == 7:
+            v = reg[a] if reg[a] else 1
+        elif op == 8:
+            v = reg[a] if reg[b] else 0
         else:
             raise ValueError(op)
         reg[dst] = v

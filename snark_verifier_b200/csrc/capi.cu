@@ -450,8 +450,8 @@ static int fr_program_stage(snarkv_ctx* ctx, const snarkv_fr_instr* program, siz
         switch (in.op) {
             case SNARKV_FR_OP_INPUT: ok = ok && in.a < n_inputs; break;
             case SNARKV_FR_OP_CONST: ok = ok && in.a < n_consts; break;
-            case SNARKV_FR_OP_ADD: case SNARKV_FR_OP_SUB: case SNARKV_FR_OP_MUL: ok = ok && src(in.a) && src(in.b); break;
-            case SNARKV_FR_OP_NEG: case SNARKV_FR_OP_INV: ok = ok && src(in.a); break;
+            case SNARKV_FR_OP_ADD: case SNARKV_FR_OP_SUB: case SNARKV_FR_OP_MUL: case SNARKV_FR_OP_KEEPZ: ok = ok && src(in.a) && src(in.b); break;
+            case SNARKV_FR_OP_NEG: case SNARKV_FR_OP_INV: case SNARKV_FR_OP_NZ: ok = ok && src(in.a); break;
             default: ok = false;
         }
         if (!ok) return ctx->fail(SNARKV_ERR_USAGE, "snarkv_fr_program_eval_batch: invalid instruction (opcode, operand out of range, or register read before it is written)");

@@ -15,6 +15,7 @@
 //   INPUT  dst <- inputs[proof][a]          CONST  dst <- consts[a]
 //   ADD    dst <- reg[a] + reg[b]           SUB    dst <- reg[a] - reg[b]         MUL  dst <- reg[a] * reg[b]
 //   NEG    dst <- -reg[a]                   INV    dst <- 1 / reg[a], and 0 when reg[a] = 0
+//   NZ     dst <- reg[a] == 0 ? 1 : reg[a]  KEEPZ  dst <- reg[b] == 0 ? 0 : reg[a]   (batch_invert's zero skipping as selects)
 // INV follows `ScalarLoader::batch_invert` (loader.rs:255-262 / util/arithmetic.rs:47-74): a zero is left untouched.
 // pow_const (loader.rs:52-69) needs no opcode: the host emits its exact square-and-multiply sequence as MULs.
 #include "ctx.hpp"
@@ -55,6 +56,13 @@ __global__ void __launch_bounds__(128) k_fr_program(const uint4* __restrict__ pr
             case SNARKV_FR_OP_SUB: v = fp_sub(fr_load_rw(reg(ins.z)), fr_load_rw(reg(ins.w))); break;
             case SNARKV_FR_OP_MUL: v = fp_mul(fr_load_rw(reg(ins.z)), fr_load_rw(reg(ins.w))); break;
             case SNARKV_FR_OP_NEG: v = fp_neg(fr_load_rw(reg(ins.z))); break;
+            case SNARKV_FR_OP_NZ:
+                v = fr_load_rw(reg(ins.z));
+                if (fp_is_zero(v)) v = fp_one<FR>();
+                break;
+            case SNARKV_FR_OP_KEEPZ:
+                v = fp_is_zero(fr_load_rw(reg(ins.w))) ? fp_zero<FR>() : fr_load_rw(reg(ins.z));
+                break;
             default: {   // SNARKV_FR_OP_INV (the host validated the opcodes)
                 v = fr_load_rw(reg(ins.z));
                 if (!fp_is_zero(v)) v = fp_inv_serial(v);

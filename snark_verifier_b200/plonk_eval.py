@@ -24,7 +24,7 @@ R_MODULUS = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
 FR_S = 28                                                                          # Fr::S
 FR_ROOT_OF_UNITY = 0x03DDB9F5166D18B798865EA93DD31F743215CF6DD39329C8D34F1ED960C37C9C  # Fr::ROOT_OF_UNITY = 7^((r-1)/2^28)
 
-OP_INPUT, OP_CONST, OP_ADD, OP_SUB, OP_MUL, OP_NEG, OP_INV = range(7)   # include/snarkv_cuda.h SNARKV_FR_OP_*
+OP_INPUT, OP_CONST, OP_ADD, OP_SUB, OP_MUL, OP_NEG, OP_INV, OP_NZ, OP_KEEPZ = range(9)   # include/snarkv_cuda.h SNARKV_FR_OP_*
 
 
 def root_of_unity(k: int) -> int:
@@ -188,7 +188,7 @@ class Program:
         self.outputs, self.output_names = outputs, output_names
 
     def op_histogram(self) -> Dict[str, int]:
-        names = ["input", "const", "add", "sub", "mul", "neg", "inv"]
+        names = ["input", "const", "add", "sub", "mul", "neg", "inv", "nz", "keepz"]
         h = {k: 0 for k in names}
         for op, _, _, _ in self.instrs:
             h[names[op]] += 1
@@ -234,6 +234,27 @@ class ProgramBuilder:
     def mul(self, a, b): return self._emit(OP_MUL, a, b)
     def neg(self, a): return self._emit(OP_NEG, a)
     def inv(self, a): return self._emit(OP_INV, a)
+    def nz(self, a): return self._emit(OP_NZ, a)
+    def keepz(self, a, b): return self._emit(OP_KEEPZ, a, b)
+
+    def batch_invert(self, values: Sequence[int]) -> List[int]:
+        """util/arithmetic.rs:47-74 (`batch_invert`, what NativeLoader's `ScalarLoader::batch_invert` calls) as straight-line code:
+        running products of the non-zero values, ONE inversion, back-substitution; a zero value stays zero.  The data-dependent
+        `filter(!is_zero)` becomes two selects: NZ feeds a 1 into the product in place of a zero, KEEPZ restores the zero."""
+        if not values:
+            return []
+        nzv = [self.nz(v) for v in values]
+        products = [nzv[0]]
+        for v in nzv[1:]:
+            products.append(self.mul(products[-1], v))
+        all_inv = self.inv(products[-1])
+        out = [None] * len(values)
+        for i in range(len(values) - 1, -1, -1):
+            inv_i = self.mul(all_inv, products[i - 1]) if i > 0 else all_inv
+            if i > 0:
+                all_inv = self.mul(all_inv, nzv[i])
+            out[i] = self.keepz(inv_i, values[i])
+        return out
 
     def pow_const(self, a: int, exp: int) -> int:
         """loader.rs:52-69, the same square-and-multiply order."""
@@ -254,9 +275,9 @@ class ProgramBuilder:
         n = len(self.ssa)
         last = list(range(n))                        # last SSA id that reads each value
         for i, (op, a, b) in enumerate(self.ssa):
-            if op in (OP_ADD, OP_SUB, OP_MUL):
+            if op in (OP_ADD, OP_SUB, OP_MUL, OP_KEEPZ):
                 last[a] = max(last[a], i); last[b] = max(last[b], i)
-            elif op in (OP_NEG, OP_INV):
+            elif op in (OP_NEG, OP_INV, OP_NZ):
                 last[a] = max(last[a], i)
         for o in outputs:
             last[o] = n                              # outputs live to the end
@@ -268,7 +289,7 @@ class ProgramBuilder:
         for i, (op, a, b) in enumerate(self.ssa):
             if op in (OP_INPUT, OP_CONST):
                 ra, rb = a, 0
-            elif op in (OP_NEG, OP_INV):
+            elif op in (OP_NEG, OP_INV, OP_NZ):
                 ra, rb = reg[a], 0
             else:
                 ra, rb = reg[a], reg[b]
@@ -295,8 +316,9 @@ class ProgramBuilder:
 # protocol.rs:211-283 and proof.rs:298-349 over the builder
 # ----------------------------------------------------------------------------------------------------------------------
 class CommonPolynomialEvaluation:
-    """protocol.rs:199-283 with `ProgramBuilder` values.  `new` + `evaluate` are folded into the constructor (the deferred
-    `Fraction` only exists to batch the inversions, which `INV` performs per value with the same zero-stays-zero rule)."""
+    """protocol.rs:199-283 with `ProgramBuilder` values: `new` collects the fractions, then — as PlonkVerifier does through
+    `denoms()` + `L::batch_invert` + `evaluate()` (verifier/plonk.rs, protocol.rs:263-282) — all denominators of a proof are
+    inverted together (Lagrange denominators in index order, then z^n - 1) and the fractions are evaluated."""
 
     def __init__(self, b: ProgramBuilder, domain: Domain, langranges, z: int):
         self.b = b
@@ -304,16 +326,17 @@ class CommonPolynomialEvaluation:
         lang = sorted(set(langranges))
         one = b.const(1)
         self.zn_minus_one = b.sub(self.zn, one)
-        self.zn_minus_one_inv = b.inv(self.zn_minus_one)            # Fraction::one_over(zn_minus_one), evaluated
         n_inv = b.const(domain.n_inv)
         numer = b.mul(self.zn_minus_one, n_inv)
         self.identity = z
-        self.lagrange = {}
+        numers, denoms = [], []
         for i in lang:
             omega = b.const(domain.rotate_scalar(1, Rotation(i)))
-            num_i = b.mul(numer, omega)                             # Fraction::new(numer * omega, z - omega)
-            den_i = b.sub(z, omega)
-            self.lagrange[i] = b.mul(num_i, b.inv(den_i))           # Fraction::evaluate: numer * denom^-1
+            numers.append(b.mul(numer, omega))                      # Fraction::new(numer * omega, z - omega)
+            denoms.append(b.sub(z, omega))
+        inv = b.batch_invert(denoms + [self.zn_minus_one])          # denoms(): lagrange values, then zn_minus_one_inv
+        self.zn_minus_one_inv = inv[-1]                             # Fraction::one_over(zn_minus_one), evaluated
+        self.lagrange = {i: b.mul(nu, dinv) for i, nu, dinv in zip(lang, numers, inv)}   # Fraction::evaluate: numer * denom^-1
 
     def get(self, poly: CommonPolynomial) -> int:
         return self.identity if poly.kind == "identity" else self.lagrange[poly.index]

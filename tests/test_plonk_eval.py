@@ -98,7 +98,8 @@ def test_standard_plonk_program_matches_oracle():
         p = pe.standard_plonk_like_protocol(k, num_instance=ninst)
         prog = pe.compile_quotient_evaluation(p)
         assert prog.n_inputs == p.input_layout()["total"]
-        assert prog.n_regs < 40, "liveness-based register reuse keeps the register file small"
+        assert prog.n_regs < 48, "liveness-based register reuse keeps the register file small"
+        assert prog.op_histogram()["inv"] == 1, "all denominators of a proof share ONE inversion (util/arithmetic.rs:47-69)"
         for row in rows_for(p, rng, 6):
             assert om.run_program(prog.instrs, prog.n_regs, prog.consts, row, prog.outputs) == oracle_row(p, row)
 
