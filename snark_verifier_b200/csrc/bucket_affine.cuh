@@ -21,7 +21,8 @@
 //
 // The kernel is co-limited: 79 % of the integer-multiplier pipe and 3.5 TB/s of DRAM traffic (gathers, tree levels, prefixes) at
 // 2^24 terms (profiles/r01_ncu_bucket_accumulate_affine_2p24.txt).  Measured and rejected: prefetch.global.L2 of the next pair's
-// operands (adds traffic: 34.3 -> 35.3 .. 37.4 ms), 5 or 6 resident blocks per SM (spills), K < 64 (more inversions).
+// operands (adds traffic: 34.3 -> 35.3 .. 37.4 ms), per-lane cp.async staging of the backward pass's operands one iteration ahead
+// (33.5 -> 34.5 ms), 5 or 6 resident blocks per SM (spills), K < 64 (more inversions).
 #pragma once
 #include "g1.cuh"
 
