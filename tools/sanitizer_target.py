@@ -34,4 +34,26 @@ kz.decide(kz.verify(accs, le(99)))
 ok, _ = kz.decide_all_fused(b"".join(a.lhs for a in accs), b"".join(a.rhs for a in accs), 4, le(31337))
 assert ok
 L.field_op(0, 3, le(5) * 4, le(5) * 4, 4)
+# batched-affine accumulation (forced: the sizes above choose XYZZ), with the task-level self-check against XYZZ (mode 3)
+for mode in (2, 3):
+    L.set_accumulate_mode(mode)
+    n = 6000
+    s = oracle.synth_scalars(8, 0, n); p = oracle.synth_points(8, 0, n, 4)
+    L.set_window_bits(6)                                                               # 32 buckets per window: long lists
+    assert L.msm(s, p, n) == oracle.msm_pippenger(s, p, n, 4), mode
+    L.set_window_bits(0)
+L.set_accumulate_mode(0)
+# rows f1-f3, a13: scalar preparation, transcript, scalar-evaluation program, limb decoding
+L.powers(le(7), 100); L.batch_invert(le(3) * 50 + le(0) * 2, 52); L.fr_mul_vec(le(3) * 10, le(4) * 10, 10)
+L.evm_transcript_challenges(bytes(range(64)) * 3, 64, [32, 64], 3)
+from snark_verifier_b200 import pcs, plonk_eval as pe
+proto = pe.standard_plonk_like_protocol(6, num_instance=2)
+prog = pe.compile_quotient_evaluation(proto)
+tot = proto.input_layout()["total"]
+L.fr_program_eval(prog, oracle.synth_scalars(6, 0, 70 * tot), 70)
+enc = pcs.LimbsEncoding(4, 68)
+rows = enc.to_repr(accs[0]) + enc.to_repr(accs[1])
+rows[3] ^= 1
+_, _, valid = enc.from_repr_batch(L, b"".join(le(v) for v in rows), 2)
+assert valid == b"\x00\x01"
 print("sanitizer target ok; launches:", L.launch_count)
