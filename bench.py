@@ -216,6 +216,21 @@ def kzg_aux(L, sv, torch, stream, dev):
                "decide_single_latency_ms": ms_one,
                "decide_all_fused": {"proofs_per_s": n / ms_fused * 1e3, "ms": ms_fused, "accept": bool(ok_fused),
                                     "what": "host buffers in; powers of rho + two 4096-term MSMs + one pairing (wall clock incl. H2D)"}}
+        # BASELINE config 4: one aggregation job = KzgAs::verify over 256 accumulators (accumulation.rs:41-63: two 256-term MSMs with
+        # the powers of r computed on the device) + one decide (decider.rs:70-82); host buffers in, wall clock
+        try:
+            n4 = 256
+            accs = [sv.KzgAccumulator(host_pts[64 * i:64 * i + 64].tobytes(), host_pts[64 * i:64 * i + 64].tobytes()) for i in range(n4)]
+            kz.decide(kz.verify(accs, rho))
+            t0 = time.perf_counter()
+            for _ in range(5):
+                kz.decide(kz.verify(accs, rho))
+            ms_job = (time.perf_counter() - t0) / 5 * 1e3
+            out["aggregate_256_then_decide"] = {"ms": ms_job, "jobs_per_s": 1e3 / ms_job,
+                                                "what": "KzgAs::verify over 256 accumulators + decide, one job at a time (single-job latency; "
+                                                        "independent jobs go to different GPUs: replicas only)"}
+        except Exception as e:
+            out["aggregate_256_then_decide"] = {"error": repr(e)}
         # rows f3 / a13 of SURVEY.md §8: the per-proof scalar evaluation and the limb decoding that sit either side of the path
         try:
             from snark_verifier_b200 import plonk_eval as pe

@@ -257,3 +257,45 @@ class LimbsEncoding:
         """m accumulators at once on the device (snarkv_kzg_accumulators_from_limbs): limbs = m x 4 LIMBS x 32 B scalars in the
         loader's format -> (lhs m x 64 B, rhs m x 64 B, valid m bytes); valid[i] = 0 where the reference would panic."""
         return loader.accumulators_from_limbs(limbs, m, self.limbs, self.bits)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# m proofs of ONE protocol at once (BASELINE config 3): scalars by a device program, one fused MSM per side, one pairing
+# ----------------------------------------------------------------------------------------------------------------------
+class Gwc19BatchVerifier:
+    """`Gwc19::verify` + the RLC `decide_all` of pcs/kzg/decider.rs:146-185 for a batch of proofs that share a protocol:
+      1. the MSM scalars of every proof — gwc19.rs:52-81 compiled once to a straight-line Fr program (plonk_eval.py) — on the device;
+      2. lhs = sum_j rho^j lhs_j and rhs = sum_j rho^j rhs_j, each as ONE Pippenger pass (snarkv_g1_msm_batch_rlc);
+      3. one pairing check e(lhs, g2) e(rhs, -s g2) == 1.
+    Per-proof data: z, v, u, the evaluations in query order, the commitments, the opening-proof points W."""
+
+    def __init__(self, loader, kzg, svk_g: bytes, queries: Sequence[tuple], num_polys: int):
+        from .plonk_eval import compile_gwc19_msm_scalars
+        self.loader, self.kzg, self.g = loader, kzg, bytes(svk_g)
+        self.compiled = compile_gwc19_msm_scalars(queries, num_polys)
+
+    def _points(self, slots, proof):
+        out = []
+        for s in slots:
+            out.append(self.g if s == ("g",) else proof["commitments"][s[1]] if s[0] == "c" else proof["ws"][s[1]])
+        return b"".join(out)
+
+    def accumulate(self, proofs: Sequence[dict], rho: int) -> KzgAccumulator:
+        cp, m = self.compiled, len(proofs)
+        le = lambda v: (v % R_MODULUS).to_bytes(32, "little")
+        rows = b"".join(le(p["z"]) + le(p["v"]) + le(p["u"]) + b"".join(le(e) for e in p["evals"]) for p in proofs)
+        scal = self.loader.fr_program_eval(cp.program, rows, m)
+        nl, nr = len(cp.lhs_slots), len(cp.rhs_slots)
+        stride = 32 * (nl + nr)
+        lhs_s = b"".join(scal[j * stride:j * stride + 32 * nl] for j in range(m))
+        rhs_s = b"".join(scal[j * stride + 32 * nl:(j + 1) * stride] for j in range(m))
+        lhs_p = b"".join(self._points(cp.lhs_slots, p) for p in proofs)
+        rhs_p = b"".join(self._points(cp.rhs_slots, p) for p in proofs)
+        rho_b = le(rho)
+        lhs = self.loader.msm_batch_rlc(lhs_s, lhs_p, [nl * j for j in range(m + 1)], rho_b)
+        rhs = self.loader.msm_batch_rlc(rhs_s, rhs_p, [nr * j for j in range(m + 1)], rho_b)
+        return KzgAccumulator(lhs, rhs)
+
+    def verify_batch(self, proofs: Sequence[dict], rho: int):
+        """Raises AssertionFailure (decider.rs:81) unless the random linear combination of all proofs decides."""
+        self.kzg.decide(self.accumulate(proofs, rho))

@@ -469,3 +469,123 @@ def standard_plonk_like_protocol(k: int, num_instance: int = 1, blinding_factors
     evaluations = [Q(i, Rotation(0)) for i in range(8)] + [Q(9 + i, Rotation(0)) for i in range(3)] + [Q(12, Rotation(0)), Q(12, Rotation(1))]
     return QuotientProtocol(domain=Domain(k), num_preprocessed=8, num_instance=[num_instance], evaluations=evaluations, num_challenge=4,
                             numerator=E.distribute_powers(constraints, alpha))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# the multi-open verifier's MSM scalars as a program: `Msm` (util/msm.rs) over virtual registers
+# ----------------------------------------------------------------------------------------------------------------------
+class SymbolicMsm:
+    """util/msm.rs:20-226 with ProgramBuilder values as scalars and BASE SLOTS (small integers) instead of curve points: the
+    bases of a proof differ from proof to proof, the slot a base occupies in the final MSM does not.  `push` dedupes by slot, as
+    the reference dedupes by point equality (msm.rs:109-116)."""
+
+    def __init__(self, b: ProgramBuilder, constant=None, terms=None):
+        self.b, self.constant, self.terms = b, constant, dict(terms or {})     # terms: slot -> scalar value (insertion ordered)
+
+    @staticmethod
+    def base(b, slot):
+        return SymbolicMsm(b, None, {slot: b.const(1)})
+
+    @staticmethod
+    def constant_(b, value):
+        return SymbolicMsm(b, value)
+
+    def scale(self, k):
+        c = None if self.constant is None else self.b.mul(self.constant, k)
+        return SymbolicMsm(self.b, c, {s: self.b.mul(v, k) for s, v in self.terms.items()})
+
+    def __mul__(self, k):
+        return self.scale(k)
+
+    def __neg__(self):
+        return SymbolicMsm(self.b, None if self.constant is None else self.b.neg(self.constant), {s: self.b.neg(v) for s, v in self.terms.items()})
+
+    def __add__(self, o):
+        if self.constant is None:
+            c = o.constant
+        elif o.constant is None:
+            c = self.constant
+        else:
+            c = self.b.add(self.constant, o.constant)
+        t = dict(self.terms)
+        for s, v in o.terms.items():
+            t[s] = self.b.add(t[s], v) if s in t else v
+        return SymbolicMsm(self.b, c, t)
+
+    def __sub__(self, o):
+        return self + (-o)
+
+    @staticmethod
+    def sum(b, msms):
+        acc = SymbolicMsm(b)
+        for m in msms:
+            acc = acc + m
+        return acc
+
+
+def _powers(b: ProgramBuilder, x: int, n: int) -> List[int]:
+    """loader.rs:71-78"""
+    out = [b.const(1)]
+    if n > 1:
+        out.append(x)
+    for _ in range(2, n):
+        out.append(b.mul(out[-1], x))
+    return out[:n]
+
+
+@dataclass
+class MsmScalarProgram:
+    """`program` outputs, per proof, the scalars of the lhs MSM followed by those of the rhs MSM; `lhs_slots` / `rhs_slots` name
+    the base behind each scalar: ("g",) = the SRS generator (carries the Msm constant, msm.rs:81-98), ("c", poly) = commitment of
+    polynomial `poly`, ("w", i) = the i-th opening proof point."""
+    program: Program
+    lhs_slots: List[tuple]
+    rhs_slots: List[tuple]
+    input_layout: Dict[str, int]
+
+
+def compile_gwc19_msm_scalars(queries: Sequence[Tuple[int, int]], num_polys: int) -> MsmScalarProgram:
+    """`Gwc19::verify` (pcs/kzg/multiopen/gwc19.rs:45-82) as a program.  `queries`: (poly, shift) in protocol order; every
+    commitment is a plain base (`Msm::base`), which is what the halo2 system produces without linearization.  Per-proof input row:
+    [z | v | u | one evaluation per query, in query order]."""
+    b = ProgramBuilder()
+    lay = {"z": 0, "v": 1, "u": 2, "evals": 3, "total": 3 + len(queries)}
+    z, v, u = b.input(0), b.input(1), b.input(2)
+    sets = []                                                           # gwc19.rs:140-160
+    for k, (poly, shift) in enumerate(queries):
+        ev = b.input(lay["evals"] + k)
+        for st in sets:
+            if st["shift"] == shift:
+                st["polys"].append(poly); st["evals"].append(ev)
+                break
+        else:
+            sets.append({"shift": shift, "polys": [poly], "evals": [ev]})
+    powers_of_u = _powers(b, u, len(sets))
+    powers_of_v = _powers(b, v, max(len(st["polys"]) for st in sets))
+    commitments = [SymbolicMsm.base(b, ("c", j)) for j in range(num_polys)]
+    f = SymbolicMsm(b)
+    for st, pu in zip(sets, powers_of_u):
+        set_msm = SymbolicMsm(b)
+        for poly, ev, pv in zip(st["polys"], st["evals"], powers_of_v):
+            set_msm = set_msm + (commitments[poly] - SymbolicMsm.constant_(b, ev)) * pv
+        f = f + set_msm * pu
+    z_omegas = [b.mul(b.const(st["shift"]), z) for st in sets]
+    rhs = [SymbolicMsm.base(b, ("w", i)) * pu for i, pu in enumerate(powers_of_u)]
+    lhs = f + SymbolicMsm.sum(b, [uw * zo for uw, zo in zip(rhs, z_omegas)])
+    rhs_sum = SymbolicMsm.sum(b, rhs)
+    return _finish_msm_program(b, lhs, rhs_sum, lay)
+
+
+def _finish_msm_program(b, lhs: SymbolicMsm, rhs: SymbolicMsm, lay) -> MsmScalarProgram:
+    def flat(m):
+        slots, vals = [], []
+        if m.constant is not None:                                      # evaluate(Some(gen)): (constant, gen) goes first
+            slots.append(("g",)); vals.append(m.constant)
+        for s, v in m.terms.items():
+            slots.append(s); vals.append(v)
+        return slots, vals
+    ls, lv = flat(lhs)
+    rs, rv = flat(rhs)
+    b.n_inputs = lay["total"]
+    prog = b.finish(lv + rv, ["lhs%d" % i for i in range(len(lv))] + ["rhs%d" % i for i in range(len(rv))])
+    return MsmScalarProgram(prog, ls, rs, lay)

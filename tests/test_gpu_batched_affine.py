@@ -113,6 +113,32 @@ def test_full_size_dlog_checksum(loader, mode, logn):
     assert bytes(out.cpu().numpy()) == oracle.msm_expected_from_dlogs(ds.cpu().numpy(), t, n)
 
 
+def test_headline_size_device_and_host_paths_checksum():
+    """2^24 terms (BASELINE.json's headline size) with the library's own choices: the device-resident path picks the batched-affine
+    kernel, the host entry point runs its term-chunk pipeline in which small chunks use XYZZ and large ones the affine kernel, all
+    accumulating into the same buckets.  Both must equal the discrete-log checksum [sum s_i t_i] G."""
+    import torch
+    L = sv.CudaLoader(0)
+    try:
+        n = 1 << 24
+        ds = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
+        dp = torch.empty(n * 64, dtype=torch.uint8, device="cuda")
+        out = torch.zeros(64, dtype=torch.uint8, device="cuda")
+        L.synth_scalars_device(91, 0, n, ds.data_ptr())
+        L.synth_points_device(91, 0, n, dp.data_ptr())
+        L.profile(True)
+        L.msm_device(ds.data_ptr(), dp.data_ptr(), n, d_out_affine=out.data_ptr())
+        torch.cuda.synchronize()
+        assert any(name == "msm_bucket_accumulate_affine" for name, _, _ in L.stage_times())
+        L.profile(False)
+        hs, hp = ds.cpu().numpy(), dp.cpu().numpy()
+        exp = oracle.msm_expected_from_dlogs(hs, oracle.synth_point_scalars(91, 0, n), n)
+        assert bytes(out.cpu().numpy()) == exp
+        assert L.msm(hs, hp, n) == exp
+    finally:
+        L.close()
+
+
 def test_heavily_skewed_large(loader):
     """2^20 terms with scalar 1: one bucket holds every term -> thousands of full-length tasks, all levels of the tree."""
     import torch

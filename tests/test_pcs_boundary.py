@@ -37,9 +37,11 @@ def poly_eval(coeffs, x):
     return acc
 
 
-def make_fixture(seed=0, num_polys=17, k=8, tamper=False):
+def make_fixture(seed=0, num_polys=17, k=8, tamper=False, srs_seed=None):
     rnd = random.Random(seed)
     s = rnd.randrange(2, R)
+    if srs_seed is not None:                                       # several proofs under ONE SRS (batch verification)
+        s = random.Random(srs_seed).randrange(2, R)
     g2 = oracle.g2_generator()
     s_g2 = oracle.g2_mul(g2, le(s))
     polys = [[rnd.randrange(R) for _ in range(1 << k)] for _ in range(num_polys)]

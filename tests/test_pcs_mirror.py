@@ -190,7 +190,76 @@ def test_limbs_encoding_round_trip_and_rejections():
         enc.from_repr(wide)
 
 
+def test_gwc19_msm_scalar_program_equals_host_mirror():
+    """gwc19.rs:52-81 compiled to a straight-line program (SymbolicMsm over virtual registers) must produce exactly the
+    (scalar, base) pairs — same order, same values — that the host mirror hands to multi_scalar_multiplication."""
+    from oracle import plonk_eval_model as om
+    from snark_verifier_b200 import plonk_eval as pe
+    rnd = random.Random(4)
+    omega = pe.root_of_unity(8)
+    shifts = [1, omega, pow(omega, -1, R)]
+    structure = [(j, shifts[(j * 7) % 3]) for j in range(17)] + [(3, shifts[1]), (5, shifts[2])]    # some polys at two points
+    mp = pe.compile_gwc19_msm_scalars(structure, 17)
+    z, v, u = (rnd.randrange(R) for _ in range(3))
+    evals = [rnd.randrange(R) for _ in structure]
+    C = [bytes([j + 1]) * 64 for j in range(17)]
+    W = [bytes([100 + i]) * 64 for i in range(3)]
+    G = bytes([255]) * 64
+    calls = []
+
+    class Recorder:
+        fmt = sv.CANONICAL
+
+        def multi_scalar_multiplication(self, pairs):
+            calls.append([(int.from_bytes(sc, "little"), pt) for sc, pt in pairs])
+            return bytes(64)
+    L = Recorder()
+    pcs.Gwc19.verify(L, G, [sv.Msm.base(L, c) for c in C], z, [pcs.Query(p, sh, e) for (p, sh), e in zip(structure, evals)],
+                     pcs.Gwc19Proof(v, W, u))
+    out = om.run_program(mp.program.instrs, mp.program.n_regs, mp.program.consts, [z, v, u] + evals, mp.program.outputs)
+    pt = lambda sl: G if sl == ("g",) else (C[sl[1]] if sl[0] == "c" else W[sl[1]])
+    nl = len(mp.lhs_slots)
+    assert [(out[i], pt(sl)) for i, sl in enumerate(mp.lhs_slots)] == calls[0]
+    assert [(out[nl + i], pt(sl)) for i, sl in enumerate(mp.rhs_slots)] == calls[1]
+    assert nl == 21 and len(mp.rhs_slots) == 3
+
+
 # ---- GPU ----------------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_gwc19_batch_verifier_pipeline_on_device():
+    """BASELINE config 3 with REAL GWC19 structure: m proofs under one SRS -> MSM scalars by the device program -> one fused MSM per
+    side (powers of rho) -> one pairing.  The fused accumulator must equal the RLC of the per-proof accumulators of the host
+    mirror (NativeLoader fold), the batch must accept, and one tampered evaluation must make it reject."""
+    m_proofs, srs = 24, 4242
+    fxs = [make_fixture(seed=100 + j, k=5, srs_seed=srs) for j in range(m_proofs)]
+    zinv = [pow(fx["points"][0], -1, R) for fx in fxs]
+    shifts = [p * zinv[0] % R for p in fxs[0]["points"]]
+    structure = [(j, shifts[j % 3]) for j in range(17)]
+
+    def as_proof(fx):
+        return dict(z=fx["points"][0], v=fx["v"], u=fx["u"], evals=[fx["evals"][j] for j in range(17)], commitments=fx["C"], ws=fx["W"])
+    L = sv.CudaLoader(0)
+    try:
+        kz = sv.KzgAs(L, sv.KzgDecidingKey(GEN, fxs[0]["g2"], fxs[0]["s_g2"]))
+        bv = pcs.Gwc19BatchVerifier(L, kz, GEN, structure, 17)
+        rho = 0x1F2E3D4C5B6A79880123456789ABCDEF
+        fused = bv.accumulate([as_proof(fx) for fx in fxs], rho)
+        N = OracleNativeLoader()
+        per = [pcs.Gwc19.verify(N, GEN, [sv.Msm.base(N, c) for c in fx["C"]], fx["points"][0], gwc19_queries(fx),
+                                pcs.Gwc19Proof(fx["v"], fx["W"], fx["u"])) for fx in fxs]
+        rs = b"".join(le(pow(rho, j, R)) for j in range(m_proofs))
+        assert fused.lhs == oracle.msm_native(rs, b"".join(a.lhs for a in per), m_proofs)
+        assert fused.rhs == oracle.msm_native(rs, b"".join(a.rhs for a in per), m_proofs)
+        bv.verify_batch([as_proof(fx) for fx in fxs], rho)
+        bad = [as_proof(fx) for fx in fxs]
+        bad[7] = as_proof(make_fixture(seed=107, k=5, srs_seed=srs, tamper=True))
+        with pytest.raises(sv.AssertionFailure):
+            bv.verify_batch(bad, rho)
+    finally:
+        L.close()
+
+
+
 @pytest.mark.gpu
 def test_multiopen_verifiers_on_cuda_loader():
     L = sv.CudaLoader(0)
