@@ -262,17 +262,22 @@ class LimbsEncoding:
 # ----------------------------------------------------------------------------------------------------------------------
 # m proofs of ONE protocol at once (BASELINE config 3): scalars by a device program, one fused MSM per side, one pairing
 # ----------------------------------------------------------------------------------------------------------------------
-class Gwc19BatchVerifier:
-    """`Gwc19::verify` + the RLC `decide_all` of pcs/kzg/decider.rs:146-185 for a batch of proofs that share a protocol:
-      1. the MSM scalars of every proof — gwc19.rs:52-81 compiled once to a straight-line Fr program (plonk_eval.py) — on the device;
+class KzgBatchVerifier:
+    """`Gwc19::verify` / `Bdfg21::verify` + the RLC `decide_all` of pcs/kzg/decider.rs:146-185 for a batch of proofs that share a
+    protocol:
+      1. the MSM scalars of every proof — the verifier's `Msm` algebra (gwc19.rs:52-81 / bdfg21.rs:58-82 with its coefficient
+         computation) compiled once to a straight-line Fr program (plonk_eval.py) — on the device;
       2. lhs = sum_j rho^j lhs_j and rhs = sum_j rho^j rhs_j, each as ONE Pippenger pass (snarkv_g1_msm_batch_rlc);
       3. one pairing check e(lhs, g2) e(rhs, -s g2) == 1.
-    Per-proof data: z, v, u, the evaluations in query order, the commitments, the opening-proof points W."""
+    Per-proof data (dict): "commitments", "evals" (query order), "ws" (opening-proof points: W_0.. for GWC19, [W, W'] for
+    SHPLONK) and the scalars "z", "v", "u" (GWC19) or "z", "mu", "gamma", "z_prime" (SHPLONK)."""
 
-    def __init__(self, loader, kzg, svk_g: bytes, queries: Sequence[tuple], num_polys: int):
-        from .plonk_eval import compile_gwc19_msm_scalars
-        self.loader, self.kzg, self.g = loader, kzg, bytes(svk_g)
-        self.compiled = compile_gwc19_msm_scalars(queries, num_polys)
+    SCALARS = {"gwc19": ("z", "v", "u"), "bdfg21": ("z", "mu", "gamma", "z_prime")}
+
+    def __init__(self, loader, kzg, svk_g: bytes, queries: Sequence[tuple], num_polys: int, scheme: str = "gwc19"):
+        from .plonk_eval import compile_bdfg21_msm_scalars, compile_gwc19_msm_scalars
+        self.loader, self.kzg, self.g, self.scheme = loader, kzg, bytes(svk_g), scheme
+        self.compiled = {"gwc19": compile_gwc19_msm_scalars, "bdfg21": compile_bdfg21_msm_scalars}[scheme](queries, num_polys)
 
     def _points(self, slots, proof):
         out = []
@@ -283,19 +288,35 @@ class Gwc19BatchVerifier:
     def accumulate(self, proofs: Sequence[dict], rho: int) -> KzgAccumulator:
         cp, m = self.compiled, len(proofs)
         le = lambda v: (v % R_MODULUS).to_bytes(32, "little")
-        rows = b"".join(le(p["z"]) + le(p["v"]) + le(p["u"]) + b"".join(le(e) for e in p["evals"]) for p in proofs)
-        scal = self.loader.fr_program_eval(cp.program, rows, m)
-        nl, nr = len(cp.lhs_slots), len(cp.rhs_slots)
-        stride = 32 * (nl + nr)
-        lhs_s = b"".join(scal[j * stride:j * stride + 32 * nl] for j in range(m))
-        rhs_s = b"".join(scal[j * stride + 32 * nl:(j + 1) * stride] for j in range(m))
+        rows = b"".join(b"".join(le(p[k]) for k in self.SCALARS[self.scheme]) + b"".join(le(e) for e in p["evals"]) for p in proofs)
         lhs_p = b"".join(self._points(cp.lhs_slots, p) for p in proofs)
         rhs_p = b"".join(self._points(cp.rhs_slots, p) for p in proofs)
-        rho_b = le(rho)
-        lhs = self.loader.msm_batch_rlc(lhs_s, lhs_p, [nl * j for j in range(m + 1)], rho_b)
-        rhs = self.loader.msm_batch_rlc(rhs_s, rhs_p, [nr * j for j in range(m + 1)], rho_b)
+        return self.accumulate_packed(rows, lhs_p, rhs_p, m, rho)
+
+    def accumulate_packed(self, rows, lhs_points, rhs_points, m: int, rho: int) -> KzgAccumulator:
+        """The same on packed arrays (bytes or numpy uint8): `rows` = m x program inputs x 32 B, `lhs_points` / `rhs_points` = the
+        bases of every proof in `compiled.lhs_slots` / `rhs_slots` order, m x slots x 64 B."""
+        import numpy as np
+        cp = self.compiled
+        nl, nr = len(cp.lhs_slots), len(cp.rhs_slots)
+        scal = np.frombuffer(self.loader.fr_program_eval(cp.program, rows, m), dtype=np.uint8).reshape(m, nl + nr, 32)
+        lhs_s = np.ascontiguousarray(scal[:, :nl]).reshape(-1)
+        rhs_s = np.ascontiguousarray(scal[:, nl:]).reshape(-1)
+        rho_b = (rho % R_MODULUS).to_bytes(32, "little")
+        lhs = self.loader.msm_batch_rlc(lhs_s, lhs_points, np.arange(m + 1, dtype=np.uint64) * nl, rho_b)
+        rhs = self.loader.msm_batch_rlc(rhs_s, rhs_points, np.arange(m + 1, dtype=np.uint64) * nr, rho_b)
         return KzgAccumulator(lhs, rhs)
 
     def verify_batch(self, proofs: Sequence[dict], rho: int):
         """Raises AssertionFailure (decider.rs:81) unless the random linear combination of all proofs decides."""
         self.kzg.decide(self.accumulate(proofs, rho))
+
+
+class Gwc19BatchVerifier(KzgBatchVerifier):
+    def __init__(self, loader, kzg, svk_g, queries, num_polys):
+        super().__init__(loader, kzg, svk_g, queries, num_polys, "gwc19")
+
+
+class Bdfg21BatchVerifier(KzgBatchVerifier):
+    def __init__(self, loader, kzg, svk_g, queries, num_polys):
+        super().__init__(loader, kzg, svk_g, queries, num_polys, "bdfg21")

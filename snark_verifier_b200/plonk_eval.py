@@ -589,3 +589,106 @@ def _finish_msm_program(b, lhs: SymbolicMsm, rhs: SymbolicMsm, lay) -> MsmScalar
     b.n_inputs = lay["total"]
     prog = b.finish(lv + rv, ["lhs%d" % i for i in range(len(lv))] + ["rhs%d" % i for i in range(len(rv))])
     return MsmScalarProgram(prog, ls, rs, lay)
+
+
+def compile_bdfg21_msm_scalars(queries: Sequence[Tuple[int, int]], num_polys: int) -> MsmScalarProgram:
+    """`Bdfg21::verify` (pcs/kzg/multiopen/bdfg21.rs:51-83; query sets :123-175, coefficients :177-371) as a program.  `queries`:
+    (poly, shift) in protocol order.  Per-proof input row: [z | mu | gamma | z' | one evaluation per query, in query order].
+    Opening-proof slots: ("w", 0) = W, ("w", 1) = W'.  The shift arithmetic (normalised ell', set grouping) depends only on the
+    protocol and is done here on the host; everything that depends on z, z', mu, gamma or the evaluations becomes instructions,
+    with the two rounds of `L::batch_invert` (bdfg21.rs:218-219) as two shared inversions."""
+    R = R_MODULUS
+    b = ProgramBuilder()
+    lay = {"z": 0, "mu": 1, "gamma": 2, "z_prime": 3, "evals": 4, "total": 4 + len(queries)}
+    z, mu, gamma, z_prime = (b.input(i) for i in range(4))
+    # ---- query_sets (bdfg21.rs:123-175) on (poly, shift, eval register) ----
+    poly_shifts = []
+    for k, (poly, shift) in enumerate(queries):
+        ev = b.input(lay["evals"] + k)
+        for ps in poly_shifts:
+            if ps[0] == poly:
+                if shift not in ps[1]:
+                    ps[1].append(shift); ps[2].append(ev)
+                break
+        else:
+            poly_shifts.append((poly, [shift], [ev]))
+    sets = []
+    for poly, shifts, evals in poly_shifts:
+        for st in sets:
+            if set(st["shifts"]) == set(shifts):
+                if poly not in st["polys"]:
+                    st["polys"].append(poly)
+                    st["evals"].append([evals[shifts.index(lhs)] for lhs in st["shifts"]])
+                break
+        else:
+            sets.append({"shifts": shifts, "polys": [poly], "evals": [evals]})
+    # ---- query_set_coeffs (bdfg21.rs:177-222) ----
+    superset = sorted({s for st in sets for s in st["shifts"]})
+    size = max([len(st["shifts"]) for st in sets] + [2])
+    powers_of_z = _powers(b, z, size)
+    zp_minus = {s: b.sub(z_prime, b.mul(z, b.const(s))) for s in superset}
+    coeffs, z_s_1 = [], None
+    for st in sets:
+        shifts = st["shifts"]
+        ell = []
+        for j, sj in enumerate(shifts):
+            acc = 1
+            for i, si in enumerate(shifts):
+                if i != j:
+                    acc = acc * (sj - si) % R
+            ell.append(acc)
+        zz, z_pow = powers_of_z[1], powers_of_z[len(shifts) - 1]
+        bary = []
+        for s, e in zip(shifts, ell):                                   # sum_products_with_coeff (bdfg21.rs:297-302)
+            t1 = b.mul(b.mul(z_pow, z_prime), b.const(e))
+            t2 = b.mul(b.mul(z_pow, zz), b.const((-(e * s)) % R))
+            bary.append(b.add(t1, t2))
+        z_s = None
+        for s in shifts:                                                # loader.product (bdfg21.rs:307-312)
+            z_s = zp_minus[s] if z_s is None else b.mul(z_s, zp_minus[s])
+        coeffs.append({"bary": bary, "z_s": z_s, "z_s_1": z_s_1})
+        if z_s_1 is None:
+            z_s_1 = z_s
+    # first batch_invert: barycentric weights (+ z_s of every set but the first)
+    den1 = []
+    for c in coeffs:
+        den1 += c["bary"] + ([c["z_s"]] if c["z_s_1"] is not None else [])
+    inv1 = b.batch_invert(den1)
+    k = 0
+    den2 = []
+    for c in coeffs:
+        n = len(c["bary"])
+        c["eval_coeffs"] = inv1[k:k + n]                                # Fraction::one_over(..).evaluate()
+        k += n
+        if c["z_s_1"] is not None:
+            c["commitment_coeff"] = b.mul(c["z_s_1"], inv1[k])          # Fraction::new(z_s_1, z_s).evaluate()
+            k += 1
+        else:
+            c["commitment_coeff"] = None
+        wsum = None
+        for w in c["eval_coeffs"]:                                      # loader.sum (bdfg21.rs:345-351)
+            wsum = w if wsum is None else b.add(wsum, w)
+        den2.append(wsum)
+    inv2 = b.batch_invert(den2)                                         # second batch_invert: the r_eval coefficients
+    for c, iv in zip(coeffs, inv2):
+        c["r_eval_coeff"] = iv if c["commitment_coeff"] is None else b.mul(c["commitment_coeff"], iv)
+    # ---- verify (bdfg21.rs:58-82) ----
+    powers_of_mu = _powers(b, mu, max(len(st["polys"]) for st in sets))
+    powers_of_gamma = _powers(b, gamma, len(sets))
+    commitments = [SymbolicMsm.base(b, ("c", j)) for j in range(num_polys)]
+    f = SymbolicMsm(b)
+    for st, co, pg in zip(sets, coeffs, powers_of_gamma):
+        set_msm = SymbolicMsm(b)
+        for poly, evals, pm in zip(st["polys"], st["evals"], powers_of_mu):
+            commitment = commitments[poly] * co["commitment_coeff"] if co["commitment_coeff"] is not None else commitments[poly]
+            r_eval = None
+            for cf, ev in zip(co["eval_coeffs"], evals):               # loader.sum_products
+                t = b.mul(cf, ev)
+                r_eval = t if r_eval is None else b.add(r_eval, t)
+            r_eval = b.mul(r_eval, co["r_eval_coeff"])
+            set_msm = set_msm + (commitment - SymbolicMsm.constant_(b, r_eval)) * pm
+        f = f + set_msm * pg
+    f = f - SymbolicMsm.base(b, ("w", 0)) * coeffs[0]["z_s"]
+    rhs = SymbolicMsm.base(b, ("w", 1))
+    lhs = f + rhs * z_prime
+    return _finish_msm_program(b, lhs, rhs, lay)

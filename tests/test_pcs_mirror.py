@@ -77,9 +77,11 @@ def vanishing(xs):
 
 
 # ---- SHPLONK fixture (prover follows eprint 2020/081 §4 as halo2's shplonk does; verifier = Bdfg21::verify) ------------------
-def make_shplonk_fixture(seed=0, k=5, tamper=False):
+def make_shplonk_fixture(seed=0, k=5, tamper=False, srs_seed=None, shuffle_seed=None):
     rnd = random.Random(seed)
     s = rnd.randrange(2, R)
+    if srs_seed is not None:                                 # several proofs under ONE SRS (batch verification)
+        s = random.Random(srs_seed).randrange(2, R)
     g2 = oracle.g2_generator()
     s_g2 = oracle.g2_mul(g2, le(s))
     commit = lambda v: oracle.g1_mul(GEN, le(v % R))
@@ -93,7 +95,7 @@ def make_shplonk_fixture(seed=0, k=5, tamper=False):
     for j, shs in enumerate(shifts_of):                     # interleave like protocol.queries would: by polynomial, then shift
         for sh in shs:
             queries.append(pcs.Query(j, sh, p_eval(polys[j], z * sh % R)))
-    rnd.shuffle(queries)
+    (random.Random(shuffle_seed) if shuffle_seed is not None else rnd).shuffle(queries)   # a batch shares ONE query order
     mu, gamma, z_prime = rnd.randrange(R), rnd.randrange(R), rnd.randrange(R)
     sets = pcs.Bdfg21.query_sets(queries)                   # the prover groups exactly like the verifier
     h = [0]
@@ -224,7 +226,68 @@ def test_gwc19_msm_scalar_program_equals_host_mirror():
     assert nl == 21 and len(mp.rhs_slots) == 3
 
 
+def test_bdfg21_msm_scalar_program_equals_host_mirror():
+    """bdfg21.rs:51-83 + :177-371 compiled to a straight-line program: same (scalar, base) pairs as the host mirror, two shared
+    inversions (the two `L::batch_invert` rounds)."""
+    from oracle import plonk_eval_model as om
+    from snark_verifier_b200 import plonk_eval as pe
+    for seed in (0, 3):
+        fx = make_shplonk_fixture(seed)
+        structure = [(q.poly, q.shift) for q in fx["queries"]]
+        mp = pe.compile_bdfg21_msm_scalars(structure, len(fx["C"]))
+        assert mp.program.op_histogram()["inv"] == 2
+        calls = []
+
+        class Recorder:
+            fmt = sv.CANONICAL
+
+            def multi_scalar_multiplication(self, pairs):
+                calls.append([(int.from_bytes(sc, "little"), pt) for sc, pt in pairs])
+                return bytes(64)
+        bdfg21_accumulator(Recorder(), fx)
+        pr = fx["proof"]
+        row = [fx["z"], pr.mu, pr.gamma, pr.z_prime] + [q.eval for q in fx["queries"]]
+        out = om.run_program(mp.program.instrs, mp.program.n_regs, mp.program.consts, row, mp.program.outputs)
+        pt = lambda sl: GEN if sl == ("g",) else (fx["C"][sl[1]] if sl[0] == "c" else (pr.w, pr.w_prime)[sl[1]])
+        nl = len(mp.lhs_slots)
+        assert [(out[i], pt(sl)) for i, sl in enumerate(mp.lhs_slots)] == calls[0]
+        assert [(out[nl + i], pt(sl)) for i, sl in enumerate(mp.rhs_slots)] == calls[1]
+
+
 # ---- GPU ----------------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_bdfg21_batch_verifier_pipeline_on_device():
+    """The SHPLONK twin of the test below: m honest proofs (real polynomial divisions) under one SRS, scalars by the device program
+    (two shared inversions per proof), one fused MSM per side, one pairing; fused accumulator == RLC of the host mirror's."""
+    m_proofs, srs = 12, 777
+    fxs = [make_shplonk_fixture(seed=200 + j, srs_seed=srs, shuffle_seed=9) for j in range(m_proofs)]
+    structure = [(q.poly, q.shift) for q in fxs[0]["queries"]]
+    assert all([(q.poly, q.shift) for q in fx["queries"]] == structure for fx in fxs)
+
+    def as_proof(fx):
+        pr = fx["proof"]
+        return dict(z=fx["z"], mu=pr.mu, gamma=pr.gamma, z_prime=pr.z_prime, evals=[q.eval for q in fx["queries"]],
+                    commitments=fx["C"], ws=[pr.w, pr.w_prime])
+    L = sv.CudaLoader(0)
+    try:
+        kz = sv.KzgAs(L, sv.KzgDecidingKey(GEN, fxs[0]["g2"], fxs[0]["s_g2"]))
+        bv = pcs.Bdfg21BatchVerifier(L, kz, GEN, structure, len(fxs[0]["C"]))
+        rho = 0x0F1E2D3C4B5A69788796A5B4C3D2E1F0
+        fused = bv.accumulate([as_proof(fx) for fx in fxs], rho)
+        N = OracleNativeLoader()
+        per = [bdfg21_accumulator(N, fx) for fx in fxs]
+        rs = b"".join(le(pow(rho, j, R)) for j in range(m_proofs))
+        assert fused.lhs == oracle.msm_native(rs, b"".join(a.lhs for a in per), m_proofs)
+        assert fused.rhs == oracle.msm_native(rs, b"".join(a.rhs for a in per), m_proofs)
+        bv.verify_batch([as_proof(fx) for fx in fxs], rho)
+        bad = [as_proof(fx) for fx in fxs]
+        bad[5] = as_proof(make_shplonk_fixture(seed=205, srs_seed=srs, shuffle_seed=9, tamper=True))
+        with pytest.raises(sv.AssertionFailure):
+            bv.verify_batch(bad, rho)
+    finally:
+        L.close()
+
+
 @pytest.mark.gpu
 def test_gwc19_batch_verifier_pipeline_on_device():
     """BASELINE config 3 with REAL GWC19 structure: m proofs under one SRS -> MSM scalars by the device program -> one fused MSM per
