@@ -150,6 +150,16 @@ def test_msm_batch_matches_native_fold(loader):
         assert got[j] == oracle.msm_native(s[32 * lo:32 * (lo + k)], p[64 * lo:64 * (lo + k)], k), j
 
 
+def test_external_known_answer_on_device(loader):
+    """EIP-196 `bn256Add` vector (public Ethereum precompile tests; BN254 = alt_bn128): (1, 2) + (1, 2), straight from the device."""
+    two_g1 = (0x030644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD3,
+              0x15ED738C0E0A7C92E7845F96B2AE9C0A68A6A449E3538FC7FF3EBF7A5A18A2C4)
+    g = m.g1_to_bytes(m.G1_GEN)
+    exp = le(two_g1[0]) + le(two_g1[1])
+    assert loader.msm(le(1) * 2, g * 2, 2) == exp
+    assert loader.msm(le(2), g, 1) == exp
+
+
 def test_msm_host_mirror_evaluate(loader):
     """util::msm::Msm algebra on the host + evaluate(Some(gen)) through the loader."""
     pts = [oracle.synth_points(41, i, 1) for i in range(3)]

@@ -134,3 +134,26 @@ def test_accumulate(golden):
     for c in golden("accumulate"):
         a, b = oracle.kzg_accumulate(H(c["lhs"]), H(c["rhs"]), c["n"], H(c["r"]))
         assert a == H(c["out_lhs"]) and b == H(c["out_rhs"])
+
+
+def test_external_known_answers_from_ethereum_precompile_vectors():
+    """The reference ships no known-answer vectors for this path, but BN254 is Ethereum's alt_bn128: the public
+    EIP-196 / EIP-197 precompile test vectors (go-ethereum's bn256Add / bn256Pairing cases) pin the group law of both groups.
+      * G1: (1, 2) + (1, 2) = 2 G  (EIP-196 `bn256Add` vector)
+      * G2: 2 * G2_generator       (the G2 operand of the `bn256Pairing` two-point cases; EVM words are imaginary part first)
+    Both the Python model and the C++ restatement must reproduce them bit for bit."""
+    two_g1 = (0x030644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD3,
+              0x15ED738C0E0A7C92E7845F96B2AE9C0A68A6A449E3538FC7FF3EBF7A5A18A2C4)
+    two_g2_evm_words = (0x203E205DB4F19B37B60121B83A7333706DB86431C6D835849957ED8C3928AD79,    # x.c1
+                        0x27DC7234FD11D3E8C36C59277C3E6F149D5CD3CFA9A62AEE49F8130962B4B3B9,    # x.c0
+                        0x195E8AA5B7827463722B8C153931579D3505566B4EDF48D498E185F0509DE152,    # y.c1
+                        0x04BB53B8977E5F92A0BC372742C4830944A59B4FE6B1C0466E2A6DAD122B5D2E)    # y.c0
+    le = m.fe_to_le
+    assert m.g1_mul(m.G1_GEN, 2) == two_g1 == m.g1_add(m.G1_GEN, m.G1_GEN)
+    gen = m.g1_to_bytes(m.G1_GEN)
+    assert oracle.g1_mul(gen, le(2)) == le(two_g1[0]) + le(two_g1[1])
+    assert oracle.msm_native(le(1) * 2, gen * 2, 2) == le(two_g1[0]) + le(two_g1[1])
+    x, y = m.g2_mul(m.G2_GEN, 2)
+    assert (x[1], x[0], y[1], y[0]) == two_g2_evm_words
+    x1, x0, y1, y0 = two_g2_evm_words
+    assert oracle.g2_mul(oracle.g2_generator(), le(2)) == le(x0) + le(x1) + le(y0) + le(y1)
