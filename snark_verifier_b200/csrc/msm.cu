@@ -268,8 +268,10 @@ __global__ void __launch_bounds__(1024) k_scan(const uint32_t* __restrict__ coun
             if (lane >= (uint32_t)o) { incl.x += vx; incl.y += vy; }
         }
         if (lane == 31) warp_tot[wid] = incl;
-        __syncthreads();
+        // read the running totals BEFORE the barrier: warp 0 overwrites them right after it (racecheck: a warp still reading
+        // carry_sm there could see the next tile's value)
         const uint2 carry = carry_sm;
+        __syncthreads();
         if (wid == 0) {
             uint2 x = lane < (NT >> 5) ? warp_tot[lane] : make_uint2(0, 0);
             uint2 ix = x;
