@@ -73,7 +73,9 @@ static MsmPlan make_plan(size_t n_terms, int c_override, int glv_mode) {
     // bucket-reduce segment length: each thread's chain is 2 seg additions + one small scalar multiple; short segments cut that
     // latency, long ones cut the total work (the small multiples) once there are enough buckets to fill the machine
     const size_t all_buckets = (size_t)p.W * p.NB;
-    p.seg = all_buckets >= ((size_t)1 << 18) ? 16 : 4;   // measured: 8 at 2^18 buckets only moves the time into k_window_sum
+    // (measured with the block-level fold in k_bucket_reduce: 2^18 buckets 16 -> 0.52 ms, 8 -> 0.50, 32 -> 0.68; 2^20 buckets
+    // 16 -> 1.26 ms, 32 -> 0.89)
+    p.seg = all_buckets >= ((size_t)1 << 19) + ((size_t)1 << 18) ? 32 : all_buckets >= ((size_t)1 << 18) ? 16 : 4;
     if (p.seg > p.NB) p.seg = p.NB;
     p.J = (p.NB + p.seg - 1) / p.seg;
     const size_t avg = (n + p.NB - 1) / p.NB;
@@ -453,20 +455,33 @@ __global__ void __launch_bounds__(128) k_bucket_merge_big(const uint8_t* __restr
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_bucket_reduce(const uint8_t* __restrict__ buckets, uint32_t NB, uint32_t seg, uint32_t J,
                                                        uint8_t* __restrict__ segpart) {
-    const uint32_t w = blockIdx.y;
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= J) return;
+    __shared__ G1Xyzz sm[128];
+    const uint32_t w = blockIdx.y, t = threadIdx.x;
+    const uint32_t j = blockIdx.x * blockDim.x + t;
     buckets += (size_t)blockIdx.z * gridDim.y * NB * 128;
-    segpart += (size_t)blockIdx.z * gridDim.y * J * 128;
-    const uint32_t lo = j * seg, hi = min(lo + seg, NB);
-    G1Xyzz running = xyzz_identity(), acc = xyzz_identity();
-    for (uint32_t idx = hi; idx-- > lo;) {
-        G1Xyzz b = xyzz_load(buckets, (size_t)w * NB + idx);
-        running = xyzz_add(running, b);
-        acc = xyzz_add(acc, running);
+    segpart += (size_t)blockIdx.z * gridDim.y * gridDim.x * 128;
+    G1Xyzz acc = xyzz_identity();
+    if (j < J) {
+        const uint32_t lo = j * seg, hi = min(lo + seg, NB);
+        G1Xyzz running = xyzz_identity();
+        for (uint32_t idx = hi; idx-- > lo;) {
+            G1Xyzz b = xyzz_load(buckets, (size_t)w * NB + idx);
+            running = xyzz_add(running, b);
+            acc = xyzz_add(acc, running);
+        }
+        if (lo > 0) acc = xyzz_add(acc, xyzz_mul_small(running, lo));
     }
-    if (lo > 0) acc = xyzz_add(acc, xyzz_mul_small(running, lo));
-    xyzz_store(segpart, (size_t)w * J + j, acc);
+    // the block's 128 segment results are summed here (7 parallel levels): the per-window kernel that follows has 128x fewer
+    // values to fold (measured: c = 16 0.45 + 0.18 -> 0.52 + 0.05 ms; c = 17 with seg 32: 1.08 + 0.27 -> 0.89 + 0.05 ms).
+    // Measured and rejected: replacing the per-thread small multiple lo * running by a weighted (T, S) tree — its doublings are
+    // serial inside the block (0.77 + 0.17 ms at c = 16).
+    sm[t] = acc;
+    __syncthreads();
+    for (uint32_t s = blockDim.x >> 1; s > 0; s >>= 1) {
+        if (t < s) sm[t] = xyzz_add(sm[t], sm[t + s]);
+        __syncthreads();
+    }
+    if (t == 0) xyzz_store(segpart, (size_t)w * gridDim.x + blockIdx.x, sm[0]);
 }
 
 // K6a: sum the J segment results of one window; one block per window, shared-memory tree.
@@ -752,7 +767,7 @@ static int msm_tail_phase(snarkv_ctx* ctx, const MsmWork& wk, int B, int out_for
     }
     {
         Stage sg(ctx, "msm_window_sum");
-        k_window_sum<<<dim3(pl.W, B), 128, 0, st>>>(wk.segpart, pl.J, wk.winsum);
+        k_window_sum<<<dim3(pl.W, B), 128, 0, st>>>(wk.segpart, (pl.J + 127) / 128, wk.winsum);   // one partial per reduce block
         SNARKV_LAUNCH_CHECK(ctx, "k_window_sum");
         sg.launched();
     }
