@@ -136,6 +136,30 @@ def cpu_pippenger_sample(log_n, threads, reps=1):
     return n / best, n, best
 
 
+def cpu_native_extras(threads):
+    """The other two CPU legs SURVEY §8(d) names, on bounded samples: (1) the LITERAL NativeLoader MSM — the fold of
+    base * scalar over the pairs, loader/native.rs:61-71, single-threaded like the reference's verifier (linear in n, so a
+    2^11-term sample extrapolates); (2) `decide` per accumulator (decider.rs:70-93, G2Prepared recomputed per call) on all cores."""
+    import oracle
+    out = {}
+    n = 1 << 11
+    s, p = oracle.synth_scalars(SEED, 0, n), oracle.synth_points(SEED, 0, n, threads)
+    t0 = time.perf_counter()
+    oracle.msm_native(s, p, n)
+    dt = time.perf_counter() - t0
+    out["native_fold"] = {"value": n / dt / 1e6, "unit": "Mscalar-mults/s", "cores": 1, "kind": "port",
+                          "sample": "2^11-term NativeLoader::multi_scalar_multiplication fold (native.rs:61-71) in %.2f s; O(n), no cross-term reuse" % dt}
+    g2 = oracle.g2_generator()
+    nchk = 16 * threads
+    pts = oracle.synth_points(SEED + 1, 0, nchk, threads)
+    t0 = time.perf_counter()
+    oracle.kzg_decide_batch(pts, pts, nchk, g2, g2, threads)
+    dt = time.perf_counter() - t0
+    out["decide"] = {"value": nchk / dt, "unit": "checks/s", "cores": threads, "kind": "port",
+                     "sample": "%d independent KzgAs::decide calls (decider.rs:84-93 loop) in %.2f s" % (nchk, dt)}
+    return out
+
+
 def kzg_aux(L, sv, torch, stream, dev):
     """KZG decide throughput on synthetic valid accumulators (a_i s G, a_i G) — the shape of the reference's own mock
     accumulator (system/halo2/test/kzg.rs:37-45): per-check decisions (decider.rs:84-93) and the RLC-fused decide_all
@@ -520,6 +544,10 @@ def main():
             rate, n_s, secs = cpu_pippenger_sample(args.ref_log_n, threads)
             line["cpu_baseline"] = {"value": rate / 1e6, "unit": "Mscalar-mults/s", "cores": threads, "kind": "port",
                                     "sample": "one 2^%d-term chunk-parallel Pippenger (util/msm.rs:308-343 restated) in %.2f s" % (args.ref_log_n, secs)}
+            try:
+                line["cpu_baseline"]["also"] = cpu_native_extras(threads)
+            except Exception as e:
+                line["cpu_baseline"]["also"] = {"error": repr(e)}
         elif world > 1:
             line["cpu_baseline"] = None
         print(json.dumps(line), flush=True)
