@@ -682,7 +682,16 @@ static int msm_accumulate_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* 
     // ~48 on (64 at 2^22 terms, c = 17: 10.5 vs 11.8 ms; e2e 2^24 from host memory 53.1 -> 51.5 ms).
     const int mode = ctx->accumulate_mode;
     const size_t mean_load = nv / pl.NB;
-    const bool affine = mode >= 2 || (mode == 0 && (mean_load >= 256 || (mean_load >= (size_t)ctx->ba_min_load && nbk >= ((size_t)1 << 19))));
+    bool affine = mode >= 2 || (mode == 0 && (mean_load >= 256 || (mean_load >= (size_t)ctx->ba_min_load && nbk >= ((size_t)1 << 19))));
+    const size_t stride_a = (nv + pl.cap) / 2 + 2, stride_b = (stride_a + pl.cap) / 2 + 2;
+    if (affine && mode == 0) {
+        // the tree levels need scratch (48 B per term and window: 12 GB at 2^24 terms, 48 GB at 2^26); when that does not fit
+        // next to the caller's data the automatic choice falls back to the XYZZ kernel, which needs none
+        const size_t need = (size_t)B * pl.W * (stride_a + stride_b) * 64;
+        const size_t held = ctx->ws_bytes[WS_BA_REGION_A] + ctx->ws_bytes[WS_BA_REGION_B];
+        size_t free_b = 0, total_b = 0;
+        if (need > held && (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || need + need / 8 + ((size_t)2 << 30) > free_b + held)) affine = false;
+    }
     if (!affine || mode == 3) {
         Stage sg(ctx, "msm_bucket_accumulate");
         uint8_t* dst = wk.task_out;
@@ -704,7 +713,6 @@ static int msm_accumulate_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* 
             SNARKV_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SNARKV_BA_THREADS, 0));
             ctx->ba_blocks_per_sm = per_sm > 0 ? per_sm : 1;
         }
-        const size_t stride_a = (nv + pl.cap) / 2 + 2, stride_b = (stride_a + pl.cap) / 2 + 2;
         const uint32_t units = ((pl.cap + 31) / 32) * pl.W * (uint32_t)B;   // 32 tasks each; one warp takes up to Q at a time
         uint32_t blocks = (uint32_t)(ctx->sm_count * ctx->ba_blocks_per_sm);
         if (blocks > (units + 3) / 4) blocks = (units + 3) / 4;
