@@ -150,7 +150,7 @@ def cpu_native_extras(threads):
     out["native_fold"] = {"value": n / dt / 1e6, "unit": "Mscalar-mults/s", "cores": 1, "kind": "port",
                           "sample": "2^11-term NativeLoader::multi_scalar_multiplication fold (native.rs:61-71) in %.2f s; O(n), no cross-term reuse" % dt}
     g2 = oracle.g2_generator()
-    nchk = 16 * threads
+    nchk = 64 * threads
     pts = oracle.synth_points(SEED + 1, 0, nchk, threads)
     t0 = time.perf_counter()
     oracle.kzg_decide_batch(pts, pts, nchk, g2, g2, threads)
