@@ -67,6 +67,15 @@ def per_kernel_hbm(stages, n, windows, hbm_peak, cap, acc_ms):
     return rows
 
 
+def canonical_affine(b, fmt):
+    """64-byte affine result in the loader's format -> canonical little-endian x || y (for the printed line only)."""
+    if fmt != "montgomery":
+        return b
+    p = 0x30644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD47
+    rinv = pow(1 << 256, -1, p)
+    return b"".join((int.from_bytes(b[i:i + 32], "little") * rinv % p).to_bytes(32, "little") for i in (0, 32))
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -363,6 +372,9 @@ def main():
     ap.add_argument("--ref-log-n", type=int, default=20, help="log2 of the per-step CPU sample for --impl reference / cpu_baseline")
     ap.add_argument("--window-bits", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--format", default="montgomery", choices=["montgomery", "canonical"],
+                    help="byte layout of scalars / points at the C ABI: halo2curves' in-memory Montgomery limbs (what the Rust glue passes, "
+                         "zero-copy from &[Fr] / &[G1Affine]; default) or canonical little-endian `to_repr` bytes")
     ap.add_argument("--no-aux", action="store_true", help="skip the secondary KZG / scalar-evaluation measurements (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
@@ -389,7 +401,7 @@ def main():
     from snark_verifier_b200.sharding import chunk_bounds
     lo, n_local = chunk_bounds(n_total, world, rank)   # util/msm.rs:322 chunk_size = ceil(n / threads)
 
-    L = sv.CudaLoader(local_rank)
+    L = sv.CudaLoader(local_rank, fmt=sv.MONTGOMERY if args.format == "montgomery" else sv.CANONICAL)
     if args.window_bits:
         L.set_window_bits(args.window_bits)
     stream = torch.cuda.Stream(device=dev)
@@ -501,7 +513,10 @@ def main():
     # ---- secondary metric of BASELINE.json: "proofs verified/s" (KZG accumulator decisions), rank 0, N = 1 only -------------
     aux = None
     if rank == 0 and world == 1 and not args.no_aux:
-        aux = kzg_aux(L, sv, torch, stream, dev)
+        La = sv.CudaLoader(local_rank)            # the secondary measurements feed canonical constants: their own canonical context
+        La.set_stream(stream.cuda_stream)
+        aux = kzg_aux(La, sv, torch, stream, dev)
+        La.close()
 
     if rank == 0:
         hbm_peak, peak_src = peaks()
@@ -519,7 +534,8 @@ def main():
                                    "one NCCL all-gather of 96-byte Jacobian partials + fold" % (args.log_n, SEED, world),
                        "terms": n_total, "terms_per_gpu": n_local, "window_bits": c_bits, "parallelism": "chunk%d" % world,
                        "l2_policy": "inputs (%.2f GB/GPU) exceed the 126 MB L2; no flush needed" % (n_local * 96 / 1e9),
-                       "result_affine_le_hex": res_dev.hex()},
+                       "byte_format": args.format + (" (halo2curves in-memory layout, as the reference's CPU arm is fed)" if args.format == "montgomery" else ""),
+                       "result_affine_le_hex": canonical_affine(res_dev, args.format).hex()},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Mscalar-mults/s", "h2d_bytes_per_step": n_local * 96 * world, "d2h_bytes_per_step": 64 * world,
                     "api": "snarkv_g1_msm (N=1) / snarkv_g1_msm_partial + all_gather + fold (N>1), pinned host buffers",
