@@ -8,6 +8,7 @@
 //   KzgDecidingKey, KzgAccumulator           <->  pcs/kzg/decider.rs:6-42, pcs/kzg/accumulator.rs:6-26
 //   KzgAs::{decide, decide_all, verify}      <->  pcs/kzg/decider.rs:70-93, pcs/kzg/accumulation.rs:41-63
 //   AssertionFailure                         <->  Error::AssertionFailure (lib.rs:18-28)
+//   Query, Gwc19::verify                     <->  pcs.rs:20-49, pcs/kzg/multiopen/gwc19.rs:45-82 (SHPLONK: Python mirror snark_verifier_b200/pcs.py)
 //   LimbsEncoding<LIMBS, BITS>::from_repr    <->  pcs/kzg/accumulator.rs:57-81 (+ util/arithmetic.rs:270-282), also for a batch
 //   FrProgram / CudaLoader::fr_program_eval  <->  verifier/plonk/protocol.rs:211-283, 336-392; proof.rs:298-349 for a batch of proofs
 // Loaded values are plain host values exactly as NativeLoader keeps them (native.rs:44,75): Fr = 32 bytes, G1Affine = 64 bytes,
@@ -80,6 +81,7 @@ struct FrOps {
     Fr (*add)(const Fr&, const Fr&);
     Fr (*mul)(const Fr&, const Fr&);
     Fr one;
+    Fr (*neg)(const Fr&) = nullptr;   // needed by Msm::operator- / the multi-open verifiers below
 };
 
 // util/msm.rs:20-24
@@ -107,6 +109,16 @@ class Msm {
         for (size_t i = 0; i < other.bases_.size(); ++i) push(other.scalars_[i], other.bases_[i]);
         return *this;
     }
+    Msm operator+(const Msm& o) const { Msm r = *this; r.extend(o); return r; }                                      // :130-154
+    Msm operator*(const Fr& k) const { Msm r = *this; r.scale(k); return r; }                                        // :180-190
+    Msm operator-() const {                                                                                          // :192-204
+        if (!ops_->neg) throw Error("Msm: FrOps::neg is required for subtraction");
+        Msm r = *this;
+        if (r.constant_) r.constant_ = ops_->neg(*r.constant_);
+        for (auto& s : r.scalars_) s = ops_->neg(s);
+        return r;
+    }
+    Msm operator-(const Msm& o) const { return *this + (-o); }                                                       // :156-178
     // evaluate(gen): prepend (constant, gen) and call the loader's MSM                                               // :81-98
     G1Affine evaluate(const std::optional<G1Affine>& gen) const {
         std::vector<std::pair<const Fr*, const G1Affine*>> pairs;
@@ -164,6 +176,50 @@ class KzgAs {
 
   private:
     CudaLoader* loader_;
+};
+
+// pcs.rs:20-49
+struct Query { size_t poly; Fr shift; Fr eval; };
+
+// GWC19 multi-open verifier (pcs/kzg/multiopen/gwc19.rs:45-82): builds the (lhs, rhs) Msm pair of the accumulator from the
+// commitments, the queries and the proof (v, W_i, u); the two `evaluate` calls are the loader's MSM.
+struct Gwc19Proof { Fr v; std::vector<G1Affine> ws; Fr u; };
+struct Gwc19 {
+    static std::vector<Fr> powers(const FrOps& o, const Fr& x, size_t n) {                                           // loader.rs:71-78
+        std::vector<Fr> out;
+        Fr acc = o.one;
+        for (size_t i = 0; i < n; ++i) { out.push_back(acc); acc = o.mul(acc, x); }
+        return out;
+    }
+    static KzgAccumulator verify(CudaLoader& loader, const FrOps& o, const G1Affine& svk_g, const std::vector<Msm>& commitments, const Fr& z,
+                                 const std::vector<Query>& queries, const Gwc19Proof& proof) {
+        struct Set { Fr shift; std::vector<size_t> polys; std::vector<Fr> evals; };
+        std::vector<Set> sets;                                                                                       // gwc19.rs:140-160
+        for (const Query& q : queries) {
+            Set* hit = nullptr;
+            for (Set& s : sets) if (s.shift == q.shift) { hit = &s; break; }
+            if (!hit) { sets.push_back({q.shift, {}, {}}); hit = &sets.back(); }
+            hit->polys.push_back(q.poly);
+            hit->evals.push_back(q.eval);
+        }
+        size_t max_polys = 0;
+        for (const Set& s : sets) max_polys = s.polys.size() > max_polys ? s.polys.size() : max_polys;
+        const std::vector<Fr> pu = powers(o, proof.u, sets.size()), pv = powers(o, proof.v, max_polys);
+        Msm f(loader, o);
+        for (size_t k = 0; k < sets.size(); ++k) {
+            Msm set_msm(loader, o);                                                                                  // QuerySet::msm, gwc19.rs:120-137
+            for (size_t i = 0; i < sets[k].polys.size(); ++i)
+                set_msm = set_msm + (commitments[sets[k].polys[i]] - Msm::constant(loader, o, sets[k].evals[i])) * pv[i];
+            f = f + set_msm * pu[k];
+        }
+        Msm lhs = f, rhs(loader, o);
+        for (size_t k = 0; k < sets.size(); ++k) {
+            const Msm uw = Msm::base(loader, o, proof.ws[k]) * pu[k];
+            lhs = lhs + uw * o.mul(sets[k].shift, z);                                                                // z_omega = shift * z
+            rhs = rhs + uw;
+        }
+        return KzgAccumulator{lhs.evaluate(svk_g), rhs.evaluate(svk_g)};
+    }
 };
 
 // `LimbsEncoding<LIMBS, BITS>` (pcs/kzg/accumulator.rs:28-82): an accumulator as 4 x LIMBS scalar-field limbs.  The reference

@@ -1,6 +1,7 @@
 // C++ host-mirror test (run by tests/test_gpu_parity.py::test_cpp_host_mirror on the GPU box): drives
 // snark_verifier_b200/host/cuda_loader.hpp through the same golden inputs as the Python suite.  Input file format (binary):
 //   u32 n | n x 32 B scalars | n x 64 B points | 64 B expected MSM | 128 B g2 | 128 B s_g2 | 64 B lhs_ok | 64 B rhs_ok | 64 B rhs_bad
+//   | GWC19 section (see main)
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -13,6 +14,38 @@ template <size_t N> static std::array<uint8_t, N> rd(FILE* f) {
     std::array<uint8_t, N> a;
     if (fread(a.data(), 1, N, f) != N) { fprintf(stderr, "short read\n"); exit(2); }
     return a;
+}
+
+// ---- minimal Fr arithmetic for the Msm bookkeeping (FrOps policy): 4 x u64 limbs, add / double-and-add multiplication -------
+static const uint64_t R_MOD[4] = {0x43e1f593f0000001ull, 0x2833e84879b97091ull, 0xb85045b68181585dull, 0x30644e72e131a029ull};
+struct U256 { uint64_t v[4]; };
+static U256 from_fr(const Fr& a) { U256 r; memcpy(r.v, a.data(), 32); return r; }
+static Fr to_fr(const U256& a) { Fr r; memcpy(r.data(), a.v, 32); return r; }
+static bool geq_mod(const U256& a) {
+    for (int i = 3; i >= 0; --i) { if (a.v[i] > R_MOD[i]) return true; if (a.v[i] < R_MOD[i]) return false; }
+    return true;
+}
+static U256 add_mod(const U256& a, const U256& b) {   // a, b < r < 2^254: no overflow out of 256 bits
+    U256 r; unsigned __int128 c = 0;
+    for (int i = 0; i < 4; ++i) { c += (unsigned __int128)a.v[i] + b.v[i]; r.v[i] = (uint64_t)c; c >>= 64; }
+    if (geq_mod(r)) { unsigned __int128 br = 0; for (int i = 0; i < 4; ++i) { unsigned __int128 d = (unsigned __int128)r.v[i] - R_MOD[i] - br; r.v[i] = (uint64_t)d; br = (d >> 64) & 1; } }
+    return r;
+}
+static Fr fr_add(const Fr& a, const Fr& b) { return to_fr(add_mod(from_fr(a), from_fr(b))); }
+static Fr fr_mul(const Fr& a, const Fr& b) {
+    U256 x = from_fr(a), y = from_fr(b), acc{};
+    for (int bit = 255; bit >= 0; --bit) {
+        acc = add_mod(acc, acc);
+        if ((y.v[bit >> 6] >> (bit & 63)) & 1) acc = add_mod(acc, x);
+    }
+    return to_fr(acc);
+}
+static Fr fr_neg(const Fr& a) {
+    U256 x = from_fr(a), r; bool zero = !(x.v[0] | x.v[1] | x.v[2] | x.v[3]);
+    if (zero) return a;
+    unsigned __int128 br = 0;
+    for (int i = 0; i < 4; ++i) { unsigned __int128 d = (unsigned __int128)R_MOD[i] - x.v[i] - br; r.v[i] = (uint64_t)d; br = (d >> 64) & 1; }
+    return to_fr(r);
 }
 
 int main(int argc, char** argv) {
@@ -29,6 +62,21 @@ int main(int argc, char** argv) {
     dk.g2 = rd<128>(f); dk.s_g2 = rd<128>(f);
     dk.g = G1Affine{};
     G1Affine lhs_ok = rd<64>(f), rhs_ok = rd<64>(f), rhs_bad = rd<64>(f);
+    // GWC19 section: u32 npoly | u32 nq | z | v | u | nq x (u32 poly | shift | eval) | npoly x commitment | u32 nw | nw x W |
+    //                g2 | s_g2 | svk g | expected lhs | expected rhs
+    uint32_t npoly, nq, nw;
+    if (fread(&npoly, 4, 1, f) != 1 || fread(&nq, 4, 1, f) != 1) return 2;
+    Fr gz = rd<32>(f), gv = rd<32>(f), gu = rd<32>(f);
+    std::vector<Query> queries(nq);
+    for (auto& q : queries) { uint32_t p32; if (fread(&p32, 4, 1, f) != 1) return 2; q.poly = p32; q.shift = rd<32>(f); q.eval = rd<32>(f); }
+    std::vector<G1Affine> commits(npoly);
+    for (auto& c : commits) c = rd<64>(f);
+    if (fread(&nw, 4, 1, f) != 1) return 2;
+    Gwc19Proof gproof{gv, std::vector<G1Affine>(nw), gu};
+    for (auto& w : gproof.ws) w = rd<64>(f);
+    KzgDecidingKey gdk;
+    gdk.g2 = rd<128>(f); gdk.s_g2 = rd<128>(f); gdk.g = rd<64>(f);
+    G1Affine exp_lhs = rd<64>(f), exp_rhs = rd<64>(f);
     fclose(f);
 
     CudaLoader loader(0);
@@ -95,6 +143,22 @@ int main(int argc, char** argv) {
         threw = false;
         try { prog.eval_batch(loader, in, 3); } catch (const Error&) { threw = true; }
         if (!threw) { fprintf(stderr, "malformed program was accepted\n"); return 1; }
+    }
+    // Gwc19::verify (gwc19.rs:45-82) through the C++ Msm algebra and the device MSM: same accumulator bytes as the Python mirror over
+    // the NativeLoader fold, and it decides under the fixture's key
+    {
+        Fr one{}; one[0] = 1;
+        FrOps ops{fr_add, fr_mul, one, fr_neg};
+        std::vector<Msm> cm;
+        for (const auto& c : commits) cm.push_back(Msm::base(loader, ops, c));
+        KzgAccumulator acc = Gwc19::verify(loader, ops, gdk.g, cm, gz, queries, gproof);
+        if (acc.lhs != exp_lhs || acc.rhs != exp_rhs) { fprintf(stderr, "Gwc19::verify accumulator mismatch\n"); return 1; }
+        KzgAs gas(loader, gdk);
+        gas.decide(acc);
+        queries[1].eval[0] ^= 1;   // tampered evaluation
+        threw = false;
+        try { gas.decide(Gwc19::verify(loader, ops, gdk.g, cm, gz, queries, gproof)); } catch (const AssertionFailure&) { threw = true; }
+        if (!threw) { fprintf(stderr, "tampered GWC19 proof was accepted\n"); return 1; }
     }
     printf("host mirror ok\n");
     return 0;

@@ -383,6 +383,19 @@ def test_cpp_host_mirror(tmp_path, golden):
     blob = struct.pack("<I", case["n"]) + H(case["scalars"]) + H(case["points"]) + H(case["expected"])
     blob += H(g["g2_generator"]) + H(g["s_g2"])
     blob += H(checks["valid_0"]["lhs"]) + H(checks["valid_0"]["rhs"]) + H(checks["tampered_rhs"]["rhs"])
+    # GWC19 section: the toy-prover fixture of test_pcs_boundary.py; expected accumulator = the Python mirror over the NativeLoader fold
+    from snark_verifier_b200 import pcs
+    from test_pcs_boundary import GEN, OracleNativeLoader, make_fixture
+    from test_pcs_mirror import gwc19_queries
+    fx = make_fixture(seed=31, k=5)
+    qs = gwc19_queries(fx)
+    N = OracleNativeLoader()
+    exp = pcs.Gwc19.verify(N, GEN, [sv.Msm.base(N, c) for c in fx["C"]], fx["points"][0], qs, pcs.Gwc19Proof(fx["v"], fx["W"], fx["u"]))
+    blob += struct.pack("<II", len(fx["C"]), len(qs)) + le(fx["points"][0]) + le(fx["v"]) + le(fx["u"])
+    for q in qs:
+        blob += struct.pack("<I", q.poly) + le(q.shift) + le(q.eval)
+    blob += b"".join(fx["C"]) + struct.pack("<I", len(fx["W"])) + b"".join(fx["W"])
+    blob += fx["g2"] + fx["s_g2"] + GEN + exp.lhs + exp.rhs
     inp = tmp_path / "in.bin"
     inp.write_bytes(blob)
     out = subprocess.run([str(exe), str(inp)], capture_output=True, text=True)
