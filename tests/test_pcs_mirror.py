@@ -192,6 +192,37 @@ def test_limbs_encoding_round_trip_and_rejections():
         enc.from_repr(wide)
 
 
+def test_limbs_golden_host(golden):
+    """tests/golden/limbs.json (oracle/gen_golden_plonk.py): LimbsEncoding::from_repr accepts / rejects exactly the committed rows."""
+    g = golden("limbs")
+    enc = pcs.LimbsEncoding(g["limbs"], g["bits"])
+    for row in g["rows"]:
+        limbs = [int(v, 16) for v in row["limbs"]]
+        if row["valid"]:
+            acc = enc.from_repr(limbs)
+            assert (acc.lhs.hex(), acc.rhs.hex()) == (row["lhs"], row["rhs"]), row["note"]
+        else:
+            with pytest.raises(pcs.InvalidAccumulator):
+                enc.from_repr(limbs)
+
+
+@pytest.mark.gpu
+def test_limbs_golden_device(golden):
+    g = golden("limbs")
+    enc = pcs.LimbsEncoding(g["limbs"], g["bits"])
+    L = sv.CudaLoader(0)
+    try:
+        rows = g["rows"]
+        buf = b"".join((int(v, 16) % R).to_bytes(32, "little") for row in rows for v in row["limbs"])
+        # a limb >= r cannot be passed as an Fr (the over-wide rows stay below r: 2^70 + ... < r)
+        lhs, rhs, valid = enc.from_repr_batch(L, buf, len(rows))
+        for a, row in enumerate(rows):
+            assert valid[a] == row["valid"], row["note"]
+            assert (lhs[64 * a:64 * a + 64].hex(), rhs[64 * a:64 * a + 64].hex()) == (row["lhs"], row["rhs"]), row["note"]
+    finally:
+        L.close()
+
+
 def test_gwc19_msm_scalar_program_equals_host_mirror():
     """gwc19.rs:52-81 compiled to a straight-line program (SymbolicMsm over virtual registers) must produce exactly the
     (scalar, base) pairs — same order, same values — that the host mirror hands to multi_scalar_multiplication."""

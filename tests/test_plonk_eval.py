@@ -130,7 +130,47 @@ def test_used_sets_and_distribute_powers_single():
     assert om.eval_expr(e.to_tuple(), 3, {-1: 7}, {(2, 0): 5}, [9]) == 35     # a single expression ignores the scalar (protocol.rs:381-383)
 
 
+def _tup(x):
+    return tuple(_tup(e) for e in x) if isinstance(x, list) else x
+
+
+def golden_cases(golden):
+    g = golden("plonk_eval")
+    for case in g["cases"]:
+        p = pe.standard_plonk_like_protocol(case["k"], num_instance=case["num_instance"], blinding_factors=g["blinding_factors"])
+        rows = [[int(v, 16) for v in r["inputs"]] for r in case["rows"]]
+        exp = [[int(v, 16) for v in r["outputs"]] for r in case["rows"]]
+        yield g, p, rows, exp
+
+
+def test_golden_fixture_pins_structure_and_values(golden):
+    """tests/golden/plonk_eval.json (oracle/gen_golden_plonk.py): the numerator written out there as plain tuples is the one the
+    product builds, and the compiled program reproduces the committed evaluations."""
+    for g, p, rows, exp in golden_cases(golden):
+        assert p.numerator.to_tuple() == _tup(g["numerator"])
+        assert [[q.poly, q.rotation.value] for q in p.evaluations] == g["evaluation_queries"]
+        prog = pe.compile_quotient_evaluation(p)
+        for row, e in zip(rows, exp):
+            assert om.run_program(prog.instrs, prog.n_regs, prog.consts, row, prog.outputs) == e
+
+
 # ---- GPU: the device kernel, bit-exact -------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_device_matches_golden_fixture(golden):
+    import snark_verifier_b200 as sv
+    L = sv.CudaLoader(0)
+    try:
+        for g, p, rows, exp in golden_cases(golden):
+            prog = pe.compile_quotient_evaluation(p)
+            buf = b"".join(v.to_bytes(32, "little") for row in rows for v in row)
+            out = L.fr_program_eval(prog, buf, len(rows))
+            got = [int.from_bytes(out[i:i + 32], "little") for i in range(0, len(out), 32)]
+            assert got == [v for e in exp for v in e]
+    finally:
+        L.close()
+
+
+
 def pack_rows(rows, montgomery=False):
     conv = (lambda v: (v << 256) % R) if montgomery else (lambda v: v)
     return b"".join(conv(v).to_bytes(32, "little") for row in rows for v in row)
