@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../snark_verifier_b200/host/cuda_loader.hpp"
+#include "../snark_verifier_b200/host/plonk_eval.hpp"
 
 using namespace snarkv;
 
@@ -77,6 +78,12 @@ int main(int argc, char** argv) {
     KzgDecidingKey gdk;
     gdk.g2 = rd<128>(f); gdk.s_g2 = rd<128>(f); gdk.g = rd<64>(f);
     G1Affine exp_lhs = rd<64>(f), exp_rhs = rd<64>(f);
+    // scalar-evaluation section (tests/golden/plonk_eval.json, case k = 8, 3 instances): u32 rows | u32 n_in | u32 n_out | inputs | expected
+    uint32_t pe_rows, pe_in, pe_out;
+    if (fread(&pe_rows, 4, 1, f) != 1 || fread(&pe_in, 4, 1, f) != 1 || fread(&pe_out, 4, 1, f) != 1) return 2;
+    std::vector<Fr> pe_inputs(pe_rows * pe_in), pe_expected(pe_rows * pe_out);
+    for (auto& x : pe_inputs) x = rd<32>(f);
+    for (auto& x : pe_expected) x = rd<32>(f);
     fclose(f);
 
     CudaLoader loader(0);
@@ -159,6 +166,13 @@ int main(int argc, char** argv) {
         threw = false;
         try { gas.decide(Gwc19::verify(loader, ops, gdk.g, cm, gz, queries, gproof)); } catch (const AssertionFailure&) { threw = true; }
         if (!threw) { fprintf(stderr, "tampered GWC19 proof was accepted\n"); return 1; }
+    }
+    // the C++ compiler (host/plonk_eval.hpp: Expression::evaluate over a ProgramBuilder) + the device program, against the golden rows
+    {
+        const plonk::QuotientProtocol proto = plonk::standard_plonk_like_protocol(8, 3);
+        const FrProgram prog = plonk::compile_quotient_evaluation(proto);
+        if (prog.n_inputs != pe_in || prog.outputs.size() != pe_out) { fprintf(stderr, "program shape mismatch\n"); return 1; }
+        if (prog.eval_batch(loader, pe_inputs, pe_rows) != pe_expected) { fprintf(stderr, "quotient evaluation mismatch\n"); return 1; }
     }
     printf("host mirror ok\n");
     return 0;

@@ -396,6 +396,11 @@ def test_cpp_host_mirror(tmp_path, golden):
         blob += struct.pack("<I", q.poly) + le(q.shift) + le(q.eval)
     blob += b"".join(fx["C"]) + struct.pack("<I", len(fx["W"])) + b"".join(fx["W"])
     blob += fx["g2"] + fx["s_g2"] + GEN + exp.lhs + exp.rhs
+    case8 = [c for c in golden("plonk_eval")["cases"] if c["k"] == 8][0]
+    ins = [int(v, 16) for r in case8["rows"] for v in r["inputs"]]
+    outs = [int(v, 16) for r in case8["rows"] for v in r["outputs"]]
+    nrows = len(case8["rows"])
+    blob += struct.pack("<III", nrows, len(ins) // nrows, len(outs) // nrows) + b"".join(le(v) for v in ins) + b"".join(le(v) for v in outs)
     inp = tmp_path / "in.bin"
     inp.write_bytes(blob)
     out = subprocess.run([str(exe), str(inp)], capture_output=True, text=True)

@@ -154,6 +154,24 @@ def test_golden_fixture_pins_structure_and_values(golden):
             assert om.run_program(prog.instrs, prog.n_regs, prog.consts, row, prog.outputs) == e
 
 
+def test_cpp_compiler_emits_the_same_program(tmp_path):
+    """snark_verifier_b200/host/plonk_eval.hpp (the C++ host mirror: Expression, CommonPolynomialEvaluation, ProgramBuilder with
+    the same liveness-based register allocation) must emit, instruction for instruction, the program the Python compiler emits."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "plonk_compile_test"
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-o", str(exe), os.path.join(root, "tests", "plonk_compile_test.cpp")])
+    for k, ninst in ((4, 1), (8, 3), (12, 2), (17, 2)):
+        out = subprocess.run([str(exe), str(k), str(ninst)], capture_output=True, text=True, check=True).stdout.splitlines()
+        prog = pe.compile_quotient_evaluation(pe.standard_plonk_like_protocol(k, num_instance=ninst))
+        hdr = out[0].split()
+        assert (int(hdr[1]), int(hdr[3])) == (prog.n_regs, prog.n_inputs)
+        assert [tuple(int(x) for x in l.split()[1:]) for l in out if l.startswith("i ")] == [tuple(i) for i in prog.instrs]
+        assert [int(l.split()[1], 16) for l in out if l.startswith("c ")] == prog.consts
+        assert [int(x) for x in [l for l in out if l.startswith("o")][0].split()[1:]] == prog.outputs
+
+
 # ---- GPU: the device kernel, bit-exact -------------------------------------------------------------------------------------
 @pytest.mark.gpu
 def test_device_matches_golden_fixture(golden):
