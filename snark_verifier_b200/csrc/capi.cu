@@ -62,7 +62,6 @@ int snarkv_init(int device, snarkv_ctx** out) {
     c->ba_k = env_int("SNARKV_BA_K", 1, 128, c->ba_k);
     c->ba_pairs_min = env_int("SNARKV_BA_PAIRS_MIN", 1, 1 << 20, c->ba_pairs_min);
     c->ba_q = env_int("SNARKV_BA_Q", 1, 4, c->ba_q);
-    c->sort_mode = env_int("SNARKV_SORT_MODE", 0, 1, c->sort_mode);
     c->host_chunks = env_int("SNARKV_HOST_CHUNKS", 2, 7, c->host_chunks);
     c->host_chunk_ratio_pct = env_int("SNARKV_HOST_RATIO", 100, 400, c->host_chunk_ratio_pct);
     c->ba_min_load = env_int("SNARKV_BA_MIN_LOAD", 1, 1 << 20, c->ba_min_load);

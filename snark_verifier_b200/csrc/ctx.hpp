@@ -51,10 +51,6 @@ enum WsSlot : int {
     WS_BA_PREFIX,         // per resident block: K x 128 x 32 B prefix products
     WS_BA_COUNTER,        // [group counter | self-check mismatch record x 4]
     WS_TASK_OUT_CHECK,    // second task-result array (accumulate mode 3)
-    WS_S2_TILECNT,        // two-level sort (sort2.cuh): W x P x tiles u32
-    WS_S2_PART,           // W x (2 P + 1) u32: partition totals | partition bases
-    WS_S2_REC,            // W x n u32 term references in partition order
-    WS_S2_KEY,            // W x n u8 low bucket bits in partition order
     WS_FR_REGS,           // fr_program register file: n_regs x m x 32 B
     WS_FR_PROG,           // fr_program: instructions | consts | out_regs
     WS_SLOTS
@@ -72,7 +68,6 @@ struct snarkv_ctx {
     int window_bits = 0;
     int glv_mode = 0;       // 0 = GLV for n < 2^22 (default), 1 = always, 2 = never
     int pairing_mode = 0;   // 0 = choose from N, 1 = one thread per check, 2 = one block per check
-    int sort_mode = 0;   // 0 = single-level sort (histogram + cursor atomics), 1 = two-level sort of sort2.cuh where it applies (EXPERIMENTAL; SNARKV_SORT_MODE)
     int host_chunks = 7, host_chunk_ratio_pct = 160;   // host entry pipeline: term-chunks of geometrically growing size (SNARKV_HOST_CHUNKS <= 7, SNARKV_HOST_RATIO in percent)
     int accumulate_mode = 0;   // 0 = choose from the bucket load, 1 = XYZZ, 2 = batched affine, 3 = both + task-level self-check
     int ba_blocks_per_sm = 0;  // occupancy of k_bucket_accumulate_affine (queried once)

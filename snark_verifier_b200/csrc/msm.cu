@@ -21,7 +21,6 @@
 #include "g1.cuh"
 #include "glv.cuh"
 #include "bucket_affine.cuh"
-#include "sort2.cuh"
 
 namespace snarkv {
 
@@ -145,7 +144,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // The scalar stream is staged through shared memory by TMA bulk copies: one elected thread issues an 8 KB
 // cp.async.bulk per 256-scalar tile into a double buffer while the block decomposes the previous tile.
 #define SNARKV_DIGIT_TILE 256
-template <bool GLV, bool HIST>
+template <bool GLV>
 __global__ void __launch_bounds__(SNARKV_DIGIT_TILE) k_digits(const uint8_t* __restrict__ scalars, size_t n, int format, int check, uint32_t c,
                                                               uint32_t W, uint32_t NB, uint32_t* __restrict__ counters,
                                                               uint32_t* __restrict__ digits, int* __restrict__ status) {
@@ -197,7 +196,7 @@ __global__ void __launch_bounds__(SNARKV_DIGIT_TILE) k_digits(const uint8_t* __r
                         carry = 1u;
                     } else carry = 0u;
                     digits[(size_t)w * n + i] = d | (neg << 31);
-                    if (HIST && d != 0) atomicAdd(&counters[w * NB + (d - 1u)], 1u);   // sort mode 1 counts in shared memory instead (sort2.cuh)
+                    if (d != 0) atomicAdd(&counters[w * NB + (d - 1u)], 1u);
                 }
             } else {
                 // two half-length virtual terms: index i carries |k1| (sign neg1) for P_i, index n + i carries |k2| for phi(P_i)
@@ -219,7 +218,7 @@ __global__ void __launch_bounds__(SNARKV_DIGIT_TILE) k_digits(const uint8_t* __r
                             carry = 1u;
                         } else carry = 0u;
                         digits[(size_t)w * nv + i + (size_t)h * n] = d | ((neg ^ sgn[h]) << 31);
-                        if (HIST && d != 0) atomicAdd(&counters[w * NB + (d - 1u)], 1u);   // sort mode 1 counts in shared memory instead (sort2.cuh)
+                        if (d != 0) atomicAdd(&counters[w * NB + (d - 1u)], 1u);
                     }
                 }
             }
@@ -567,10 +566,6 @@ struct MsmWork {
     MsmPlan pl;
     int* status;
     uint32_t *counts, *offsets, *cursor, *sorted, *digits;
-    // two-level sort (sort mode 1, sort2.cuh): null when the single-level path is used
-    uint32_t *s2_tilecnt = nullptr, *s2_part = nullptr, *s2_rec = nullptr;
-    uint8_t* s2_key = nullptr;
-    uint32_t s2_lb = 0, s2_P = 0;
     uint32_t *task_base, *window_tasks, *big;   // big = [count | list of bucket ids]
     uint2* tasks;
     uint32_t* order;
@@ -600,18 +595,6 @@ static int msm_alloc(snarkv_ctx* ctx, size_t n, void* d_status, MsmWork& wk, int
     wk.tasks = (uint2*)ctx->wsget(WS_TASKS, (size_t)pl.W * pl.cap * 8);
     wk.task_out = (uint8_t*)ctx->wsget(WS_TASK_OUT, (size_t)B * pl.W * pl.cap * 128);
     wk.order = (uint32_t*)ctx->wsget(WS_ORDER, (size_t)pl.W * pl.cap * 4);
-    // two-level sort: experimental, chosen only when asked for (developer knob SNARKV_SORT_MODE=1) and where its layout applies
-    // (9..16 bucket bits: 2..256 partitions of <= 256 low keys; enough terms for full tiles)
-    if (ctx->sort_mode == 1 && pl.c >= 10 && pl.c <= 17 && nv >= ((size_t)1 << 20)) {
-        wk.s2_lb = 8;
-        wk.s2_P = 1u << (pl.c - 1 - 8);
-        const size_t T = (nv + SNARKV_S2_TILE - 1) / SNARKV_S2_TILE;
-        wk.s2_tilecnt = (uint32_t*)ctx->wsget(WS_S2_TILECNT, (size_t)pl.W * wk.s2_P * T * 4);
-        wk.s2_part = (uint32_t*)ctx->wsget(WS_S2_PART, (size_t)pl.W * (2 * wk.s2_P + 1) * 4);   // parttot [W][P] | partbase [W][P + 1]
-        wk.s2_rec = (uint32_t*)ctx->wsget(WS_S2_REC, (size_t)pl.W * nv * 4);
-        wk.s2_key = (uint8_t*)ctx->wsget(WS_S2_KEY, (size_t)pl.W * nv);
-        if (!wk.s2_tilecnt || !wk.s2_part || !wk.s2_rec || !wk.s2_key) return SNARKV_ERR_CUDA;
-    }
     if (!wk.status || !wk.counts || !wk.offsets || !wk.cursor || !wk.sorted || !wk.buckets || !wk.segpart || !wk.winsum ||
         !wk.digits || !wk.task_base || !wk.window_tasks || !wk.big || !wk.tasks || !wk.task_out || !wk.order)
         return SNARKV_ERR_CUDA;
@@ -629,28 +612,14 @@ static int msm_sort_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* d_scal
         Stage sg(ctx, "msm_digits_count");
         SNARKV_CUDA_TRY(ctx, cudaMemsetAsync(wk.status, 0, 4, st));
         SNARKV_CUDA_TRY(ctx, cudaMemsetAsync(wk.counts, 0, nbk * 4, st));
-        const bool two_level = wk.s2_rec != nullptr;
-        auto kd = pl.glv ? (two_level ? k_digits<true, false> : k_digits<true, true>) : (two_level ? k_digits<false, false> : k_digits<false, true>);
-        kd<<<dig_blocks, 256, 0, st>>>((const uint8_t*)d_scalars, n, scalar_format, check, pl.c, pl.W, pl.NB, wk.counts, wk.digits, wk.status);
+        if (pl.glv)
+            k_digits<true><<<dig_blocks, 256, 0, st>>>((const uint8_t*)d_scalars, n, scalar_format, check, pl.c, pl.W, pl.NB, wk.counts,
+                                                       wk.digits, wk.status);
+        else
+            k_digits<false><<<dig_blocks, 256, 0, st>>>((const uint8_t*)d_scalars, n, scalar_format, check, pl.c, pl.W, pl.NB, wk.counts,
+                                                        wk.digits, wk.status);
         SNARKV_LAUNCH_CHECK(ctx, "k_digits");
         sg.launched();
-        if (two_level) {   // level 1 + the bucket counts of level 2 (sort2.cuh); offsets / tasks come from the scans below as always
-            const size_t nv2 = plan_virtual_terms(pl, n);
-            const uint32_t T2 = (uint32_t)((nv2 + SNARKV_S2_TILE - 1) / SNARKV_S2_TILE), P2 = wk.s2_P;
-            uint32_t* parttot = wk.s2_part;
-            uint32_t* partbase = wk.s2_part + (size_t)pl.W * P2;
-            k_part_count<<<dim3(T2, pl.W), 256, 0, st>>>(wk.digits, nv2, wk.s2_lb, P2, T2, wk.s2_tilecnt);
-            SNARKV_LAUNCH_CHECK(ctx, "k_part_count");
-            k_part_scan<<<dim3(P2, pl.W), 1024, 0, st>>>(wk.s2_tilecnt, P2, T2, parttot);
-            SNARKV_LAUNCH_CHECK(ctx, "k_part_scan");
-            k_part_base<<<pl.W, SNARKV_S2_MAXP, 0, st>>>(parttot, P2, partbase);
-            SNARKV_LAUNCH_CHECK(ctx, "k_part_base");
-            k_part_scatter<<<dim3(T2, pl.W), 256, 0, st>>>(wk.digits, nv2, wk.s2_lb, P2, T2, wk.s2_tilecnt, partbase, wk.s2_rec, wk.s2_key);
-            SNARKV_LAUNCH_CHECK(ctx, "k_part_scatter");
-            k_bin_count<<<dim3(P2, pl.W), 1024, 0, st>>>(wk.s2_key, nv2, wk.s2_lb, P2, pl.NB, partbase, wk.counts);
-            SNARKV_LAUNCH_CHECK(ctx, "k_bin_count");
-            sg.launched(5);
-        }
     }
     {
         Stage sg(ctx, "msm_scan");
@@ -668,16 +637,10 @@ static int msm_sort_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* d_scal
         Stage sg(ctx, "msm_digits_scatter");
         const size_t nv = plan_virtual_terms(pl, n);
         // 8 elements per thread; at most 65535 blocks per window
-        if (wk.s2_rec) {
-            const uint32_t* partbase = wk.s2_part + (size_t)pl.W * wk.s2_P;
-            k_bin_place<<<dim3(wk.s2_P, pl.W), 1024, 0, st>>>(wk.s2_key, wk.s2_rec, nv, wk.s2_lb, wk.s2_P, pl.NB, partbase, wk.offsets, wk.sorted);
-            SNARKV_LAUNCH_CHECK(ctx, "k_bin_place");
-        } else {
-            size_t gx = (nv + 2047) / 2048;
-            if (gx > 65535) gx = 65535;
-            k_scatter<<<dim3((unsigned)gx, pl.W), 256, 0, st>>>(wk.digits, nv, pl.W, pl.NB, wk.cursor, wk.sorted);
-            SNARKV_LAUNCH_CHECK(ctx, "k_scatter");
-        }
+        size_t gx = (nv + 2047) / 2048;
+        if (gx > 65535) gx = 65535;
+        k_scatter<<<dim3((unsigned)gx, pl.W), 256, 0, st>>>(wk.digits, nv, pl.W, pl.NB, wk.cursor, wk.sorted);
+        SNARKV_LAUNCH_CHECK(ctx, "k_scatter");
         sg.launched();
     }
     return SNARKV_OK;
