@@ -1,5 +1,5 @@
 //! UNCOMPILED reference text.  Mirrors snark-verifier/src/pcs/kzg/decider.rs:62-94 for `CudaLoader`, plus the batch forms.
-use crate::{ffi::*, loader::*};
+use crate::{cuda_loader::*, ffi::*};
 use halo2curves::bn256::{Bn256, Fr, G1Affine};
 use snark_verifier::{
     pcs::{
