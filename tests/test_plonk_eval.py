@@ -113,6 +113,69 @@ def test_random_expression_programs_match_oracle():
             assert om.run_program(prog.instrs, prog.n_regs, prog.consts, row, prog.outputs) == oracle_row(p, row)
 
 
+def test_register_allocation_on_random_programs():
+    """ProgramBuilder.finish maps SSA values onto registers by liveness; whatever the dataflow, the allocated program must compute
+    what the SSA program computes (values read after their register was recycled would show up here)."""
+    rng = random.Random(77)
+    for trial in range(60):
+        b = pe.ProgramBuilder()
+        vals = [b.input(i) for i in range(4)] + [b.const(rng.choice([0, 1, 5, R - 1]))]
+        ref = None
+        for _ in range(rng.randrange(5, 80)):
+            k = rng.randrange(8)
+            x, y = rng.choice(vals), rng.choice(vals)
+            if k == 0:
+                vals.append(b.add(x, y))
+            elif k == 1:
+                vals.append(b.sub(x, y))
+            elif k in (2, 3):
+                vals.append(b.mul(x, y))
+            elif k == 4:
+                vals.append(b.neg(x))
+            elif k == 5:
+                vals.append(b.inv(x))
+            elif k == 6:
+                vals.extend(b.batch_invert(rng.sample(vals, rng.randrange(1, min(5, len(vals)) + 1))))
+            else:
+                vals.append(b.pow_const(x, rng.randrange(1, 40)))
+        outs = rng.sample(vals, rng.randrange(1, 6))
+        prog = b.finish(outs)
+        row = [rng.choice([0, 1, rng.randrange(R)]) for _ in range(4)]
+        # direct SSA evaluation (one slot per value, never recycled)
+        ssa = []
+        for op, a, c in b.ssa:
+            if op == pe.OP_INPUT:
+                ssa.append(row[a] % R)
+            elif op == pe.OP_CONST:
+                ssa.append(b.consts[a])
+            elif op == pe.OP_ADD:
+                ssa.append((ssa[a] + ssa[c]) % R)
+            elif op == pe.OP_SUB:
+                ssa.append((ssa[a] - ssa[c]) % R)
+            elif op == pe.OP_MUL:
+                ssa.append(ssa[a] * ssa[c] % R)
+            elif op == pe.OP_NEG:
+                ssa.append((-ssa[a]) % R)
+            elif op == pe.OP_INV:
+                ssa.append(om.inv_or_zero(ssa[a]))
+            elif op == pe.OP_NZ:
+                ssa.append(ssa[a] if ssa[a] else 1)
+            else:
+                ssa.append(ssa[a] if ssa[c] else 0)
+        assert om.run_program(prog.instrs, prog.n_regs, prog.consts, row, prog.outputs) == [ssa[o] for o in outs], trial
+        assert prog.n_regs <= len(b.ssa)
+
+
+def test_batch_invert_matches_individual_inverses_with_zeros():
+    """util/arithmetic.rs:47-74 as straight-line code: zeros stay zero and do not poison the shared inversion."""
+    for values in ([3, 0, 7], [0, 0], [0], [5], [1, 2, 3, 4, 0, 6]):
+        b = pe.ProgramBuilder()
+        ins = [b.input(i) for i in range(len(values))]
+        prog = b.finish(b.batch_invert(ins))
+        assert prog.op_histogram()["inv"] == 1
+        assert om.run_program(prog.instrs, prog.n_regs, prog.consts, values, prog.outputs) == [om.inv_or_zero(v) for v in values]
+
+
 def test_missing_query_and_challenge_are_errors():
     E = pe.Expression
     p = pe.QuotientProtocol(pe.Domain(4), 1, [], [], 1, E.polynomial(pe.Query(0)))
