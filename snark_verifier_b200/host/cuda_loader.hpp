@@ -8,7 +8,7 @@
 //   KzgDecidingKey, KzgAccumulator           <->  pcs/kzg/decider.rs:6-42, pcs/kzg/accumulator.rs:6-26
 //   KzgAs::{decide, decide_all, verify}      <->  pcs/kzg/decider.rs:70-93, pcs/kzg/accumulation.rs:41-63
 //   AssertionFailure                         <->  Error::AssertionFailure (lib.rs:18-28)
-//   Query, Gwc19::verify                     <->  pcs.rs:20-49, pcs/kzg/multiopen/gwc19.rs:45-82 (SHPLONK: Python mirror snark_verifier_b200/pcs.py)
+//   Query, Gwc19::verify                     <->  pcs.rs:20-49, pcs/kzg/multiopen/gwc19.rs:45-82 (SHPLONK: host/pcs.hpp)
 //   LimbsEncoding<LIMBS, BITS>::from_repr    <->  pcs/kzg/accumulator.rs:57-81 (+ util/arithmetic.rs:270-282), also for a batch
 //   FrProgram / CudaLoader::fr_program_eval  <->  verifier/plonk/protocol.rs:211-283, 336-392; proof.rs:298-349 for a batch of proofs
 // Loaded values are plain host values exactly as NativeLoader keeps them (native.rs:44,75): Fr = 32 bytes, G1Affine = 64 bytes,
@@ -82,14 +82,18 @@ struct FrOps {
     Fr (*mul)(const Fr&, const Fr&);
     Fr one;
     Fr (*neg)(const Fr&) = nullptr;   // needed by Msm::operator- / the multi-open verifiers below
+    Fr (*inv)(const Fr&) = nullptr;   // needed by Bdfg21 (host/pcs.hpp); must map 0 to 0 (batch_invert leaves zeros untouched)
 };
 
-// util/msm.rs:20-24
-class Msm {
+// util/msm.rs:20-24.  `Loader` only needs `multi_scalar_multiplication(pairs)`: CudaLoader in production, a recording stand-in in the
+// CPU tests of the host logic (tests/pcs_mirror_test.cpp).
+template <class Loader>
+class BasicMsm {
   public:
-    Msm(CudaLoader& loader, const FrOps& ops) : loader_(&loader), ops_(&ops) {}
-    static Msm constant(CudaLoader& l, const FrOps& o, const Fr& c) { Msm m(l, o); m.constant_ = c; return m; }   // :46-52
-    static Msm base(CudaLoader& l, const FrOps& o, const G1Affine& b) {                                              // :54-61
+    using Msm = BasicMsm;
+    BasicMsm(Loader& loader, const FrOps& ops) : loader_(&loader), ops_(&ops) {}
+    static Msm constant(Loader& l, const FrOps& o, const Fr& c) { Msm m(l, o); m.constant_ = c; return m; }   // :46-52
+    static Msm base(Loader& l, const FrOps& o, const G1Affine& b) {                                              // :54-61
         Msm m(l, o); m.scalars_.push_back(o.one); m.bases_.push_back(b); return m;
     }
     size_t size() const { return bases_.size(); }
@@ -131,12 +135,13 @@ class Msm {
     }
 
   private:
-    CudaLoader* loader_;
+    Loader* loader_;
     const FrOps* ops_;
     std::optional<Fr> constant_;
     std::vector<Fr> scalars_;
     std::vector<G1Affine> bases_;
 };
+using Msm = BasicMsm<CudaLoader>;
 
 struct KzgAccumulator { G1Affine lhs, rhs; };            // pcs/kzg/accumulator.rs:6-26
 struct KzgDecidingKey { G1Affine g; G2Affine g2, s_g2; };  // pcs/kzg/decider.rs:6-42 (svk.g, g2, s_g2)
@@ -184,14 +189,16 @@ struct Query { size_t poly; Fr shift; Fr eval; };
 // GWC19 multi-open verifier (pcs/kzg/multiopen/gwc19.rs:45-82): builds the (lhs, rhs) Msm pair of the accumulator from the
 // commitments, the queries and the proof (v, W_i, u); the two `evaluate` calls are the loader's MSM.
 struct Gwc19Proof { Fr v; std::vector<G1Affine> ws; Fr u; };
-struct Gwc19 {
+template <class Loader>
+struct BasicGwc19 {
+    using Msm = BasicMsm<Loader>;
     static std::vector<Fr> powers(const FrOps& o, const Fr& x, size_t n) {                                           // loader.rs:71-78
         std::vector<Fr> out;
         Fr acc = o.one;
         for (size_t i = 0; i < n; ++i) { out.push_back(acc); acc = o.mul(acc, x); }
         return out;
     }
-    static KzgAccumulator verify(CudaLoader& loader, const FrOps& o, const G1Affine& svk_g, const std::vector<Msm>& commitments, const Fr& z,
+    static KzgAccumulator verify(Loader& loader, const FrOps& o, const G1Affine& svk_g, const std::vector<Msm>& commitments, const Fr& z,
                                  const std::vector<Query>& queries, const Gwc19Proof& proof) {
         struct Set { Fr shift; std::vector<size_t> polys; std::vector<Fr> evals; };
         std::vector<Set> sets;                                                                                       // gwc19.rs:140-160
@@ -221,6 +228,7 @@ struct Gwc19 {
         return KzgAccumulator{lhs.evaluate(svk_g), rhs.evaluate(svk_g)};
     }
 };
+using Gwc19 = BasicGwc19<CudaLoader>;
 
 // `LimbsEncoding<LIMBS, BITS>` (pcs/kzg/accumulator.rs:28-82): an accumulator as 4 x LIMBS scalar-field limbs.  The reference
 // panics when the limbs do not encode two curve points; here that is an `Error`.

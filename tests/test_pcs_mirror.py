@@ -285,6 +285,62 @@ def test_bdfg21_msm_scalar_program_equals_host_mirror():
         assert [(out[nl + i], pt(sl)) for i, sl in enumerate(mp.rhs_slots)] == calls[1]
 
 
+def test_cpp_multiopen_mirrors_emit_the_python_mirror_pairs(tmp_path):
+    """The C++ host mirrors (`BasicGwc19` in host/cuda_loader.hpp, `BasicBdfg21` in host/pcs.hpp) over a recording loader: every
+    (scalar, base) pair they hand to multi_scalar_multiplication — lhs call, then rhs call — equals the Python mirror's."""
+    import os
+    import struct
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "pcs_mirror_test"
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-o", str(exe), os.path.join(root, "tests", "pcs_mirror_test.cpp")])
+
+    class Recorder:
+        fmt = sv.CANONICAL
+
+        def __init__(self):
+            self.calls = []
+
+        def multi_scalar_multiplication(self, pairs):
+            self.calls.append([(int.from_bytes(sc, "little"), bytes(pt)) for sc, pt in pairs])
+            return bytes(64)
+
+    def run_cpp(blob):
+        inp = tmp_path / "in.bin"
+        inp.write_bytes(blob)
+        out = subprocess.run([str(exe), str(inp)], capture_output=True, text=True, check=True).stdout.split("\n")
+        calls = []
+        for line in out:
+            if line.startswith("msm "):
+                calls.append([])
+            elif line:
+                sc, pt = line.split()
+                calls[-1].append((int(sc, 16), bytes.fromhex(pt)))
+        return calls
+
+    def common(scheme, commitments, queries, z):
+        blob = struct.pack("<BII", scheme, len(commitments), len(queries)) + le(z)
+        for q in queries:
+            blob += struct.pack("<I", q.poly) + le(q.shift) + le(q.eval)
+        return blob + b"".join(commitments) + GEN
+
+    # GWC19
+    fx = make_fixture(seed=8, k=5)
+    qs = gwc19_queries(fx)
+    rec = Recorder()
+    pcs.Gwc19.verify(rec, GEN, [sv.Msm.base(rec, c) for c in fx["C"]], fx["points"][0], qs, pcs.Gwc19Proof(fx["v"], fx["W"], fx["u"]))
+    blob = common(0, fx["C"], qs, fx["points"][0]) + le(fx["v"]) + le(fx["u"]) + struct.pack("<I", len(fx["W"])) + b"".join(fx["W"])
+    assert run_cpp(blob) == rec.calls and len(rec.calls) == 2
+    # SHPLONK
+    for seed in (0, 4):
+        sx = make_shplonk_fixture(seed)
+        rec = Recorder()
+        bdfg21_accumulator(rec, sx)
+        pr = sx["proof"]
+        blob = common(1, sx["C"], sx["queries"], sx["z"]) + le(pr.mu) + le(pr.gamma) + pr.w + le(pr.z_prime) + pr.w_prime
+        assert run_cpp(blob) == rec.calls and len(rec.calls) == 2
+
+
 # ---- GPU ----------------------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
 def test_bdfg21_batch_verifier_pipeline_on_device():
