@@ -439,5 +439,246 @@ inline QuotientProtocol standard_plonk_like_protocol(int k, size_t num_instance 
     return QuotientProtocol{Domain(k), 8, {num_instance}, evaluations, 4, distribute_powers(constraints, alpha)};
 }
 
+// ---- the multi-open verifier's MSM scalars as a program: `Msm` (util/msm.rs) over virtual registers -----------------------------
+// Bases are SLOTS — ('g') the SRS generator carrying the Msm constant, ('c', j) the commitment of polynomial j, ('w', i) the i-th
+// opening-proof point: the bases differ from proof to proof, the slot a base occupies in the final MSM does not.  Every statement
+// below emits in the order of snark_verifier_b200/plonk_eval.py (SymbolicMsm, compile_*_msm_scalars), which follows the reference's
+// evaluation order; tests/test_pcs_mirror.py::test_cpp_msm_scalar_programs_equal_python compares the programs instruction by instruction.
+struct Slot {
+    char kind;      // 'g', 'c', 'w'
+    uint32_t idx;
+    bool operator==(const Slot& o) const { return kind == o.kind && idx == o.idx; }
+};
+class SymbolicMsm {
+  public:
+    using Val = ProgramBuilder::Val;
+    explicit SymbolicMsm(ProgramBuilder& b) : b_(&b) {}
+    static SymbolicMsm base(ProgramBuilder& b, Slot s) { SymbolicMsm m(b); m.terms_.push_back({s, b.constant(fe_from_u64(1))}); return m; }
+    static SymbolicMsm constant_(ProgramBuilder& b, Val v) { SymbolicMsm m(b); m.has_const_ = true; m.const_ = v; return m; }
+    SymbolicMsm operator*(Val k) const {   // scale: constant first, then the terms in order (msm.rs:100-107)
+        SymbolicMsm r(*b_);
+        if (has_const_) { r.has_const_ = true; r.const_ = b_->mul(const_, k); }
+        for (const auto& t : terms_) r.terms_.push_back({t.first, b_->mul(t.second, k)});
+        return r;
+    }
+    SymbolicMsm operator-() const {
+        SymbolicMsm r(*b_);
+        if (has_const_) { r.has_const_ = true; r.const_ = b_->neg(const_); }
+        for (const auto& t : terms_) r.terms_.push_back({t.first, b_->neg(t.second)});
+        return r;
+    }
+    SymbolicMsm operator+(const SymbolicMsm& o) const {   // extend: push dedupes by slot (msm.rs:109-128)
+        SymbolicMsm r = *this;
+        if (o.has_const_) {
+            if (r.has_const_) r.const_ = b_->add(r.const_, o.const_);
+            else { r.has_const_ = true; r.const_ = o.const_; }
+        }
+        for (const auto& t : o.terms_) {
+            auto it = std::find_if(r.terms_.begin(), r.terms_.end(), [&](const std::pair<Slot, Val>& x) { return x.first == t.first; });
+            if (it == r.terms_.end()) r.terms_.push_back(t);
+            else it->second = b_->add(it->second, t.second);
+        }
+        return r;
+    }
+    SymbolicMsm operator-(const SymbolicMsm& o) const { const SymbolicMsm n = -o; return *this + n; }
+    static SymbolicMsm sum(ProgramBuilder& b, const std::vector<SymbolicMsm>& ms) {
+        SymbolicMsm acc(b);
+        for (const auto& m : ms) acc = acc + m;
+        return acc;
+    }
+    bool has_const_ = false;
+    Val const_ = 0;
+    std::vector<std::pair<Slot, Val>> terms_;
+
+  private:
+    ProgramBuilder* b_;
+};
+
+inline std::vector<ProgramBuilder::Val> powers(ProgramBuilder& b, ProgramBuilder::Val x, size_t n) {   // loader.rs:71-78
+    std::vector<ProgramBuilder::Val> out{b.constant(fe_from_u64(1))};
+    if (n > 1) out.push_back(x);
+    for (size_t i = 2; i < n; ++i) out.push_back(b.mul(out.back(), x));
+    out.resize(std::min(out.size(), n));
+    return out;
+}
+
+// program outputs, per proof: the scalars of the lhs MSM followed by those of the rhs MSM; `lhs_slots` / `rhs_slots` name the bases
+struct MsmScalarProgram {
+    FrProgram program;
+    std::vector<Slot> lhs_slots, rhs_slots;
+};
+inline MsmScalarProgram finish_msm_program(ProgramBuilder& b, const SymbolicMsm& lhs, const SymbolicMsm& rhs, size_t total_inputs) {
+    MsmScalarProgram out;
+    std::vector<ProgramBuilder::Val> vals;
+    auto flat = [&](const SymbolicMsm& m, std::vector<Slot>& slots) {
+        if (m.has_const_) { slots.push_back({'g', 0}); vals.push_back(m.const_); }   // evaluate(Some(gen)): (constant, gen) goes first
+        for (const auto& t : m.terms_) { slots.push_back(t.first); vals.push_back(t.second); }
+    };
+    flat(lhs, out.lhs_slots);
+    flat(rhs, out.rhs_slots);
+    b.n_inputs = total_inputs;
+    out.program = b.finish(vals);
+    return out;
+}
+
+struct ShiftQuery { size_t poly; Fe shift; };   // (poly, shift) of one query, protocol order
+
+// `Gwc19::verify` (pcs/kzg/multiopen/gwc19.rs:45-82).  Per-proof input row: [z | v | u | one evaluation per query, in query order]
+inline MsmScalarProgram compile_gwc19_msm_scalars(const std::vector<ShiftQuery>& queries, size_t num_polys) {
+    using Val = ProgramBuilder::Val;
+    ProgramBuilder b;
+    const Val z = b.input(0), v = b.input(1), u = b.input(2);
+    struct Set { Fe shift; std::vector<size_t> polys; std::vector<Val> evals; };
+    std::vector<Set> sets;   // gwc19.rs:140-160
+    for (size_t k = 0; k < queries.size(); ++k) {
+        const Val ev = b.input((uint32_t)(3 + k));
+        auto it = std::find_if(sets.begin(), sets.end(), [&](const Set& s) { return s.shift == queries[k].shift; });
+        if (it == sets.end()) { sets.push_back({queries[k].shift, {}, {}}); it = sets.end() - 1; }
+        it->polys.push_back(queries[k].poly);
+        it->evals.push_back(ev);
+    }
+    size_t max_polys = 0;
+    for (const Set& s : sets) max_polys = std::max(max_polys, s.polys.size());
+    const std::vector<Val> pu = powers(b, u, sets.size());
+    const std::vector<Val> pv = powers(b, v, max_polys);
+    std::vector<SymbolicMsm> commitments;
+    for (size_t j = 0; j < num_polys; ++j) commitments.push_back(SymbolicMsm::base(b, {'c', (uint32_t)j}));
+    SymbolicMsm f(b);
+    for (size_t k = 0; k < sets.size(); ++k) {
+        SymbolicMsm set_msm(b);   // QuerySet::msm (gwc19.rs:120-137)
+        for (size_t i = 0; i < sets[k].polys.size(); ++i) {
+            const SymbolicMsm diff = commitments[sets[k].polys[i]] - SymbolicMsm::constant_(b, sets[k].evals[i]);
+            const SymbolicMsm scaled = diff * pv[i];
+            set_msm = set_msm + scaled;
+        }
+        const SymbolicMsm su = set_msm * pu[k];
+        f = f + su;
+    }
+    std::vector<Val> z_omegas;
+    for (const Set& s : sets) { const Val sh = b.constant(s.shift); z_omegas.push_back(b.mul(sh, z)); }
+    std::vector<SymbolicMsm> rhs;
+    for (size_t i = 0; i < sets.size(); ++i) { const SymbolicMsm w = SymbolicMsm::base(b, {'w', (uint32_t)i}); rhs.push_back(w * pu[i]); }
+    std::vector<SymbolicMsm> uwz;
+    for (size_t i = 0; i < sets.size(); ++i) uwz.push_back(rhs[i] * z_omegas[i]);
+    const SymbolicMsm uwz_sum = SymbolicMsm::sum(b, uwz);
+    const SymbolicMsm lhs = f + uwz_sum;
+    const SymbolicMsm rhs_sum = SymbolicMsm::sum(b, rhs);
+    return finish_msm_program(b, lhs, rhs_sum, 3 + queries.size());
+}
+
+// `Bdfg21::verify` (bdfg21.rs:51-83; query sets :123-175, coefficients :177-371).  Per-proof input row:
+// [z | mu | gamma | z' | one evaluation per query, in query order]; ('w', 0) = W, ('w', 1) = W'.
+inline MsmScalarProgram compile_bdfg21_msm_scalars(const std::vector<ShiftQuery>& queries, size_t num_polys) {
+    using Val = ProgramBuilder::Val;
+    ProgramBuilder b;
+    const Val z = b.input(0), mu = b.input(1), gamma = b.input(2), z_prime = b.input(3);
+    struct PolyShifts { size_t poly; std::vector<Fe> shifts; std::vector<Val> evals; };
+    std::vector<PolyShifts> ps;
+    for (size_t k = 0; k < queries.size(); ++k) {
+        const Val ev = b.input((uint32_t)(4 + k));
+        auto it = std::find_if(ps.begin(), ps.end(), [&](const PolyShifts& p) { return p.poly == queries[k].poly; });
+        if (it == ps.end()) ps.push_back({queries[k].poly, {queries[k].shift}, {ev}});
+        else if (std::find(it->shifts.begin(), it->shifts.end(), queries[k].shift) == it->shifts.end()) { it->shifts.push_back(queries[k].shift); it->evals.push_back(ev); }
+    }
+    struct Set { std::vector<Fe> shifts; std::vector<size_t> polys; std::vector<std::vector<Val>> evals; };
+    std::vector<Set> sets;
+    for (const PolyShifts& p : ps) {
+        auto same = [&](const Set& s) {
+            if (s.shifts.size() != p.shifts.size()) return false;
+            for (const Fe& x : p.shifts) if (std::find(s.shifts.begin(), s.shifts.end(), x) == s.shifts.end()) return false;
+            return true;
+        };
+        auto it = std::find_if(sets.begin(), sets.end(), same);
+        if (it == sets.end()) { sets.push_back({p.shifts, {p.poly}, {p.evals}}); continue; }
+        if (std::find(it->polys.begin(), it->polys.end(), p.poly) != it->polys.end()) continue;
+        it->polys.push_back(p.poly);
+        std::vector<Val> ordered;
+        for (const Fe& lhs : it->shifts) ordered.push_back(p.evals[std::find(p.shifts.begin(), p.shifts.end(), lhs) - p.shifts.begin()]);
+        it->evals.push_back(ordered);
+    }
+    // query_set_coeffs
+    std::vector<Fe> superset;
+    for (const Set& s : sets) for (const Fe& x : s.shifts) if (std::find(superset.begin(), superset.end(), x) == superset.end()) superset.push_back(x);
+    std::sort(superset.begin(), superset.end());
+    size_t size = 2;
+    for (const Set& s : sets) size = std::max(size, s.shifts.size());
+    const std::vector<Val> powers_of_z = powers(b, z, size);
+    std::vector<std::pair<Fe, Val>> zp_minus;
+    for (const Fe& x : superset) { const Val c = b.constant(x); const Val zx = b.mul(z, c); zp_minus.push_back({x, b.sub(z_prime, zx)}); }
+    auto zp_of = [&](const Fe& x) { for (auto& kv : zp_minus) if (kv.first == x) return kv.second; throw Error("shift not in superset"); };
+    struct Coeff { std::vector<Val> bary, eval_coeffs; Val z_s = 0; bool has_z_s_1 = false; Val z_s_1 = 0; bool has_cc = false; Val commitment_coeff = 0, r_eval_coeff = 0; };
+    std::vector<Coeff> coeffs;
+    bool have_first = false;
+    Val first_z_s = 0;
+    for (const Set& s : sets) {
+        Coeff c;
+        const Val zz = powers_of_z[1], z_pow = powers_of_z[s.shifts.size() - 1];
+        for (size_t j = 0; j < s.shifts.size(); ++j) {
+            Fe ell = fe_from_u64(1);
+            for (size_t i = 0; i < s.shifts.size(); ++i) if (i != j) ell = fe_mul(ell, fe_sub(s.shifts[j], s.shifts[i]));
+            const Val m1 = b.mul(z_pow, z_prime);
+            const Val c1 = b.constant(ell);
+            const Val t1 = b.mul(m1, c1);
+            const Val m2 = b.mul(z_pow, zz);
+            const Val c2 = b.constant(fe_neg(fe_mul(ell, s.shifts[j])));
+            const Val t2 = b.mul(m2, c2);
+            c.bary.push_back(b.add(t1, t2));
+        }
+        bool have = false;
+        Val z_s = 0;
+        for (const Fe& x : s.shifts) { z_s = have ? b.mul(z_s, zp_of(x)) : zp_of(x); have = true; }
+        c.z_s = z_s;
+        if (have_first) { c.has_z_s_1 = true; c.z_s_1 = first_z_s; }
+        else { have_first = true; first_z_s = z_s; }
+        coeffs.push_back(c);
+    }
+    std::vector<Val> den1;
+    for (const Coeff& c : coeffs) { den1.insert(den1.end(), c.bary.begin(), c.bary.end()); if (c.has_z_s_1) den1.push_back(c.z_s); }
+    const std::vector<Val> inv1 = b.batch_invert(den1);
+    size_t k = 0;
+    std::vector<Val> den2;
+    for (Coeff& c : coeffs) {
+        c.eval_coeffs.assign(inv1.begin() + k, inv1.begin() + k + c.bary.size());
+        k += c.bary.size();
+        if (c.has_z_s_1) { c.has_cc = true; c.commitment_coeff = b.mul(c.z_s_1, inv1[k]); ++k; }
+        Val wsum = c.eval_coeffs[0];
+        for (size_t i = 1; i < c.eval_coeffs.size(); ++i) wsum = b.add(wsum, c.eval_coeffs[i]);
+        den2.push_back(wsum);
+    }
+    const std::vector<Val> inv2 = b.batch_invert(den2);
+    for (size_t i = 0; i < coeffs.size(); ++i) coeffs[i].r_eval_coeff = coeffs[i].has_cc ? b.mul(coeffs[i].commitment_coeff, inv2[i]) : inv2[i];
+    // verify
+    size_t max_polys = 0;
+    for (const Set& s : sets) max_polys = std::max(max_polys, s.polys.size());
+    const std::vector<Val> powers_of_mu = powers(b, mu, max_polys);
+    const std::vector<Val> powers_of_gamma = powers(b, gamma, sets.size());
+    std::vector<SymbolicMsm> commitments;
+    for (size_t j = 0; j < num_polys; ++j) commitments.push_back(SymbolicMsm::base(b, {'c', (uint32_t)j}));
+    SymbolicMsm f(b);
+    for (size_t si = 0; si < sets.size(); ++si) {
+        const Set& st = sets[si];
+        const Coeff& co = coeffs[si];
+        SymbolicMsm set_msm(b);
+        for (size_t i = 0; i < st.polys.size(); ++i) {
+            const SymbolicMsm commitment = co.has_cc ? commitments[st.polys[i]] * co.commitment_coeff : commitments[st.polys[i]];
+            Val r_eval = b.mul(co.eval_coeffs[0], st.evals[i][0]);
+            for (size_t j = 1; j < co.eval_coeffs.size(); ++j) { const Val t = b.mul(co.eval_coeffs[j], st.evals[i][j]); r_eval = b.add(r_eval, t); }
+            r_eval = b.mul(r_eval, co.r_eval_coeff);
+            const SymbolicMsm diff = commitment - SymbolicMsm::constant_(b, r_eval);
+            const SymbolicMsm scaled = diff * powers_of_mu[i];
+            set_msm = set_msm + scaled;
+        }
+        const SymbolicMsm sg = set_msm * powers_of_gamma[si];
+        f = f + sg;
+    }
+    const SymbolicMsm w_base = SymbolicMsm::base(b, {'w', 0});
+    const SymbolicMsm wz = w_base * coeffs[0].z_s;
+    f = f - wz;
+    const SymbolicMsm rhs = SymbolicMsm::base(b, {'w', 1});
+    const SymbolicMsm rz = rhs * z_prime;
+    const SymbolicMsm lhs = f + rz;
+    return finish_msm_program(b, lhs, rhs, 4 + queries.size());
+}
+
 }  // namespace plonk
 }  // namespace snarkv

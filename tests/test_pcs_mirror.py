@@ -341,6 +341,39 @@ def test_cpp_multiopen_mirrors_emit_the_python_mirror_pairs(tmp_path):
         assert run_cpp(blob) == rec.calls and len(rec.calls) == 2
 
 
+def test_cpp_msm_scalar_programs_equal_python(tmp_path):
+    """host/plonk_eval.hpp `compile_gwc19_msm_scalars` / `compile_bdfg21_msm_scalars` (SymbolicMsm over a ProgramBuilder in C++)
+    emit, instruction for instruction and slot for slot, the programs the Python compiler emits."""
+    import os
+    import struct
+    import subprocess
+    from snark_verifier_b200 import plonk_eval as pe
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "plonk_compile_test"
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-o", str(exe), os.path.join(root, "tests", "plonk_compile_test.cpp")])
+    omega = pe.root_of_unity(8)
+    shifts = [1, omega, pow(omega, -1, R)]
+    gwc_structure = [(j, shifts[(j * 7) % 3]) for j in range(17)] + [(3, shifts[1]), (5, shifts[2])]
+    sx = make_shplonk_fixture(1)
+    cases = [("gwc19", gwc_structure, 17, pe.compile_gwc19_msm_scalars),
+             ("bdfg21", [(q.poly, q.shift) for q in sx["queries"]], len(sx["C"]), pe.compile_bdfg21_msm_scalars),
+             ("bdfg21", [(j, shifts[j % 3]) for j in range(6)] + [(2, shifts[0]), (4, shifts[0]), (4, shifts[1])], 6, pe.compile_bdfg21_msm_scalars)]
+    for mode, structure, npoly, compile_py in cases:
+        inp = tmp_path / "q.bin"
+        inp.write_bytes(struct.pack("<II", npoly, len(structure)) + b"".join(struct.pack("<I", p) + le(sh) for p, sh in structure))
+        out = subprocess.run([str(exe), mode, str(inp)], capture_output=True, text=True, check=True).stdout.splitlines()
+        mp = compile_py(structure, npoly)
+        prog = mp.program
+        hdr = out[0].split()
+        assert (int(hdr[1]), int(hdr[3])) == (prog.n_regs, prog.n_inputs)
+        assert [tuple(int(x) for x in l.split()[1:]) for l in out if l.startswith("i ")] == [tuple(i) for i in prog.instrs]
+        assert [int(l.split()[1], 16) for l in out if l.startswith("c ")] == prog.consts
+        assert [int(x) for x in [l for l in out if l.startswith("o")][0].split()[1:]] == prog.outputs
+        slot = lambda sl: "g0" if sl == ("g",) else "%s%d" % (sl[0], sl[1])
+        assert [l for l in out if l.startswith("l")][0].split()[1:] == [slot(sl) for sl in mp.lhs_slots]
+        assert [l for l in out if l.startswith("r")][0].split()[1:] == [slot(sl) for sl in mp.rhs_slots]
+
+
 # ---- GPU ----------------------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
 def test_bdfg21_batch_verifier_pipeline_on_device():
