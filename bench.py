@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""bench.py — BN254 G1 MSM throughput on B200 (BASELINE.json metric: M scalar-mults/s on a 2^24-term MSM, 1/2/4/8 GPUs).
+"""bench.py — BN254 G1 MSM throughput on B200 (BASELINE.json metric: M scalar-mults/s on a 2^24-term MSM; proofs verified/s;
+1/2/4/8 GPUs).
 
 One "step" = one full pass of the hot path over the 2^24-term workload: every rank runs the Pippenger pipeline on its
 contiguous chunk of the terms (util/msm.rs:322-332 shape), the 96-byte Jacobian partials are all-gathered over NCCL, and
@@ -11,11 +12,15 @@ every rank folds them and normalises (util/msm.rs:333-335 + native.rs:70).  Tota
              result inside the timed region
   roofline   dominant kernel (msm_bucket_accumulate[_affine]): algorithmic bytes (96 B/term) / its live CUDA-event duration vs the
              measured HBM peak — plus the integer-pipe view, because this kernel is IMAD-bound, not HBM-bound
+  aux        the metric's second half and BASELINE configs 3-5 at THIS N, sharded over the ranks: proofs verified/s (4096 GWC19
+             proofs, sharded by proof, one RLC + one pairing per rank), independent KZG decisions/s (4096 and 2^20 checks, check
+             i -> rank i mod N), RLC-fused decide_all, config-4 aggregation jobs/s (replicas), MSM size sweep 2^10..2^26
   cpu_baseline / --impl reference
-             the oracle's restatement of the reference's chunk-parallel Pippenger (util/msm.rs:308-343) on all host cores,
-             on a bounded sample of the same synthetic workload
+             the oracle's restatement of the reference's chunk-parallel Pippenger (util/msm.rs:308-343) on all host cores, on the
+             SAME 2^24-term workload (one full-size MSM per step)
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -31,20 +36,43 @@ SEED = 2024
 ALG_BYTES_PER_TERM = 96            # 64 B affine point + 32 B scalar, each read once
 MADD_MULMODS = 10                  # XYZZ mixed addition: 8M + 2S (csrc/g1.cuh)
 AFFINE_MULMODS = 6                 # batched-affine addition: 3 for the shared inversion + 1M + 1S + 1M (csrc/bucket_affine.cuh)
-IMAD_PER_MULMOD = 170              # IMAD-pipe instructions per Montgomery multiplication (cuobjdump: 150 IMAD.WIDE + 20 IMAD)
+IMAD_PER_MULMOD = 152              # FMA-pipe instructions per Montgomery multiplication (cuobjdump: 122 IMAD.WIDE + 30 IMAD/IMAD.HI/IMAD.X)
+TRAFFIC_JSON = os.path.join("profiles", "r02_traffic.json")
+KERNEL_SOURCES = ("msm.cu", "bucket_affine.cuh", "sort.cuh", "g1.cuh", "fp.cuh", "fp_ptx.inc")
+
+
+def workload_name(log_n):
+    """The ONE description of the workload both arms (--impl cuda / reference) print in config.workload."""
+    return "BN254 G1 MSM, 2^%d uniformly random scalars x points [t_i]G (seed %d)" % (log_n, SEED)
+
+
+def kernel_source_hash():
+    """sha256 over the sources the MSM kernels are built from: an ncu traffic capture is only quoted for the code it was taken on."""
+    h = hashlib.sha256()
+    for fn in KERNEL_SOURCES:
+        p = os.path.join(ROOT, "snark_verifier_b200", "csrc", fn)
+        if os.path.exists(p):
+            with open(p, "rb") as f:
+                h.update(f.read())
+    return h.hexdigest()[:16]
 
 
 def ncu_capture(kernel, log_n, c_bits):
-    """DRAM traffic and FMA-heavy pipe utilisation of `kernel` from the committed ncu --set full capture, if it was taken on
-    this very configuration (profiles/r01_traffic.json); None otherwise."""
+    """DRAM traffic and FMA-heavy pipe utilisation of `kernel` from the committed `ncu --set full` capture (tools/ncu_traffic.py
+    writes profiles/r02_traffic.json) — only if it was taken on this very configuration AND on the kernel sources of this tree.
+    -> (record | None, note)"""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        with open(os.path.join(ROOT, TRAFFIC_JSON)) as f:
             rec = json.load(f)[kernel]
-        if rec["log_n"] == log_n and rec["window_bits"] == c_bits:
-            return rec
     except Exception:
-        pass
-    return None
+        return None, "no ncu capture committed for %s" % kernel
+    if rec.get("log_n") != log_n or rec.get("window_bits") != c_bits:
+        return None, "ncu capture is for another configuration (2^%s terms, c=%s)" % (rec.get("log_n"), rec.get("window_bits"))
+    if rec.get("source_hash") != kernel_source_hash():
+        print("bench.py: %s is STALE (kernel sources changed since the capture): roofline.traffic omitted; re-run tools/ncu_traffic.py"
+              % TRAFFIC_JSON, file=sys.stderr, flush=True)
+        return None, "ncu capture is older than the kernel sources (stale): omitted"
+    return rec, "ncu --set full capture of this kernel on this configuration and these sources (%s)" % rec.get("source", TRAFFIC_JSON)
 
 
 def per_kernel_hbm(stages, n, windows, hbm_peak, cap, acc_ms):
@@ -52,6 +80,7 @@ def per_kernel_hbm(stages, n, windows, hbm_peak, cap, acc_ms):
     copy peak.  For the accumulation kernel the ALGORITHMIC bytes are the 96 B/term of the headline roofline; its `traffic_frac` is
     the DRAM traffic ncu measured per launch over the same live time (what the memory system actually sustains)."""
     rows = []
+
     def row(kernel, stage, bytes_per_term, what):
         ms = stages.get(stage)
         if ms:
@@ -59,6 +88,8 @@ def per_kernel_hbm(stages, n, windows, hbm_peak, cap, acc_ms):
             rows.append({"kernel": kernel, "ms": ms, "algorithmic_bytes_per_term": bytes_per_term, "achieved_gbs": gbs, "frac": gbs / hbm_peak, "what": what})
     row("k_digits", "msm_digits_count", 32 + 4 * windows, "scalar read once, one 4-byte signed digit per window written (+ histogram atomics in L2)")
     row("k_scatter", "msm_digits_scatter", 8 * windows, "digits read, 4-byte term references written at random inside one window's L2-resident region")
+    row("k_sort_partition", "msm_sort_partition", 32 + 8 * windows, "scalar read once, one 8-byte (digit, term) record per window written into its coarse partition")
+    row("k_sort_buckets", "msm_sort_buckets", 12 * windows, "8-byte records read, 4-byte term references written into their bucket runs (+ bucket counts)")
     row("k_points_prepare", "msm_points_prepare", 128, "canonical affine points read, Montgomery copy written")
     if cap:
         gbs = cap["dram_bytes_per_launch"] / (acc_ms / 1e3) / 1e9
@@ -128,23 +159,6 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_pippenger_sample(log_n, threads, reps=1):
-    """Oracle restatement of util/msm.rs:308-343 (`parallel` feature) on `threads` host threads; returns (terms/s, n)."""
-    import oracle
-    n = 1 << log_n
-    # inputs in halo2curves' in-memory (Montgomery) layout, prepared outside the timed region: the Rust reference is handed
-    # `&[Fr]` / `&[G1Affine]` and never parses bytes on this path
-    s = oracle.to_mont_batch(1, oracle.synth_scalars(SEED, 0, n), n, threads)
-    p = oracle.to_mont_batch(0, oracle.synth_points(SEED, 0, n, threads), 2 * n, threads)
-    best = None
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        oracle.msm_pippenger_raw(s, p, n, threads)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return n / best, n, best
-
-
 def cpu_native_extras(threads):
     """The other two CPU legs SURVEY §8(d) names, on bounded samples: (1) the LITERAL NativeLoader MSM — the fold of
     base * scalar over the pairs, loader/native.rs:61-71, single-threaded like the reference's verifier (linear in n, so a
@@ -169,104 +183,158 @@ def cpu_native_extras(threads):
     return out
 
 
-def kzg_aux(L, sv, torch, stream, dev):
-    """KZG decide throughput on synthetic valid accumulators (a_i s G, a_i G) — the shape of the reference's own mock
-    accumulator (system/halo2/test/kzg.rs:37-45): per-check decisions (decider.rs:84-93) and the RLC-fused decide_all
-    (decider.rs:146-185 shape: two 4096-term MSMs + ONE pairing).  All operands are produced on the device."""
-    import ctypes
-    n = 4096
-    out = {}
-    try:
-        # key: g2 = generator, s_g2 = [s] g2 with s = 1 (accumulators (a G, a G) are then valid); enough for throughput
-        g2 = bytes.fromhex(
-            "edf692d95cbdde46ddda5ef7d422436779445c5e66006a42761e1f12efde0018c212f3aeb785e49712e7a9353349aaf1255dfb31b7bf60723a480d9293938e19"
-            "aa7dfa6601cce64c7bd3430c69e7d1e38f40cb8d8071ab4aeb6d8cdba55ec8125b9722d1dcdaac55f38eb37033314bbc95330c69ad999eec75f05f58d0890609")
-        gen = (1).to_bytes(32, "little") + (2).to_bytes(32, "little")
-        kz = sv.KzgAs(L, sv.KzgDecidingKey(gen, g2, g2))
-        with torch.cuda.stream(stream):
-            pts = torch.empty(n * 64, dtype=torch.uint8, device=dev)
-            L.synth_points_device(SEED + 1, 0, n, pts.data_ptr())
-            acc = torch.zeros(n, dtype=torch.uint8, device=dev)
+G2_GEN = bytes.fromhex(
+    "edf692d95cbdde46ddda5ef7d422436779445c5e66006a42761e1f12efde0018c212f3aeb785e49712e7a9353349aaf1255dfb31b7bf60723a480d9293938e19"
+    "aa7dfa6601cce64c7bd3430c69e7d1e38f40cb8d8071ab4aeb6d8cdba55ec8125b9722d1dcdaac55f38eb37033314bbc95330c69ad999eec75f05f58d0890609")
+G1_GEN = (1).to_bytes(32, "little") + (2).to_bytes(32, "little")
 
-            def timed(fn, reps):
+
+class Aux:
+    """Secondary measurements at N ranks.  Every leg: all ranks enter together (barrier), each works on ITS shard, local time is
+    taken (CUDA events on the launch stream for device-resident legs, wall clock around the synchronous C-ABI call for host-buffer
+    legs) after at least one untimed warm-up call, and the reported time is the max over ranks; a leg that throws on a rank reports
+    the error instead of a number but never skips a barrier."""
+
+    def __init__(self, sv, torch, dist, L, stream, dev, rank, world):
+        self.sv, self.torch, self.dist, self.L, self.stream, self.dev, self.rank, self.world = sv, torch, dist, L, stream, dev, rank, world
+        self.out = {}
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce(self, ms, ok, extra_sum=None):
+        """-> (max ms over ranks, all ok, sum of extra over ranks)"""
+        torch = self.torch
+        t = torch.tensor([ms if ms is not None else float("nan"), 1.0 if ok else 0.0, extra_sum or 0.0], device=self.dev, dtype=torch.float64)
+        if self.world > 1:
+            mx = t.clone(); self.dist.all_reduce(mx, op=self.dist.ReduceOp.MAX)
+            mn = t.clone(); self.dist.all_reduce(mn, op=self.dist.ReduceOp.MIN)
+            sm = t.clone(); self.dist.all_reduce(sm, op=self.dist.ReduceOp.SUM)
+            return float(mx[0]), bool(mn[1] > 0.5), float(sm[2])
+        return float(t[0]), bool(t[1] > 0.5), float(t[2])
+
+    def timed_events(self, fn, reps, warm=2):
+        torch, stream = self.torch, self.stream
+        with torch.cuda.stream(stream):
+            for _ in range(warm):
                 fn()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(stream)
-                for _ in range(reps):
-                    fn()
-                e1.record(stream)
-                stream.synchronize()
-                return e0.elapsed_time(e1) / reps
-            ms_batch = timed(lambda: kz.decide_batch_device(pts.data_ptr(), pts.data_ptr(), n, acc.data_ptr()), 3)
-            ok_batch = bool(acc.min().item() == 1)
-            ms_one = timed(lambda: kz.decide_batch_device(pts.data_ptr(), pts.data_ptr(), 1, acc.data_ptr()), 3)
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(reps):
+                fn()
+            e1.record(stream)
         stream.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    def timed_wall(self, fn, reps, warm=2):
+        for _ in range(warm):
+            fn()
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        self.torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / reps * 1e3
+
+    def leg(self, name, body):
+        """body() -> (local ms | None, ok, dict of fields, units for the rate, rate key, extra)"""
+        try:
+            self.barrier()
+            res = body()
+        except Exception as e:   # the headline metric must still print; every rank still reaches the reduction below
+            res = (None, False, {"error": repr(e)}, 0, None)
+        ms, ok, fields, units, key = res
+        ms_max, ok_all, _ = self.reduce(ms, ok)
+        rec = dict(fields)
+        if ms is not None and ms_max == ms_max:
+            rec["ms"] = ms_max
+            if key:
+                rec[key] = units / ms_max * 1e3
+        rec["ok"] = ok_all
+        self.out[name] = rec
+
+    # ---- legs ---------------------------------------------------------------------------------------------------------------
+    def run(self, do_pairing_2p20=True):
+        sv, torch, L, stream, dev, rank, world = self.sv, self.torch, self.L, self.stream, self.dev, self.rank, self.world
+        import numpy as np
+        kz = sv.KzgAs(L, sv.KzgDecidingKey(G1_GEN, G2_GEN, G2_GEN))     # key with s = 1: accumulators (aG, aG) are valid
+        n = 4096
+        mine = list(range(rank, n, world))                               # check i -> rank i mod N  (SURVEY §8e)
+        with torch.cuda.stream(stream):
+            pts_all = torch.empty(n * 64, dtype=torch.uint8, device=dev)
+            L.synth_points_device(SEED + 1, 0, n, pts_all.data_ptr())
+            pts = pts_all.view(n, 64)[torch.tensor(mine, device=dev)].contiguous().view(-1)
+            acc = torch.zeros(len(mine), dtype=torch.uint8, device=dev)
+        stream.synchronize()
+        nl = len(mine)
+
+        def decide_independent():
+            ms = self.timed_events(lambda: kz.decide_batch_device(pts.data_ptr(), pts.data_ptr(), nl, acc.data_ptr()), 3)
+            return ms, bool(acc.min().item() == 1), {"checks": n, "what": "4096 separate 2-pair pairing checks (decider.rs:84-93), check i -> rank i mod N, "
+                                                                           "operands resident in HBM"}, n, "checks_per_s"
+        self.leg("decide_independent", decide_independent)
+
+        def decide_single():
+            ms = self.timed_events(lambda: kz.decide_batch_device(pts.data_ptr(), pts.data_ptr(), 1, acc.data_ptr()), 5)
+            return ms, bool(acc[0].item() == 1), {"what": "one KzgAs::decide (decider.rs:70-82), operands resident; latency, not sharded"}, 1, None
+        self.leg("decide_single_latency", decide_single)
+
+        if do_pairing_2p20:
+            def decide_2p20():
+                N = 1 << 20
+                loc = N // world
+                with torch.cuda.stream(stream):
+                    big = torch.empty(loc * 64, dtype=torch.uint8, device=dev)
+                    L.synth_points_device(SEED + 5, rank * loc, loc, big.data_ptr())
+                    rhs = big.clone()
+                    v_l, v_r = big.view(loc, 64), rhs.view(loc, 64)
+                    bad = torch.arange(0, loc - 1, 7, device=dev)          # every 7th check of the shard is made invalid
+                    v_r[bad] = v_l[bad + 1]
+                    a = torch.zeros(loc, dtype=torch.uint8, device=dev)
+                ms = self.timed_events(lambda: kz.decide_batch_device(big.data_ptr(), rhs.data_ptr(), loc, a.data_ptr()), 1, warm=1)
+                exp = torch.ones(loc, dtype=torch.uint8, device=dev); exp[bad] = 0
+                return ms, bool((a == exp).all().item()), {"checks": N, "what": "BASELINE config 5: 2^20 independent 2-pair checks (every 7th invalid), sharded "
+                                                                                "over the ranks in contiguous blocks, operands resident; accept vector verified"}, N, "checks_per_s"
+            self.leg("decide_batch_2p20", decide_2p20)
+
         host_pts = pts.cpu().numpy()
         rho = (0x123456789ABCDEF0FEDCBA987654321).to_bytes(32, "little")
-        t0 = time.perf_counter()
-        reps = 3
-        for _ in range(reps):
-            ok_fused, _ = kz.decide_all_fused(host_pts, host_pts, n, rho)
-        ms_fused = (time.perf_counter() - t0) / reps * 1e3
-        # BASELINE config 3: batch-verify 4096 proofs = one fused G1 MSM per side + ONE pairing.  Per proof a GWC19-shaped
-        # 21-term lhs / 3-term rhs MSM (SURVEY §3.1); the terms are synthetic but consistent (lhs_j == rhs_j as points, key s = 1),
-        # so the batch must ACCEPT: rhs_j = 3 random terms, lhs_j = the same 3 terms + 9 cancelling pairs (s, P), (r - s, P).
-        import numpy as np
-        R_MOD = sv.R_MODULUS
-        m_proofs = 4096
-        with torch.cuda.stream(stream):
-            sc = torch.empty(m_proofs * 12 * 32, dtype=torch.uint8, device=dev)
-            pt = torch.empty(m_proofs * 12 * 64, dtype=torch.uint8, device=dev)
-            L.synth_scalars_device(SEED + 2, 0, m_proofs * 12, sc.data_ptr())
-            L.synth_points_device(SEED + 2, 0, m_proofs * 12, pt.data_ptr())
-        stream.synchronize()
-        sc_h = sc.cpu().numpy().reshape(m_proofs, 12, 32)
-        pt_h = pt.cpu().numpy().reshape(m_proofs, 12, 64)
-        neg = np.empty((m_proofs, 9, 32), dtype=np.uint8)
-        for j in range(m_proofs):                              # r - s for the 9 cancelling pairs (host-side test-data prep)
-            for k in range(9):
-                v = int.from_bytes(sc_h[j, 3 + k].tobytes(), "little")
-                neg[j, k] = np.frombuffer(((R_MOD - v) % R_MOD).to_bytes(32, "little"), dtype=np.uint8)
-        lhs_s = np.concatenate([sc_h[:, :3], sc_h[:, 3:], neg], axis=1).reshape(-1)           # 3 + 9 + 9 = 21 terms
-        lhs_p = np.concatenate([pt_h[:, :3], pt_h[:, 3:], pt_h[:, 3:]], axis=1).reshape(-1)
-        rhs_s = np.ascontiguousarray(sc_h[:, :3]).reshape(-1)
-        rhs_p = np.ascontiguousarray(pt_h[:, :3]).reshape(-1)
-        lhs_off = np.arange(m_proofs + 1, dtype=np.uint64) * 21
-        rhs_off = np.arange(m_proofs + 1, dtype=np.uint64) * 3
-        reps = 3
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            f_lhs = L.msm_batch_rlc(lhs_s, lhs_p, lhs_off, rho)
-            f_rhs = L.msm_batch_rlc(rhs_s, rhs_p, rhs_off, rho)
-            acc1, _ = kz.decide_batch(f_lhs, f_rhs, 1)
-        ms_bv = (time.perf_counter() - t0) / reps * 1e3
-        out = {"accumulators": n,
-               "batch_verify_fused": {"proofs_per_s": m_proofs / ms_bv * 1e3, "ms": ms_bv, "accept": acc1 == b"\x01", "proofs": m_proofs,
-                                      "what": "4096 proofs x (21-term lhs + 3-term rhs) MSMs fused by powers of rho into two MSMs "
-                                              "(86016 and 12288 terms) + one pairing; host buffers in, wall clock incl. H2D"},
-               "decide_independent": {"checks_per_s": n / ms_batch * 1e3, "ms": ms_batch, "all_accept": ok_batch,
-                                      "what": "4096 separate 2-pair pairing checks, operands resident in HBM"},
-               "decide_single_latency_ms": ms_one,
-               "decide_all_fused": {"proofs_per_s": n / ms_fused * 1e3, "ms": ms_fused, "accept": bool(ok_fused),
-                                    "what": "host buffers in; powers of rho + two 4096-term MSMs + one pairing (wall clock incl. H2D)"}}
+
+        def decide_all_fused():
+            res = {}
+            def call():
+                res["ok"], _ = kz.decide_all_fused(host_pts, host_pts, nl, rho)
+            ms = self.timed_wall(call, 3)
+            return ms, bool(res["ok"]), {"accumulators": n, "what": "RLC decide_all (decider.rs:146-185): every rank fuses ITS accumulators (powers of rho + two "
+                                                                    "MSMs + one pairing), verdict = AND over ranks; host buffers in, wall clock incl. H2D"}, n, "proofs_per_s"
+        self.leg("decide_all_fused", decide_all_fused)
+
         # BASELINE config 3 with the REAL multi-open structure: 4096 GWC19 proofs of a StandardPlonk-shaped protocol (17 committed
         # polynomials opened at 3 rotations => 21-term lhs / 3-term rhs per proof, SURVEY §3.1) under the SRS secret s = 1 of the key
-        # above.  Honest proofs are built backwards from random discrete logs (commitments and opening proofs as single-term MSMs on
-        # the device, outside the timed region); timed: per-proof MSM scalars by the device program compiled from Gwc19::verify,
-        # one fused MSM per side (powers of rho), one pairing.  Host buffers in, wall clock.
-        try:
+        # above, sharded by proof.  Honest proofs are built backwards from random discrete logs (commitments and opening proofs as
+        # single-term MSMs on the device, outside the timed region); timed: per-proof MSM scalars by the device program compiled from
+        # Gwc19::verify, one fused MSM per side (powers of rho), one pairing — per rank, on its shard.  Host buffers in, wall clock.
+        m_proofs = 4096
+        my_proofs = list(range(rank, m_proofs, world))
+
+        def batch_verify_gwc19():
             import random as _random
             from snark_verifier_b200 import pcs, plonk_eval as pe
-            rnd = _random.Random(SEED + 4)
+            R_MOD = sv.R_MODULUS
             npoly = 17
             omega = pe.root_of_unity(12)
             shifts = [1, omega, pow(omega, -1, R_MOD)]
             structure = [(j, shifts[j % 3]) for j in range(npoly)]
-            bv = pcs.Gwc19BatchVerifier(L, kz, gen, structure, npoly)
+            bv = pcs.Gwc19BatchVerifier(L, kz, G1_GEN, structure, npoly)
             cpd = bv.compiled
             le32 = lambda v: (v % R_MOD).to_bytes(32, "little")
             dl, rows = [], []                                           # per proof: discrete logs of its 17 commitments + 3 W's
-            for j in range(m_proofs):
+            for j in my_proofs:
+                rnd = _random.Random((SEED + 4) * 1000003 + j)
                 z, v, u = (rnd.randrange(1, R_MOD) for _ in range(3))
                 c = [rnd.randrange(R_MOD) for _ in range(npoly)]
                 e = [rnd.randrange(R_MOD) for _ in range(npoly)]
@@ -277,83 +345,134 @@ def kzg_aux(L, sv, torch, stream, dev):
                 dl.append(c + w)
                 rows.append(b"".join(le32(x) for x in [z, v, u] + e))
             flat = [x for d in dl for x in d]
-            pts = L.msm_batch(b"".join(le32(x) for x in flat), gen * len(flat), list(range(len(flat) + 1)))
+            gp = L.msm_batch(b"".join(le32(x) for x in flat), G1_GEN * len(flat), list(range(len(flat) + 1)))
             per = npoly + 3
             slot_ix = lambda sl: None if sl == ("g",) else (sl[1] if sl[0] == "c" else npoly + sl[1])
-            pack = lambda slots: b"".join(gen if slot_ix(sl) is None else pts[j * per + slot_ix(sl)] for j in range(m_proofs) for sl in slots)
+            mp = len(my_proofs)
+            pack = lambda slots: b"".join(G1_GEN if slot_ix(sl) is None else gp[j * per + slot_ix(sl)] for j in range(mp) for sl in slots)
             rows_b, lhs_pb, rhs_pb = b"".join(rows), pack(cpd.lhs_slots), pack(cpd.rhs_slots)
             rho_i = int.from_bytes(rho, "little")
-            kz.decide(bv.accumulate_packed(rows_b, lhs_pb, rhs_pb, m_proofs, rho_i))       # warm-up; raises unless the batch accepts
-            t0 = time.perf_counter()
-            for _ in range(3):
-                kz.decide(bv.accumulate_packed(rows_b, lhs_pb, rhs_pb, m_proofs, rho_i))
-            ms_g = (time.perf_counter() - t0) / 3 * 1e3
-            out["batch_verify_gwc19"] = {"proofs_per_s": m_proofs / ms_g * 1e3, "ms": ms_g, "accept": True, "proofs": m_proofs,
-                                         "lhs_terms_per_proof": len(cpd.lhs_slots), "rhs_terms_per_proof": len(cpd.rhs_slots),
-                                         "what": "4096 honest GWC19 proofs (17 polynomials, 3 rotations): MSM scalars by the device program "
-                                                 "compiled from Gwc19::verify + two fused MSMs (powers of rho) + one pairing; wall clock incl. H2D"}
-        except Exception as e:
-            out["batch_verify_gwc19"] = {"error": repr(e)}
+            ms = self.timed_wall(lambda: kz.decide(bv.accumulate_packed(rows_b, lhs_pb, rhs_pb, mp, rho_i)), 3)   # raises unless it accepts
+            return ms, True, {"proofs": m_proofs, "lhs_terms_per_proof": len(cpd.lhs_slots), "rhs_terms_per_proof": len(cpd.rhs_slots),
+                              "what": "4096 honest GWC19 proofs (17 polynomials, 3 rotations), sharded by proof: per rank the MSM scalars by the device "
+                                      "program compiled from Gwc19::verify + two fused MSMs (powers of rho, every point validated on the device) + one "
+                                      "pairing; verdict = AND over ranks; wall clock incl. H2D"}, m_proofs, "proofs_per_s"
+        self.leg("batch_verify_gwc19", batch_verify_gwc19)
+
         # BASELINE config 4: one aggregation job = KzgAs::verify over 256 accumulators (accumulation.rs:41-63: two 256-term MSMs with
-        # the powers of r computed on the device) + one decide (decider.rs:70-82); host buffers in, wall clock
-        try:
+        # the powers of r computed on the device) + one decide (decider.rs:70-82); host buffers in, wall clock.  A single job does not
+        # shard (latency-bound): REPLICAS — every rank runs its own jobs, jobs/s is the sum over ranks.
+        def aggregate_256():
             n4 = 256
-            accs = [sv.KzgAccumulator(host_pts[64 * i:64 * i + 64].tobytes(), host_pts[64 * i:64 * i + 64].tobytes()) for i in range(n4)]
-            kz.decide(kz.verify(accs, rho))
-            t0 = time.perf_counter()
-            for _ in range(5):
-                kz.decide(kz.verify(accs, rho))
-            ms_job = (time.perf_counter() - t0) / 5 * 1e3
-            out["aggregate_256_then_decide"] = {"ms": ms_job, "jobs_per_s": 1e3 / ms_job,
-                                                "what": "KzgAs::verify over 256 accumulators + decide, one job at a time (single-job latency; "
-                                                        "independent jobs go to different GPUs: replicas only)"}
-        except Exception as e:
-            out["aggregate_256_then_decide"] = {"error": repr(e)}
-        # rows f3 / a13 of SURVEY.md §8: the per-proof scalar evaluation and the limb decoding that sit either side of the path
-        try:
+            reps = 5
+            allp = pts_all[: n4 * 64].cpu().numpy()
+            accs = [sv.KzgAccumulator(allp[64 * i:64 * i + 64].tobytes(), allp[64 * i:64 * i + 64].tobytes()) for i in range(n4)]
+            ms = self.timed_wall(lambda: kz.decide(kz.verify(accs, rho)), reps)
+            return ms, True, {"what": "BASELINE config 4: KzgAs::verify over 256 accumulators + decide per job; replicas only (one independent job stream per "
+                                      "rank); ms = single-job latency, jobs_per_s = sum over ranks"}, world, "jobs_per_s"
+        self.leg("aggregate_256_then_decide", aggregate_256)
+
+        def plonk_scalar_eval():
             from snark_verifier_b200 import plonk_eval as pe
             proto = pe.standard_plonk_like_protocol(12, num_instance=1)
             prog = pe.compile_quotient_evaluation(proto)
             tot = proto.input_layout()["total"]
+            mp = len(my_proofs)
             with torch.cuda.stream(stream):
-                d_in = torch.empty(m_proofs * tot * 32, dtype=torch.uint8, device=dev)
-                d_out = torch.zeros(m_proofs * len(prog.outputs) * 32, dtype=torch.uint8, device=dev)
-                L.synth_scalars_device(SEED + 3, 0, m_proofs * tot, d_in.data_ptr())
-                ms_pe = timed(lambda: L.fr_program_eval(prog, None, m_proofs, d_inputs=d_in.data_ptr(), d_outputs=d_out.data_ptr()), 3)
-            out["plonk_scalar_eval"] = {"proofs_per_s": m_proofs / ms_pe * 1e3, "ms": ms_pe, "proofs": m_proofs, "instructions": len(prog.instrs),
-                                        "what": "StandardPlonk-shaped quotient evaluation (protocol.rs:211-283, 336-392; proof.rs:298-349) as one "
-                                                "straight-line Fr program, one thread per proof, operands resident in HBM"}
-        except Exception as e:
-            out["plonk_scalar_eval"] = {"error": repr(e)}
-    except Exception as e:  # the headline metric must still print
-        out = {"error": repr(e)}
-    return out
+                d_in = torch.empty(mp * tot * 32, dtype=torch.uint8, device=dev)
+                d_out = torch.zeros(mp * len(prog.outputs) * 32, dtype=torch.uint8, device=dev)
+                L.synth_scalars_device(SEED + 3, rank * mp * tot, mp * tot, d_in.data_ptr())
+            ms = self.timed_events(lambda: L.fr_program_eval(prog, None, mp, d_inputs=d_in.data_ptr(), d_outputs=d_out.data_ptr()), 3)
+            return ms, True, {"proofs": m_proofs, "instructions": len(prog.instrs),
+                              "what": "StandardPlonk-shaped quotient evaluation (protocol.rs:211-283, 336-392; proof.rs:298-349) as one straight-line Fr "
+                                      "program, one thread per proof, sharded by proof, operands resident in HBM"}, m_proofs, "proofs_per_s"
+        self.leg("plonk_scalar_eval", plonk_scalar_eval)
+        return self.out
+
+
+def size_sweep(sv, torch, dist, Lm, stream, dev, rank, world, lo, hi):
+    """BASELINE config 5: MSM size sweep 2^lo .. 2^hi at this N with the library's own plan; chunk partition + NCCL all-gather of the
+    96-byte partials + fold, operands resident, best of 3 after 2 warm-ups (CUDA events, max over ranks)."""
+    from snark_verifier_b200.sharding import chunk_bounds
+    rows = []
+    nmax = 1 << hi
+    lo_max, cnt_max = chunk_bounds(nmax, world, rank)
+    with torch.cuda.stream(stream):
+        ds = torch.empty(max(cnt_max, 1) * 32, dtype=torch.uint8, device=dev)
+        dp = torch.empty(max(cnt_max, 1) * 64, dtype=torch.uint8, device=dev)
+        part = torch.zeros(96, dtype=torch.uint8, device=dev)
+        parts = torch.zeros(96 * world, dtype=torch.uint8, device=dev)
+        out = torch.zeros(64, dtype=torch.uint8, device=dev)
+        ident = torch.zeros(96, dtype=torch.uint8, device=dev); ident[32] = 1
+        if cnt_max:   # generated once: rank r's chunk of an n-term input is the first ceil(n / N) terms of its slice of the largest one
+            Lm.synth_scalars_device(SEED + 7, lo_max, cnt_max, ds.data_ptr())
+            Lm.synth_points_device(SEED + 7, lo_max, cnt_max, dp.data_ptr())
+    for lg in range(lo, hi + 1):
+        n = 1 << lg
+        _, cnt = chunk_bounds(n, world, rank)
+        ts = []
+        for rep in range(5):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                e0.record(stream)
+                if cnt:
+                    Lm.msm_device(ds.data_ptr(), dp.data_ptr(), cnt, d_out_jacobian=part.data_ptr())
+                else:
+                    part.copy_(ident)
+                if world > 1:
+                    dist.all_gather_into_tensor(parts, part)
+                    Lm.fold_partials_device(parts.data_ptr(), world, out.data_ptr())
+                else:
+                    Lm.fold_partials_device(part.data_ptr(), 1, out.data_ptr())
+                e1.record(stream)
+            stream.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            if rep >= 2:
+                ts.append(float(t.item()))
+        pl = Lm.msm_plan(max(cnt, 1))
+        rows.append({"log_n": lg, "ms": min(ts), "mterms_per_s": n / min(ts) / 1e3, "window_bits_per_rank": pl["window_bits"]})
+    return rows
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm for the path, all host threads, bounded sample per step."""
+    """--impl reference: the reference's CPU algorithm for the path (util/msm.rs:308-343 with the `parallel` feature, restated in
+    oracle/oracle.cpp) on all host threads, on the SAME workload as the CUDA arm: every step is one full 2^log_n-term MSM."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import oracle
     threads = os.cpu_count() or 1
-    log_n = args.ref_log_n
+    log_n = args.ref_log_n if args.ref_log_n else args.log_n
     n = 1 << log_n
+    t0 = time.perf_counter()
     s = oracle.to_mont_batch(1, oracle.synth_scalars(SEED, 0, n), n, threads)              # halo2curves in-memory layout,
     p = oracle.to_mont_batch(0, oracle.synth_points(SEED, 0, n, threads), 2 * n, threads)  # prepared outside the timed region
-    for _ in range(args.warmup):
+    gen_s = time.perf_counter() - t0
+    # one full-size step costs ~10 s of all cores: the warm-up is capped at one step so that the run stays within minutes
+    warm_run = min(args.warmup, 1)
+    for _ in range(warm_run):
         oracle.msm_pippenger_raw(s, p, n, threads)
     t0 = time.perf_counter()
+    res = None
     for _ in range(args.steps):
-        oracle.msm_pippenger_raw(s, p, n, threads)
+        res = oracle.msm_pippenger_raw(s, p, n, threads)
     dt = time.perf_counter() - t0
     val = n * args.steps / dt / 1e6
-    sample = "2^%d-term slice of the synthetic 2^%d workload per step" % (log_n, args.log_n)
+    same = log_n == args.log_n
+    sample = ("one full 2^%d-term MSM per step (the whole workload)" % log_n) if same else \
+             ("2^%d-term slice of the synthetic 2^%d workload per step" % (log_n, args.log_n))
     line = {
         "impl": "reference", "metric": "BN254 G1 MSM throughput", "value": val, "unit": "Mscalar-mults/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "u256 (4x64-bit Montgomery limbs)", "data": "synthetic",
-        "config": {"workload": "BN254 G1 MSM 2^%d terms (config: metric's headline size)" % args.log_n, "sample": sample},
+        "config": {"workload": workload_name(args.log_n), "terms": 1 << args.log_n, "terms_per_step": n, "same_config_as_cuda_arm": same,
+                   "byte_format": "montgomery (halo2curves in-memory layout)", "result_affine_le_hex": res.hex() if res else None,
+                   "warmup_steps_run": warm_run, "input_generation_s": gen_s},
         "cpu_baseline": {"value": val, "unit": "Mscalar-mults/s", "cores": threads, "kind": "port", "sample": sample,
                          "what": "oracle restatement of util::msm::multi_scalar_multiplication with the `parallel` feature "
                                  "(util/msm.rs:308-343); the Rust reference itself cannot be built here (no cargo, halo2curves not vendored)"},
@@ -369,13 +488,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--log-n", type=int, default=LOG_N_DEFAULT, help="log2 of the MSM size (metric is quoted at 24)")
-    ap.add_argument("--ref-log-n", type=int, default=20, help="log2 of the per-step CPU sample for --impl reference / cpu_baseline")
+    ap.add_argument("--ref-log-n", type=int, default=0, help="log2 of the per-step CPU MSM for --impl reference / cpu_baseline (0 = the full workload)")
     ap.add_argument("--window-bits", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--format", default="montgomery", choices=["montgomery", "canonical"],
                     help="byte layout of scalars / points at the C ABI: halo2curves' in-memory Montgomery limbs (what the Rust glue passes, "
                          "zero-copy from &[Fr] / &[G1Affine]; default) or canonical little-endian `to_repr` bytes")
     ap.add_argument("--no-aux", action="store_true", help="skip the secondary KZG / scalar-evaluation measurements (profiling runs)")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the 2^10..2^26 MSM size sweep of the aux block")
+    ap.add_argument("--sweep", default="10,26", help="lo,hi (log2) of the size sweep")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
     if args.impl == "reference":
@@ -510,13 +631,26 @@ def main():
     e2e_value = n_total * args.steps / float(e2e_s.item()) / 1e6
     res_e2e = bytes(h_out.numpy())
 
-    # ---- secondary metric of BASELINE.json: "proofs verified/s" (KZG accumulator decisions), rank 0, N = 1 only -------------
+    # ---- the metric's second half ("proofs verified/s", configs 3-5) at THIS N, sharded over the ranks ------------------------
     aux = None
-    if rank == 0 and world == 1 and not args.no_aux:
-        La = sv.CudaLoader(local_rank)            # the secondary measurements feed canonical constants: their own canonical context
-        La.set_stream(stream.cuda_stream)
-        aux = kzg_aux(La, sv, torch, stream, dev)
-        La.close()
+    if not args.no_aux:
+        try:
+            La = sv.CudaLoader(local_rank)            # the secondary measurements feed canonical constants: their own canonical context
+            La.set_stream(stream.cuda_stream)
+            aux = Aux(sv, torch, dist, La, stream, dev, rank, world).run()
+            La.close()
+        except Exception as e:
+            aux = {"error": repr(e)}
+        if not args.no_sweep:
+            try:
+                s_lo, s_hi = (int(x) for x in args.sweep.split(","))
+                del d_s, d_p
+                torch.cuda.empty_cache()
+                aux["msm_size_sweep"] = {"what": "BASELINE config 5: MSM sizes 2^%d..2^%d at this N, chunk partition + NCCL all-gather of 96-byte partials + fold, "
+                                                 "operands resident, best of 3 (CUDA events, max over ranks)" % (s_lo, s_hi),
+                                         "rows": size_sweep(sv, torch, dist, L, stream, dev, rank, world, s_lo, s_hi)}
+            except Exception as e:
+                aux["msm_size_sweep"] = {"error": repr(e)}
 
     if rank == 0:
         hbm_peak, peak_src = peaks()
@@ -524,15 +658,15 @@ def main():
         achieved = alg_bytes / (acc_ms / 1e3) / 1e9
         plan = L.msm_plan(n_local)
         c_bits, windows = plan["window_bits"], plan["windows"]
-        cap = ncu_capture(acc_kernel, args.log_n if world == 1 else -1, c_bits)
+        cap, cap_note = ncu_capture(acc_kernel, args.log_n if world == 1 else -1, c_bits)
         mulmods_per_s = n_local * windows * acc_mulmods / (acc_ms / 1e3)
         line = {
             "metric": "BN254 G1 MSM throughput", "value": value, "unit": "Mscalar-mults/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u256 (8x32-bit Montgomery limbs, integer only)", "data": "synthetic",
-            "config": {"workload": "BN254 G1 MSM, 2^%d uniformly random scalars x points [t_i]G (seed %d), chunk-partitioned over %d GPU(s), "
-                                   "one NCCL all-gather of 96-byte Jacobian partials + fold" % (args.log_n, SEED, world),
-                       "terms": n_total, "terms_per_gpu": n_local, "window_bits": c_bits, "parallelism": "chunk%d" % world,
+            "config": {"workload": workload_name(args.log_n), "terms": n_total,
+                       "partition": "chunk-partitioned over %d GPU(s), one NCCL all-gather of 96-byte Jacobian partials + fold" % world,
+                       "terms_per_gpu": n_local, "window_bits": c_bits, "parallelism": "chunk%d" % world,
                        "l2_policy": "inputs (%.2f GB/GPU) exceed the 126 MB L2; no flush needed" % (n_local * 96 / 1e9),
                        "byte_format": args.format + (" (halo2curves in-memory layout, as the reference's CPU arm is fed)" if args.format == "montgomery" else ""),
                        "result_affine_le_hex": canonical_affine(res_dev, args.format).hex()},
@@ -542,28 +676,41 @@ def main():
                     "result_matches_device_path": res_e2e == res_dev},
             "gpu_launches": int(launches),
             "roofline": {"kernel": acc_kernel, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": cap["dram_bytes_per_launch"] if cap else None,
+                         "frac": achieved / hbm_peak, "traffic": cap["dram_bytes_per_launch"] if cap else None, "traffic_source": cap_note,
                          "peak_source": peak_src, "kernel_ms": acc_ms, "algorithmic_bytes_per_launch": alg_bytes,
                          "note": "this kernel is bound by the integer multiplier (FMA-heavy pipe), not by HBM: %d point additions x %d "
-                                 "Montgomery multiplications x ~%d IMAD per term; 'traffic' is each 64-byte point gathered once per window "
-                                 "(plus, for the batched-affine kernel, the intermediate tree levels and the inversion prefixes)"
+                                 "Montgomery multiplications x ~%d FMA-pipe instructions per term; 'traffic' is each 64-byte point gathered once "
+                                 "per window (plus, for the batched-affine kernel, the intermediate tree levels and the inversion prefixes)"
                                  % (windows, acc_mulmods, IMAD_PER_MULMOD),
                          "per_kernel_hbm": per_kernel_hbm(stages, n_local, windows, hbm_peak, cap, acc_ms),
                          "alu": {"mulmods_per_s": mulmods_per_s,
                                  "fmaheavy_pipe_pct_of_peak_ncu": cap["fmaheavy_pct"] if cap else None,
-                                 "source": cap["source"] if cap else "no ncu capture for this configuration"}},
+                                 "source": cap_note}},
             "stages_ms": stages,
             "aux": aux,
         }
         if not args.no_cpu_baseline and world == 1:
+            # the SAME workload on the host cores: the pinned e2e buffers hold exactly the bytes the GPU arm consumed (Montgomery =
+            # halo2curves' in-memory layout, which is what the Rust reference holds; canonical bytes are converted outside the timing)
+            import oracle
             threads = os.cpu_count() or 1
-            rate, n_s, secs = cpu_pippenger_sample(args.ref_log_n, threads)
-            line["cpu_baseline"] = {"value": rate / 1e6, "unit": "Mscalar-mults/s", "cores": threads, "kind": "port",
-                                    "sample": "one 2^%d-term chunk-parallel Pippenger (util/msm.rs:308-343 restated) in %.2f s" % (args.ref_log_n, secs)}
             try:
+                log_c = args.ref_log_n if args.ref_log_n else args.log_n
+                n_c = 1 << log_c
+                hs, hp = h_s.numpy()[: n_c * 32], h_p.numpy()[: n_c * 64]
+                if args.format != "montgomery":
+                    hs = np.frombuffer(oracle.to_mont_batch(1, hs, n_c, threads), dtype=np.uint8)
+                    hp = np.frombuffer(oracle.to_mont_batch(0, hp, 2 * n_c, threads), dtype=np.uint8)
+                t0 = time.perf_counter()
+                res_cpu = oracle.msm_pippenger_raw(hs, hp, n_c, threads)
+                secs = time.perf_counter() - t0
+                line["cpu_baseline"] = {"value": n_c / secs / 1e6, "unit": "Mscalar-mults/s", "cores": threads, "kind": "port",
+                                        "sample": "one %s chunk-parallel Pippenger (util/msm.rs:308-343 restated) over 2^%d terms in %.2f s"
+                                                  % ("FULL-SIZE" if log_c == args.log_n else "reduced", log_c, secs),
+                                        "result_matches_gpu": (res_cpu == canonical_affine(res_dev, args.format)) if log_c == args.log_n else None}
                 line["cpu_baseline"]["also"] = cpu_native_extras(threads)
             except Exception as e:
-                line["cpu_baseline"]["also"] = {"error": repr(e)}
+                line["cpu_baseline"] = {"error": repr(e)}
         elif world > 1:
             line["cpu_baseline"] = None
         print(json.dumps(line), flush=True)

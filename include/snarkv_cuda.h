@@ -91,6 +91,17 @@ int snarkv_set_pairing_mode(snarkv_ctx* ctx, int mode);
 int snarkv_g1_msm(snarkv_ctx* ctx, const uint8_t* scalars, const uint8_t* points, size_t n, int format, int flags,
                   uint8_t out_affine[64]);
 
+/* The same MSM against a RESIDENT base set.  A verifier's fixed bases (the preprocessed / vk commitments of a `PlonkProtocol`,
+ * verifier/plonk/protocol.rs:30-34, the SRS generator of `KzgSuccinctVerifyingKey`, pcs/kzg.rs:19-35) do not change between calls:
+ * upload them once — validated (SNARKV_CHECK_INPUTS), converted and, for the GLV plans, extended by their endomorphism images on the
+ * device — and pass only the n x 32 B scalars per call (one scalar per base, in the order of the upload).  Results are identical to
+ * snarkv_g1_msm on the same pairs.  The handle belongs to the context's device and must be freed before the context. */
+typedef struct snarkv_bases snarkv_bases;
+int snarkv_g1_bases_upload(snarkv_ctx* ctx, const uint8_t* points, size_t n, int format, int flags, snarkv_bases** out);
+void snarkv_g1_bases_free(snarkv_ctx* ctx, snarkv_bases* bases);
+int snarkv_g1_msm_bases_resident(snarkv_ctx* ctx, const snarkv_bases* bases, const uint8_t* scalars, size_t n, int format, int flags,
+                                 uint8_t out_affine[64]);
+
 /* One rank's share of a chunk-partitioned MSM (util/msm.rs:322-332: `scalars.chunks(chunk_size).zip(bases.chunks(..))`, one
  * serial MSM per chunk): host slices in, the chunk's Jacobian partial (96 B) left in DEVICE memory, ready for the
  * all-gather + snarkv_g1_fold_partials_device that replaces the fold at util/msm.rs:333-335.  Synchronises the stream. */
@@ -206,6 +217,32 @@ int snarkv_fr_program_eval_batch(snarkv_ctx* ctx, const snarkv_fr_instr* program
 int snarkv_fr_program_eval_batch_device(snarkv_ctx* ctx, const snarkv_fr_instr* program, size_t n_instr, uint32_t n_regs,
                                         const uint8_t* consts, size_t n_consts, const void* d_inputs, size_t n_inputs, size_t m,
                                         const uint32_t* out_regs, size_t n_out, int format, void* d_outputs);
+
+/* ---- multi-GPU: one host call, all the GPUs of the box -----------------------------------------------------------------------
+ * What the rayon `parallel` feature is to the reference's large MSM (util/msm.rs:311-336: one contiguous chunk of the term slice
+ * per thread, partial results folded), a multi-device context is here: device g gets terms [g ceil(n/G), (g+1) ceil(n/G)), runs the
+ * single-device pipeline on them from its own host thread and leaves a 96-byte Jacobian partial in its HBM; the single exchange
+ * step (the fold of util/msm.rs:333-335) is ONE kernel on device 0 that reads every partial out of its producer's memory over
+ * NVLink peer access.  This is the entry a `CudaLoader::multi_scalar_multiplication` (loader.rs:108-113) binds to use the whole
+ * box.  Units that are independent shard with no exchange: pairing checks (decider.rs:84-93) in contiguous blocks, RLC-fused
+ * batches by MSM segment (device g starts its powers of rho at rho^(first segment of g)).  Results are bit-identical to the
+ * single-device entry points for every device count.
+ * `devices` = CUDA ordinals (NULL: 0 .. n_devices - 1; n_devices <= 0: every visible device).  Peer access from devices[0] to
+ * the others is required (SNARKV_ERR_CUDA otherwise).  Thread-compatible like snarkv_ctx; snarkv_multi_ctx(m, i) exposes the
+ * per-device context for the tuning setters. */
+typedef struct snarkv_multi snarkv_multi;
+int snarkv_multi_init(const int* devices, int n_devices, snarkv_multi** out);
+void snarkv_multi_destroy(snarkv_multi* m);
+int snarkv_multi_device_count(const snarkv_multi* m);
+snarkv_ctx* snarkv_multi_ctx(snarkv_multi* m, int i);
+const char* snarkv_multi_last_error(const snarkv_multi* m);
+int snarkv_multi_g1_msm(snarkv_multi* m, const uint8_t* scalars, const uint8_t* points, size_t n, int format, int flags,
+                        uint8_t out_affine[64]);
+int snarkv_multi_g1_msm_batch_rlc(snarkv_multi* m, const uint8_t* scalars, const uint8_t* points, const uint64_t* offsets, size_t segs,
+                                  const uint8_t rho[32], int format, int flags, uint8_t out_affine[64]);
+int snarkv_multi_kzg_set_deciding_key(snarkv_multi* m, const uint8_t g1[64], const uint8_t g2[128], const uint8_t s_g2[128]);
+int snarkv_multi_kzg_decide_batch(snarkv_multi* m, const uint8_t* lhs, const uint8_t* rhs, size_t N, int format, uint8_t* accept,
+                                  uint8_t* gt_out);
 
 /* ---- synthetic workload (bench / tests) ----------------------------------------------------------------------------------
  * Deterministic inputs (the test suite restates the same definition independently):

@@ -46,6 +46,7 @@ def lib():
             "oracle_synth_scalars": [u64, u64, sz, vp],
             "oracle_synth_point_scalars": [u64, u64, sz, vp],
             "oracle_synth_points": [u64, u64, sz, i32, vp],
+            "oracle_synth_points_slow": [u64, u64, sz, vp],
             "oracle_msm_expected_from_dlogs": [vp, vp, sz, u8p],
         }
         for name, args in sigs.items():
@@ -119,6 +120,8 @@ def synth_point_scalars(seed, start, n):
     o = (ctypes.c_uint64 * n)(); lib().oracle_synth_point_scalars(seed, start, n, ctypes.cast(o, ctypes.c_void_p)); return o
 def synth_points(seed, start, n, threads=1):
     o = _buf(64 * n); lib().oracle_synth_points(seed, start, n, threads, ctypes.cast(o, ctypes.c_void_p)); return o.raw
+def synth_points_slow(seed, start, n):
+    o = _buf(64 * n); lib().oracle_synth_points_slow(seed, start, n, ctypes.cast(o, ctypes.c_void_p)); return o.raw
 def msm_expected_from_dlogs(scalars, t, n):
     o = _buf(64)
     _chk(lib().oracle_msm_expected_from_dlogs(_ptr(scalars), ctypes.cast(t, ctypes.c_void_p), n, o), "expected_from_dlogs"); return o.raw

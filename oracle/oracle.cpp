@@ -716,18 +716,44 @@ void oracle_synth_scalars(u64 seed, u64 start, size_t n, uint8_t* out) {
 void oracle_synth_point_scalars(u64 seed, u64 start, size_t n, u64* out) {
     for (size_t i = 0; i < n; ++i) out[i] = splitmix64(seed * 0x100000001B3ull + 0x5151515151515151ull + start + i) | 1;
 }
-// P_i = [t_i] G, affine canonical bytes
+// P_i = [t_i] G, affine canonical bytes.  Same definition as before; computed with a fixed-base comb (8 windows of 8 bits over
+// the 64-bit t_i: table[w][d] = d 2^(8w) G, 7 mixed additions per point) so that the full 2^24-term workload of the bench's
+// CPU arm is generated in seconds.  oracle_synth_points_slow keeps the literal double-and-add for the cross-check in tests/.
+static const G1Affine* synth_comb_table() {
+    static std::vector<G1Affine> table;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        std::vector<G1> jac(8 * 256);
+        G1 base = G1::from_affine(G1Affine::generator());
+        for (int w = 0; w < 8; ++w) {
+            G1 acc = G1::identity();
+            for (int d = 0; d < 256; ++d) {
+                jac[w * 256 + d] = acc;
+                acc = acc.add(base);
+            }
+            base = acc;   // 256 * previous base
+        }
+        table.resize(8 * 256);
+        g1_batch_to_affine(jac.data(), table.data(), jac.size());
+    });
+    return table.data();
+}
 void oracle_synth_points(u64 seed, u64 start, size_t n, int threads, uint8_t* out) {
     if (threads < 1) threads = 1;
-    const G1Affine g = G1Affine::generator();
+    const G1Affine* table = synth_comb_table();
     auto work = [&](size_t lo, size_t hi) {
-        const size_t B = 256;
+        const size_t B = 1024;
         std::vector<G1> jac(B); std::vector<G1Affine> aff(B);
         for (size_t base = lo; base < hi; base += B) {
             size_t m = hi - base < B ? hi - base : B;
             for (size_t j = 0; j < m; ++j) {
-                u64 t[4] = {splitmix64(seed * 0x100000001B3ull + 0x5151515151515151ull + start + base + j) | 1, 0, 0, 0};
-                jac[j] = g1_mul_vartime(g, t);
+                const u64 t = splitmix64(seed * 0x100000001B3ull + 0x5151515151515151ull + start + base + j) | 1;
+                G1 acc = G1::from_affine(table[t & 0xff]);      // t is odd: the low digit is never 0
+                for (int w = 1; w < 8; ++w) {
+                    const unsigned d = (unsigned)(t >> (8 * w)) & 0xffu;
+                    if (d) acc = acc.add_mixed(table[w * 256 + d]);
+                }
+                jac[j] = acc;
             }
             g1_batch_to_affine(jac.data(), aff.data(), m);
             for (size_t j = 0; j < m; ++j) store_g1(aff[j], out + 64 * (base + j));
@@ -741,6 +767,13 @@ void oracle_synth_points(u64 seed, u64 start, size_t n, int threads, uint8_t* ou
         pool.emplace_back(work, lo, hi);
     }
     for (auto& th : pool) th.join();
+}
+void oracle_synth_points_slow(u64 seed, u64 start, size_t n, uint8_t* out) {
+    const G1Affine g = G1Affine::generator();
+    for (size_t j = 0; j < n; ++j) {
+        u64 t[4] = {splitmix64(seed * 0x100000001B3ull + 0x5151515151515151ull + start + j) | 1, 0, 0, 0};
+        store_g1(g1_mul_vartime(g, t).to_affine(), out + 64 * j);
+    }
 }
 // checksum for full-size runs: (sum_i s_i * t_i mod r) * G, where P_i = [t_i] G
 int oracle_msm_expected_from_dlogs(const uint8_t* scalars, const u64* t, size_t n, uint8_t* out) {

@@ -61,6 +61,18 @@ C_ABI = {
     "snarkv_set_accumulate_mode": (_i, [_vp, _i]),
     "snarkv_g1_msm": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp]),
     "snarkv_g1_msm_partial": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp]),
+    "snarkv_g1_bases_upload": (_i, [_vp, _vp, _sz, _i, _i, ctypes.POINTER(_vp)]),
+    "snarkv_g1_bases_free": (None, [_vp, _vp]),
+    "snarkv_g1_msm_bases_resident": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp]),
+    "snarkv_multi_init": (_i, [ctypes.POINTER(ctypes.c_int), _i, ctypes.POINTER(_vp)]),
+    "snarkv_multi_destroy": (None, [_vp]),
+    "snarkv_multi_device_count": (_i, [_vp]),
+    "snarkv_multi_ctx": (_vp, [_vp, _i]),
+    "snarkv_multi_last_error": (ctypes.c_char_p, [_vp]),
+    "snarkv_multi_g1_msm": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp]),
+    "snarkv_multi_g1_msm_batch_rlc": (_i, [_vp, _vp, _vp, _vp, _sz, _vp, _i, _i, _vp]),
+    "snarkv_multi_kzg_set_deciding_key": (_i, [_vp, _vp, _vp, _vp]),
+    "snarkv_multi_kzg_decide_batch": (_i, [_vp, _vp, _vp, _sz, _i, _vp, _vp]),
     "snarkv_g1_msm_device": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp, _vp, _vp]),
     "snarkv_g1_fold_partials_device": (_i, [_vp, _vp, _sz, _i, _vp]),
     "snarkv_g1_msm_batch": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _vp]),
@@ -216,6 +228,21 @@ class CudaLoader:
         self._check(self.lib.snarkv_g1_msm(self.h, _addr(scalars), _addr(points), n, self.fmt, flags, out), "multi_scalar_multiplication")
         return out.raw
 
+    def bases_upload(self, points, n, flags=CHECK_INPUTS):
+        """Upload a fixed base set once (validated by default); returns an opaque handle for msm_bases_resident / bases_free."""
+        h = ctypes.c_void_p()
+        self._check(self.lib.snarkv_g1_bases_upload(self.h, _addr(points), n, self.fmt, flags, ctypes.byref(h)), "bases_upload")
+        return h
+
+    def bases_free(self, handle):
+        self.lib.snarkv_g1_bases_free(self.h, handle)
+
+    def msm_bases_resident(self, handle, scalars, n, flags=0):
+        """MSM against a resident base set: only the n x 32 B scalars cross PCIe."""
+        out = ctypes.create_string_buffer(64)
+        self._check(self.lib.snarkv_g1_msm_bases_resident(self.h, handle, _addr(scalars), n, self.fmt, flags, out), "msm_bases_resident")
+        return out.raw
+
     def msm_partial(self, scalars, points, n, d_out_jacobian, flags=0):
         """Host slices in, 96-byte Jacobian partial left on the device (one rank's chunk of util/msm.rs:322-336)."""
         self._check(self.lib.snarkv_g1_msm_partial(self.h, _addr(scalars), _addr(points), n, self.fmt, flags, _addr(d_out_jacobian)),
@@ -310,6 +337,77 @@ class CudaLoader:
 
     def synth_points_device(self, seed, start, n, d_out):
         self._check(self.lib.snarkv_synth_points_device(self.h, seed, start, n, self.fmt, _addr(d_out)), "synth_points")
+
+
+class MultiCudaLoader:
+    """One host call, all the GPUs of the box (snarkv_multi_*): the chunk partition of util/msm.rs:322-336 with devices for rayon
+    threads, folded on device 0 over NVLink peer memory; pairing checks and RLC batches shard as independent units."""
+
+    def __init__(self, devices=None, fmt=CANONICAL):
+        self.lib = load_library()
+        h = ctypes.c_void_p()
+        if devices is None:
+            rc = self.lib.snarkv_multi_init(None, 0, ctypes.byref(h))
+        else:
+            arr = (ctypes.c_int * len(devices))(*devices)
+            rc = self.lib.snarkv_multi_init(arr, len(devices), ctypes.byref(h))
+        if rc != 0 or not h:
+            raise CudaError(f"snarkv_multi_init failed (rc={rc}): needs sm_100 GPUs with peer access; there is no CPU fallback")
+        self.h, self.fmt = h, fmt
+        self.n_devices = int(self.lib.snarkv_multi_device_count(h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.snarkv_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc == 0:
+            return
+        msg = self.lib.snarkv_multi_last_error(self.h).decode()
+        if rc == ERR_CUDA:
+            raise CudaError(f"{what}: {msg}")
+        raise Error(f"{what}: rc={rc} {msg}")
+
+    def device_ctx(self, i):
+        """Per-device context handle (for the tuning setters of the C ABI)."""
+        return ctypes.c_void_p(self.lib.snarkv_multi_ctx(self.h, i))
+
+    def set_accumulate_mode(self, mode):
+        for i in range(self.n_devices):
+            self.lib.snarkv_set_accumulate_mode(self.device_ctx(i), mode)
+
+    def multi_scalar_multiplication(self, pairs):
+        pairs = list(pairs)
+        return self.msm(b"".join(bytes(s) for s, _ in pairs), b"".join(bytes(p) for _, p in pairs), len(pairs))
+
+    def msm(self, scalars, points, n, flags=0):
+        out = ctypes.create_string_buffer(64)
+        self._check(self.lib.snarkv_multi_g1_msm(self.h, _addr(scalars), _addr(points), n, self.fmt, flags, out), "multi msm")
+        return out.raw
+
+    def msm_batch_rlc(self, scalars, points, offsets, rho, flags=0):
+        m = len(offsets) - 1
+        off = offsets if hasattr(offsets, "ctypes") else (ctypes.c_uint64 * (m + 1))(*offsets)
+        out = ctypes.create_string_buffer(64)
+        self._check(self.lib.snarkv_multi_g1_msm_batch_rlc(self.h, _addr(scalars), _addr(points), _addr(off), m, bytes(rho), self.fmt, flags, out),
+                    "multi msm_batch_rlc")
+        return out.raw
+
+    def set_deciding_key(self, dk):
+        self._check(self.lib.snarkv_multi_kzg_set_deciding_key(self.h, dk.g1, dk.g2, dk.s_g2), "multi KzgDecidingKey")
+
+    def decide_batch(self, lhs, rhs, n, want_gt=False):
+        acc = ctypes.create_string_buffer(max(n, 1))
+        gt = ctypes.create_string_buffer(384 * n) if want_gt else None
+        self._check(self.lib.snarkv_multi_kzg_decide_batch(self.h, _addr(lhs), _addr(rhs), n, self.fmt, acc, gt), "multi decide")
+        return acc.raw[:n], (gt.raw if want_gt else None)
 
 
 class Msm:

@@ -8,6 +8,7 @@
 
 #include <cstdlib>
 
+#include <cstring>
 #include <vector>
 #include "ctx.hpp"
 
@@ -22,6 +23,53 @@ using namespace snarkv;
     } while (0)
 
 static int bad_format(int f) { return f != SNARKV_CANONICAL && f != SNARKV_MONTGOMERY; }
+
+// Host-buffer body of snarkv_g1_msm_batch_rlc, shared with the multi-device entry (multi.cu): segments j = 0..m-1 are scaled by
+// rho^(first_power + j); the result is returned as affine bytes (out_affine) and/or left as a Jacobian partial on the device.
+namespace snarkv {
+int msm_batch_rlc_host(snarkv_ctx* ctx, const uint8_t* scalars, const uint8_t* points, const uint64_t* offsets, size_t m, const uint8_t rho[32],
+                       int format, int flags, uint64_t first_power, uint8_t* out_affine, void* d_out_jacobian) {
+    if (!scalars || !points || !offsets || !rho || bad_format(format) || m == 0)
+        return ctx->fail(SNARKV_ERR_USAGE, "snarkv_g1_msm_batch_rlc: bad argument");
+    const uint64_t base = offsets[0];
+    for (size_t j = 0; j < m; ++j)
+        if (offsets[j + 1] <= offsets[j]) return ctx->fail(SNARKV_ERR_EMPTY, "empty or decreasing MSM segment");
+    const size_t total = offsets[m] - base;
+    ctx->profile_begin_call();
+    uint8_t* d_s = (uint8_t*)ctx->wsget(WS_IO_A, total * 32);
+    uint8_t* d_p = (uint8_t*)ctx->wsget(WS_IO_B, total * 64);
+    uint64_t* d_off = (uint64_t*)ctx->wsget(WS_IO_C, (m + 1) * 8);
+    uint8_t* d_scaled = (uint8_t*)ctx->wsget(WS_IO_D, total * 32);
+    uint8_t* d_pw = (uint8_t*)ctx->wsget(WS_IO_E, m * 32 + 32);   // [rho | powers]
+    uint8_t* d_o = (uint8_t*)ctx->wsget(WS_OUT, 1024);            // [affine 64 | status 2 x 4 @64]
+    if (!d_s || !d_p || !d_off || !d_scaled || !d_pw || !d_o) return SNARKV_ERR_CUDA;
+    cudaStream_t st = ctx->stream;
+    std::vector<uint64_t> rebased;
+    const uint64_t* off = offsets;
+    if (base != 0) {   // a shard of a longer batch: offsets relative to the shard's first term
+        rebased.resize(m + 1);
+        for (size_t j = 0; j <= m; ++j) rebased[j] = offsets[j] - base;
+        off = rebased.data();
+    }
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_pw, rho, 32, cudaMemcpyHostToDevice, st));
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_s, scalars + base * 32, total * 32, cudaMemcpyHostToDevice, st));
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_off, off, (m + 1) * 8, cudaMemcpyHostToDevice, st));
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_p, points + base * 64, total * 64, cudaMemcpyHostToDevice, st));
+    int rc = msm_batch_rlc_device(ctx, d_s, d_p, d_off, m, total, d_pw, format, flags, d_scaled, d_pw + 32, d_o, d_o + 64, first_power,
+                                  d_out_jacobian);
+    if (rc) { cudaStreamSynchronize(st); return rc; }   // `rebased` (pageable) must have left the host before it is destroyed
+    uint8_t host[72];
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(host, d_o, 72, cudaMemcpyDeviceToHost, st));
+    SNARKV_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    int st0, st1;
+    memcpy(&st0, host + 64, 4);
+    memcpy(&st1, host + 68, 4);
+    const int status = st0 ? st0 : st1;
+    if (status != 0) return ctx->fail(status, status == SNARKV_ERR_BAD_SCALAR ? "scalar is not a canonical Fr" : "point is not a valid G1Affine");
+    if (out_affine) memcpy(out_affine, host, 64);
+    return SNARKV_OK;
+}
+}  // namespace snarkv
 
 extern "C" {
 
@@ -130,6 +178,7 @@ int snarkv_profile_enable(snarkv_ctx* ctx, int on) {
 
 int snarkv_profile_read(snarkv_ctx* ctx, snarkv_stage_time* out, int cap) {
     CTX_GUARD(ctx);
+    if (!out || cap < 0) return ctx->fail(SNARKV_ERR_USAGE, "snarkv_profile_read: bad argument");
     SNARKV_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     int k = 0;
     for (const StageRecord& r : ctx->stages) {
@@ -156,6 +205,65 @@ int snarkv_g1_msm(snarkv_ctx* ctx, const uint8_t* scalars, const uint8_t* points
     return msm_run_host(ctx, scalars, points, n, format, flags, out_affine, nullptr);
 }
 
+// ---- resident base set: the preprocessed / vk commitments of a protocol are fixed, only the scalars change per call ---------
+struct snarkv_bases {
+    int device;
+    size_t n;
+    void* d_points;   // 2 n x 64 B: Montgomery P_i, then phi(P_i) for the GLV plans
+};
+
+int snarkv_g1_bases_upload(snarkv_ctx* ctx, const uint8_t* points, size_t n, int format, int flags, snarkv_bases** out) {
+    CTX_GUARD(ctx);
+    if (!out) return ctx->fail(SNARKV_ERR_USAGE, "snarkv_g1_bases_upload: bad argument");
+    *out = nullptr;
+    if (n == 0) return ctx->fail(SNARKV_ERR_EMPTY, "empty base set");
+    if (!points || bad_format(format) || n >= (1ull << 30)) return ctx->fail(SNARKV_ERR_USAGE, "snarkv_g1_bases_upload: bad argument");
+    snarkv_bases* b = new (std::nothrow) snarkv_bases();
+    if (!b) return ctx->fail(SNARKV_ERR_USAGE, "out of host memory");
+    b->device = ctx->device;
+    b->n = n;
+    cudaError_t ce = cudaMalloc(&b->d_points, 2 * n * 64);
+    if (ce != cudaSuccess) { delete b; return ctx->fail(SNARKV_ERR_CUDA, "cudaMalloc(resident bases)", ce); }
+    uint8_t* d_in = (uint8_t*)ctx->wsget(WS_IO_B, n * 64);
+    int* d_status = (int*)ctx->wsget(WS_STATUS, 4);
+    int rc = (!d_in || !d_status) ? SNARKV_ERR_CUDA : SNARKV_OK;
+    int status = 0;
+    cudaStream_t st = ctx->stream;
+    if (!rc && (ce = cudaMemcpyAsync(d_in, points, n * 64, cudaMemcpyHostToDevice, st)) != cudaSuccess) rc = ctx->fail(SNARKV_ERR_CUDA, "H2D", ce);
+    if (!rc) rc = msm_bases_prepare(ctx, d_in, n, format, (flags & SNARKV_CHECK_INPUTS) ? 1 : 0, b->d_points, d_status);
+    if (!rc && (ce = cudaMemcpyAsync(&status, d_status, 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) rc = ctx->fail(SNARKV_ERR_CUDA, "D2H", ce);
+    if ((ce = cudaStreamSynchronize(st)) != cudaSuccess && !rc) rc = ctx->fail(SNARKV_ERR_CUDA, "cudaStreamSynchronize", ce);
+    if (!rc && status != 0) rc = ctx->fail(status, "point is not a valid G1Affine");
+    if (rc) {
+        cudaFree(b->d_points);
+        delete b;
+        return rc;
+    }
+    *out = b;
+    return SNARKV_OK;
+}
+
+void snarkv_g1_bases_free(snarkv_ctx* ctx, snarkv_bases* bases) {
+    if (!bases) return;
+    if (ctx) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+    }
+    cudaFree(bases->d_points);
+    delete bases;
+}
+
+int snarkv_g1_msm_bases_resident(snarkv_ctx* ctx, const snarkv_bases* bases, const uint8_t* scalars, size_t n, int format, int flags,
+                                 uint8_t out_affine[64]) {
+    CTX_GUARD(ctx);
+    if (n == 0) return ctx->fail(SNARKV_ERR_EMPTY, "multi_scalar_multiplication on an empty slice");
+    if (!bases || !scalars || !out_affine || bad_format(format)) return ctx->fail(SNARKV_ERR_USAGE, "snarkv_g1_msm_bases_resident: bad argument");
+    if (bases->device != ctx->device) return ctx->fail(SNARKV_ERR_USAGE, "base set lives on another device");
+    if (n != bases->n) return ctx->fail(SNARKV_ERR_USAGE, "one scalar per resident base: n must equal the size of the base set");
+    ctx->profile_begin_call();
+    return msm_run_host(ctx, scalars, nullptr, n, format, flags, out_affine, nullptr, (const uint8_t*)bases->d_points);
+}
+
 int snarkv_g1_msm_partial(snarkv_ctx* ctx, const uint8_t* scalars, const uint8_t* points, size_t n, int format, int flags,
                           void* d_out_jacobian) {
     CTX_GUARD(ctx);
@@ -170,6 +278,8 @@ int snarkv_g1_msm_device(snarkv_ctx* ctx, const void* d_scalars, const void* d_p
     CTX_GUARD(ctx);
     if (n == 0) return ctx->fail(SNARKV_ERR_EMPTY, "multi_scalar_multiplication on an empty slice");
     if (!d_scalars || !d_points || bad_format(format)) return ctx->fail(SNARKV_ERR_USAGE, "snarkv_g1_msm_device: bad argument");
+    if ((flags & SNARKV_CHECK_INPUTS) && !d_status)
+        return ctx->fail(SNARKV_ERR_USAGE, "snarkv_g1_msm_device: SNARKV_CHECK_INPUTS needs a d_status word to report into");
     ctx->profile_begin_call();
     return msm_run_device(ctx, d_scalars, d_points, n, format, format, format, flags, d_out_affine, d_out_jacobian, d_status);
 }
@@ -214,37 +324,9 @@ int snarkv_g1_msm_batch(snarkv_ctx* ctx, const uint8_t* scalars, const uint8_t* 
 int snarkv_g1_msm_batch_rlc(snarkv_ctx* ctx, const uint8_t* scalars, const uint8_t* points, const uint64_t* offsets, size_t m,
                             const uint8_t rho[32], int format, int flags, uint8_t out_affine[64]) {
     CTX_GUARD(ctx);
-    if (!scalars || !points || !offsets || !rho || !out_affine || bad_format(format) || m == 0)
-        return ctx->fail(SNARKV_ERR_USAGE, "snarkv_g1_msm_batch_rlc: bad argument");
+    if (!out_affine || !offsets) return ctx->fail(SNARKV_ERR_USAGE, "snarkv_g1_msm_batch_rlc: bad argument");
     if (offsets[0] != 0) return ctx->fail(SNARKV_ERR_USAGE, "offsets[0] must be 0");
-    for (size_t j = 0; j < m; ++j)
-        if (offsets[j + 1] <= offsets[j]) return ctx->fail(SNARKV_ERR_EMPTY, "empty or decreasing MSM segment");
-    const size_t total = offsets[m];
-    ctx->profile_begin_call();
-    uint8_t* d_s = (uint8_t*)ctx->wsget(WS_IO_A, total * 32);
-    uint8_t* d_p = (uint8_t*)ctx->wsget(WS_IO_B, total * 64);
-    uint64_t* d_off = (uint64_t*)ctx->wsget(WS_IO_C, (m + 1) * 8);
-    uint8_t* d_scaled = (uint8_t*)ctx->wsget(WS_IO_D, total * 32);
-    uint8_t* d_pw = (uint8_t*)ctx->wsget(WS_IO_E, m * 32 + 32);   // [rho | powers]
-    uint8_t* d_o = (uint8_t*)ctx->wsget(WS_OUT, 1024);            // [affine 64 | status 2 x 4 @64]
-    if (!d_s || !d_p || !d_off || !d_scaled || !d_pw || !d_o) return SNARKV_ERR_CUDA;
-    cudaStream_t st = ctx->stream;
-    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_pw, rho, 32, cudaMemcpyHostToDevice, st));
-    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_s, scalars, total * 32, cudaMemcpyHostToDevice, st));
-    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_off, offsets, (m + 1) * 8, cudaMemcpyHostToDevice, st));
-    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_p, points, total * 64, cudaMemcpyHostToDevice, st));
-    int rc = msm_batch_rlc_device(ctx, d_s, d_p, d_off, m, total, d_pw, format, flags, d_scaled, d_pw + 32, d_o, d_o + 64);
-    if (rc) return rc;
-    uint8_t host[72];
-    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(host, d_o, 72, cudaMemcpyDeviceToHost, st));
-    SNARKV_CUDA_TRY(ctx, cudaStreamSynchronize(st));
-    int st0, st1;
-    memcpy(&st0, host + 64, 4);
-    memcpy(&st1, host + 68, 4);
-    const int status = st0 ? st0 : st1;
-    if (status != 0) return ctx->fail(status, status == SNARKV_ERR_BAD_SCALAR ? "scalar is not a canonical Fr" : "point is not a valid G1Affine");
-    memcpy(out_affine, host, 64);
-    return SNARKV_OK;
+    return msm_batch_rlc_host(ctx, scalars, points, offsets, m, rho, format, flags, 0, out_affine, nullptr);
 }
 
 // ---- KzgAs::verify -------------------------------------------------------------------------------------------------------
@@ -257,7 +339,7 @@ int snarkv_kzg_accumulate(snarkv_ctx* ctx, const uint8_t* lhs, const uint8_t* rh
     uint8_t* d_l = (uint8_t*)ctx->wsget(WS_IO_A, n * 64);
     uint8_t* d_r = (uint8_t*)ctx->wsget(WS_IO_B, n * 64);
     uint8_t* d_pw = (uint8_t*)ctx->wsget(WS_IO_C, n * 32 + 32);  // [r | powers]
-    uint8_t* d_o = (uint8_t*)ctx->wsget(WS_OUT, 256);
+    uint8_t* d_o = (uint8_t*)ctx->wsget(WS_OUT, 256);   // [lhs' 64 | rhs' 64 | status 4]
     if (!d_l || !d_r || !d_pw || !d_o) return SNARKV_ERR_CUDA;
     cudaStream_t st = ctx->stream;
     SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_pw, r, 32, cudaMemcpyHostToDevice, st));
@@ -265,11 +347,16 @@ int snarkv_kzg_accumulate(snarkv_ctx* ctx, const uint8_t* lhs, const uint8_t* rh
     SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_r, rhs, n * 64, cudaMemcpyHostToDevice, st));
     int rc = fr_powers_device(ctx, d_pw, format, n, d_pw + 32);
     if (rc) return rc;
-    rc = msm_run_device_pair(ctx, d_pw + 32, d_l, d_r, n, SNARKV_MONTGOMERY, format, format, 0, d_o, nullptr);
+    // accumulators come out of proofs: every point is validated like `read_ec_point` / `from_xy` does before the reference ever
+    // adds it (canonical coordinates, on the curve) — the a = 0 addition formulas would accept an off-curve point silently
+    rc = msm_run_device_pair(ctx, d_pw + 32, d_l, d_r, n, SNARKV_MONTGOMERY, format, format, SNARKV_CHECK_INPUTS, d_o, d_o + 128);
     if (rc) return rc;
-    uint8_t host[128];
-    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(host, d_o, 128, cudaMemcpyDeviceToHost, st));
+    uint8_t host[132];
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(host, d_o, 132, cudaMemcpyDeviceToHost, st));
     SNARKV_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    int status;
+    memcpy(&status, host + 128, 4);
+    if (status != 0) return ctx->fail(status, "accumulator point is not a valid G1Affine");
     memcpy(out_lhs, host, 64);
     memcpy(out_rhs, host + 64, 64);
     return SNARKV_OK;
@@ -334,19 +421,17 @@ int snarkv_kzg_decide_all_fused(snarkv_ctx* ctx, const uint8_t* lhs, const uint8
     SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_r, rhs, N * 64, cudaMemcpyHostToDevice, st));
     int rc = fr_powers_device(ctx, d_pw, format, N, d_pw + 32);
     if (rc) return rc;
-    // layout of d_o: [lhs' 64 | rhs' 64 | accept 1 .. pad to 132 | status 4 | unused 4]
-    SNARKV_CUDA_TRY(ctx, cudaMemsetAsync(d_o + 136, 0, 4, st));
+    // layout of d_o: [lhs' 64 | rhs' 64 | accept 1 .. pad to 132 | status 4]  (one status word covers both base sets)
     rc = msm_run_device_pair(ctx, d_pw + 32, d_l, d_r, N, SNARKV_MONTGOMERY, format, format, SNARKV_CHECK_INPUTS, d_o, d_o + 132);
     if (rc) return rc;
     rc = kzg_decide_device(ctx, d_o, d_o + 64, 1, format, d_o + 128, nullptr);
     if (rc) return rc;
-    uint8_t host[140];
-    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(host, d_o, 140, cudaMemcpyDeviceToHost, st));
+    uint8_t host[136];
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(host, d_o, 136, cudaMemcpyDeviceToHost, st));
     SNARKV_CUDA_TRY(ctx, cudaStreamSynchronize(st));
-    int status_l, status_r;
-    memcpy(&status_l, host + 132, 4);
-    memcpy(&status_r, host + 136, 4);
-    *accept = (status_l == 0 && status_r == 0 && host[128] == 1) ? 1 : 0;   // a non-curve accumulator rejects the batch
+    int status;
+    memcpy(&status, host + 132, 4);
+    *accept = (status == 0 && host[128] == 1) ? 1 : 0;   // a non-curve accumulator rejects the batch
     if (out_lhs) memcpy(out_lhs, host, 64);
     if (out_rhs) memcpy(out_rhs, host + 64, 64);
     return SNARKV_OK;
@@ -412,6 +497,7 @@ int snarkv_fr_mul_vec(snarkv_ctx* ctx, const uint8_t* a, const uint8_t* b, size_
 int snarkv_kzg_accumulators_from_limbs(snarkv_ctx* ctx, const uint8_t* limbs, size_t m, uint32_t num_limbs, uint32_t limb_bits, int format,
                                        uint8_t* lhs, uint8_t* rhs, uint8_t* valid) {
     CTX_GUARD(ctx);
+    if (m == 0 && !bad_format(format)) return SNARKV_OK;   // an empty batch needs no buffers
     if (!limbs || !lhs || !rhs || !valid || bad_format(format) || num_limbs == 0 || num_limbs > 8 || limb_bits == 0 ||
         (uint64_t)limb_bits * (num_limbs - 1) > 256)
         return ctx->fail(SNARKV_ERR_USAGE, "snarkv_kzg_accumulators_from_limbs: bad argument");
@@ -476,7 +562,7 @@ int snarkv_fr_program_eval_batch_device(snarkv_ctx* ctx, const snarkv_fr_instr* 
                                         const uint8_t* consts, size_t n_consts, const void* d_inputs, size_t n_inputs, size_t m,
                                         const uint32_t* out_regs, size_t n_out, int format, void* d_outputs) {
     CTX_GUARD(ctx);
-    if (!d_outputs || (n_inputs && !d_inputs)) return ctx->fail(SNARKV_ERR_USAGE, "snarkv_fr_program_eval_batch_device: bad argument");
+    if (m != 0 && (!d_outputs || (n_inputs && !d_inputs))) return ctx->fail(SNARKV_ERR_USAGE, "snarkv_fr_program_eval_batch_device: bad argument");
     uint8_t *d_prog, *d_consts, *d_out_regs;
     int rc = fr_program_stage(ctx, program, n_instr, n_regs, consts, n_consts, n_inputs, m, out_regs, n_out, format, &d_prog, &d_consts, &d_out_regs);
     if (rc) return rc;
@@ -492,7 +578,7 @@ int snarkv_fr_program_eval_batch(snarkv_ctx* ctx, const snarkv_fr_instr* program
                                  size_t n_consts, const uint8_t* inputs, size_t n_inputs, size_t m, const uint32_t* out_regs, size_t n_out,
                                  int format, uint8_t* outputs) {
     CTX_GUARD(ctx);
-    if (!outputs || (n_inputs && !inputs)) return ctx->fail(SNARKV_ERR_USAGE, "snarkv_fr_program_eval_batch: bad argument");
+    if (m != 0 && (!outputs || (n_inputs && !inputs))) return ctx->fail(SNARKV_ERR_USAGE, "snarkv_fr_program_eval_batch: bad argument");
     uint8_t *d_prog, *d_consts, *d_out_regs;
     int rc = fr_program_stage(ctx, program, n_instr, n_regs, consts, n_consts, n_inputs, m, out_regs, n_out, format, &d_prog, &d_consts, &d_out_regs);
     if (rc) return rc;

@@ -11,6 +11,8 @@
 
 #include "../../include/snarkv_cuda.h"
 
+#define SNARKV_MAX_DEVICES 16   // devices of one multi-device context (one box: 8)
+
 namespace snarkv {
 
 struct StageRecord {
@@ -173,13 +175,18 @@ int msm_run_device(snarkv_ctx* ctx, const void* d_scalars, const void* d_points,
 int msm_run_device_pair(snarkv_ctx* ctx, const void* d_scalars, const void* d_points0, const void* d_points1, size_t n, int scalar_format,
                         int point_format, int out_format, int flags, void* d_out_affine, void* d_status);
 int msm_run_host(snarkv_ctx* ctx, const uint8_t* scalars, const uint8_t* points, size_t n, int format, int flags, uint8_t* out,
-                 void* d_out_jacobian);
+                 void* d_out_jacobian, const uint8_t* d_resident = nullptr);
+int msm_bases_prepare(snarkv_ctx* ctx, const void* d_in, size_t n, int format, int check, void* d_out, void* d_status);
 void msm_plan_query(snarkv_ctx* ctx, size_t n, uint32_t out[4]);
 int msm_fold_partials_device(snarkv_ctx* ctx, const void* d_partials, size_t k, int format, void* d_out_affine);
 int msm_batch_device(snarkv_ctx* ctx, const void* d_scalars, const void* d_points, const void* d_offsets, size_t m, size_t total,
                      int format, int flags, void* d_out_affine, void* d_status);
 int msm_batch_rlc_device(snarkv_ctx* ctx, const void* d_scalars, const void* d_points, const void* d_offsets, size_t m, size_t total,
-                         const void* d_rho, int format, int flags, void* d_scaled, void* d_powers, void* d_out_affine, void* d_status);
+                         const void* d_rho, int format, int flags, void* d_scaled, void* d_powers, void* d_out_affine, void* d_status,
+                         uint64_t first_power = 0, void* d_out_jacobian = nullptr);
+int msm_batch_rlc_host(snarkv_ctx* ctx, const uint8_t* scalars, const uint8_t* points, const uint64_t* offsets, size_t m, const uint8_t rho[32],
+                       int format, int flags, uint64_t first_power, uint8_t* out_affine, void* d_out_jacobian);
+int msm_fold_partials_peer(snarkv_ctx* ctx, const void* const* d_partials, size_t k, int format, void* d_out_affine);
 int fr_batch_invert_device(snarkv_ctx* ctx, void* d_values, size_t n, int format, const void* d_coeff, void* d_scratch);
 int accumulators_from_limbs_device(snarkv_ctx* ctx, const void* d_limbs, size_t m, uint32_t L, uint32_t bits, int format, void* d_lhs,
                                    void* d_rhs, void* d_valid);
@@ -189,7 +196,7 @@ int fr_mul_vec_device(snarkv_ctx* ctx, const void* d_a, const void* d_b, size_t 
 int fr_from_mont_device(snarkv_ctx* ctx, void* d_v, size_t n);
 int evm_transcript_device(snarkv_ctx* ctx, const void* d_streams, size_t stream_len, const void* d_seg_end, size_t k, size_t m, int format,
                           void* d_out);
-int fr_powers_device(snarkv_ctx* ctx, const void* d_r, int format, size_t n, void* d_out_mont);
+int fr_powers_device(snarkv_ctx* ctx, const void* d_r, int format, size_t n, void* d_out_mont, uint64_t first = 0);
 int field_op_device(snarkv_ctx* ctx, int field, int op, const void* d_a, const void* d_b, size_t n, void* d_out);
 int synth_scalars_device(snarkv_ctx* ctx, uint64_t seed, uint64_t start, size_t n, int format, void* d_out);
 int synth_points_device(snarkv_ctx* ctx, uint64_t seed, uint64_t start, size_t n, int format, void* d_out);

@@ -185,6 +185,16 @@ template <Field F> __device__ __forceinline__ Fp<F> fp_load(const void* p) {
     r.v[4] = hi.x; r.v[5] = hi.y; r.v[6] = hi.z; r.v[7] = hi.w;
     return r;
 }
+// coherent variant: for buffers the running kernel also WRITES (the read-only / ld.global.nc path of fp_load is only legal for
+// data that stays constant for the whole kernel)
+template <Field F> __device__ __forceinline__ Fp<F> fp_load_rw(const void* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 lo = q[0], hi = q[1];
+    Fp<F> r;
+    r.v[0] = lo.x; r.v[1] = lo.y; r.v[2] = lo.z; r.v[3] = lo.w;
+    r.v[4] = hi.x; r.v[5] = hi.y; r.v[6] = hi.z; r.v[7] = hi.w;
+    return r;
+}
 template <Field F> __device__ __forceinline__ void fp_store(void* p, const Fp<F>& a) {
     uint4* q = reinterpret_cast<uint4*>(p);
     q[0] = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]);

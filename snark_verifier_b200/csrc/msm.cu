@@ -94,8 +94,9 @@ __global__ void k_points_prepare(const uint8_t* __restrict__ in, uint8_t* __rest
                                  int* __restrict__ status) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         G1Affine p = g1_affine_load(in, i);
+        // raw limbs must be reduced in EITHER format: zero tests and equality tests downstream assume a unique representative
+        if (check && (!fp_is_canonical(p.x) || !fp_is_canonical(p.y))) atomicCAS(status, 0, SNARKV_ERR_BAD_POINT);
         if (format == SNARKV_CANONICAL) {
-            if (check && (!fp_is_canonical(p.x) || !fp_is_canonical(p.y))) atomicCAS(status, 0, SNARKV_ERR_BAD_POINT);
             p.x = fp_to_mont(p.x);
             p.y = fp_to_mont(p.y);
         }
@@ -179,8 +180,8 @@ __global__ void __launch_bounds__(SNARKV_DIGIT_TILE) k_digits(const uint8_t* __r
                 uint4 lo = q[0], hi = q[1];
                 s.v[0] = lo.x; s.v[1] = lo.y; s.v[2] = lo.z; s.v[3] = lo.w; s.v[4] = hi.x; s.v[5] = hi.y; s.v[6] = hi.z; s.v[7] = hi.w;
             }
+            if (check && !fp_is_canonical(s)) atomicCAS(status, 0, SNARKV_ERR_BAD_SCALAR);   // raw limbs >= r in either format
             if (format == SNARKV_MONTGOMERY) s = fp_from_mont(s);
-            else if (check && !fp_is_canonical(s)) atomicCAS(status, 0, SNARKV_ERR_BAD_SCALAR);
             if (!GLV) {
                 uint32_t carry = 0;
                 for (uint32_t w = 0; w < W; ++w) {
@@ -557,6 +558,27 @@ __global__ void k_fold_partials(const uint8_t* __restrict__ partials, uint32_t k
     }
 }
 
+// The same fold fused with the gather: partial i is read straight out of the memory of the GPU that produced it (peer access over
+// NVLink: `src.p[i]` points into device i's HBM), so the one exchange step of the chunk-partitioned MSM (util/msm.rs:333-335 across
+// GPUs) needs no separate collective or staging copy — 96 bytes per peer cross the link inside this kernel.
+struct PartialPtrs { const uint8_t* p[SNARKV_MAX_DEVICES]; };
+__global__ void k_fold_partials_peer(PartialPtrs src, uint32_t k, int format, void* out_affine, void* out_jacobian) {
+    __shared__ Fq xch[4];
+    const int lane = threadIdx.x & 3;
+    G1Xyzz acc = xyzz_identity();
+    for (uint32_t i = 0; i < k; ++i) {
+        G1Jac j;
+        const uint8_t* p = src.p[i];
+        j.x = fp_load_rw<FQ>(p); j.y = fp_load_rw<FQ>(p + 32); j.z = fp_load_rw<FQ>(p + 64);   // coherent loads: peer memory
+        acc = xyzz_add_x4(acc, jacobian_to_xyzz(j), lane, xch);
+    }
+    if (out_jacobian && threadIdx.x == 0) store_jacobian(out_jacobian, xyzz_to_jacobian(acc));
+    if (out_affine) {
+        G1Affine a = xyzz_to_affine_serial(acc);
+        if (threadIdx.x == 0) store_affine_fmt(out_affine, a, format);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // host orchestration
 // ---------------------------------------------------------------------------------------------------------------------
@@ -577,6 +599,8 @@ static int msm_alloc(snarkv_ctx* ctx, size_t n, void* d_status, MsmWork& wk, int
     if (n >= (1ull << 31)) return ctx->fail(SNARKV_ERR_USAGE, "n must be < 2^31");
     wk.pl = make_plan(n, ctx->window_bits, glv_mode >= 0 ? glv_mode : ctx->glv_mode);
     const MsmPlan& pl = wk.pl;
+    // sorted references keep the (virtual) term index in 31 bits next to the sign bit
+    if (plan_virtual_terms(pl, n) >= (1ull << 31)) return ctx->fail(SNARKV_ERR_USAGE, "GLV doubles the term count: n must be < 2^30 with snarkv_set_glv_mode(1)");
     const size_t nbk = (size_t)pl.W * pl.NB;
     wk.status = (int*)d_status;
     if (!wk.status) wk.status = (int*)ctx->wsget(WS_STATUS, 4);
@@ -650,15 +674,16 @@ static int msm_sort_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* d_scal
 // array.  B = 1 or 2 base sets share the scalars / sort of `wk`.  `add_existing`: the buckets already hold the sums of earlier
 // term-chunks of the same MSM (host entry point pipeline) and this chunk is added on top.  `conv_dst`: caller-provided
 // destination for the Montgomery copy of CANONICAL points (B must be 1).
+// `prepared`: d_points is a resident base set (snarkv_g1_bases_upload): validated, Montgomery, [P | phi(P)] — nothing to convert.
 static int msm_accumulate_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* d_points, size_t n, int point_format, int check,
-                                const void* d_points1 = nullptr, int add_existing = 0, uint8_t* conv_dst = nullptr) {
+                                const void* d_points1 = nullptr, int add_existing = 0, uint8_t* conv_dst = nullptr, bool prepared = false) {
     const MsmPlan& pl = wk.pl;
     cudaStream_t st = ctx->stream;
     const size_t nbk = (size_t)pl.W * pl.NB;
     const int B = d_points1 ? 2 : 1;
     const size_t nv = plan_virtual_terms(pl, n);
     const uint8_t* pts[2] = {(const uint8_t*)d_points, (const uint8_t*)d_points1};
-    if (point_format == SNARKV_CANONICAL || check || pl.glv) {
+    if (!prepared && (point_format == SNARKV_CANONICAL || check || pl.glv)) {
         Stage sg(ctx, "msm_points_prepare");
         uint8_t* conv = nullptr;
         if (point_format == SNARKV_CANONICAL || pl.glv) {   // GLV gathers from one array [P | phi(P)] of nv points per base set
@@ -824,12 +849,16 @@ int msm_run_device(snarkv_ctx* ctx, const void* d_scalars, const void* d_points,
 // geometrically growing size (x1.6; measured sweep profiles/r01_host_chunks.txt): chunk k+1 is copied on the copy stream while chunk k is sorted and accumulated INTO THE SAME
 // bucket array (plan fixed from the total n), so the first copy is short, no chunk pays its own reduce / Horner tail, and the
 // copy engine stays ahead of the SMs (96 B/term at ~50 GB/s vs ~2.9 ns/term of compute).
+// `d_resident` != nullptr: the bases already sit in HBM (prepared by msm_bases_prepare: Montgomery, validated, phi(P) appended);
+// `points` is then ignored and only the scalars cross PCIe.
 int msm_run_host(snarkv_ctx* ctx, const uint8_t* scalars, const uint8_t* points, size_t n, int format, int flags, uint8_t* out,
-                 void* d_out_jacobian) {
+                 void* d_out_jacobian, const uint8_t* d_resident) {
     const int check = (flags & SNARKV_CHECK_INPUTS) ? 1 : 0;
     if (n == 0) return ctx->fail(SNARKV_ERR_EMPTY, "multi_scalar_multiplication on an empty slice");
+    const bool resident = d_resident != nullptr;
+    const int pfmt = resident ? SNARKV_MONTGOMERY : format;
     uint8_t* d_s = (uint8_t*)ctx->wsget(WS_IO_A, n * 32);
-    uint8_t* d_p = (uint8_t*)ctx->wsget(WS_IO_B, n * 64);
+    uint8_t* d_p = resident ? const_cast<uint8_t*>(d_resident) : (uint8_t*)ctx->wsget(WS_IO_B, n * 64);
     uint8_t* d_o = (uint8_t*)ctx->wsget(WS_OUT, 1024);   // [affine 64 | pad | status K x 4 @512]
     if (!d_s || !d_p || !d_o) return SNARKV_ERR_CUDA;
     cudaStream_t st = ctx->stream;
@@ -841,15 +870,27 @@ int msm_run_host(snarkv_ctx* ctx, const uint8_t* scalars, const uint8_t* points,
     MsmWork wk;
     int rc = msm_alloc(ctx, n, d_status, wk, 1, K > 1 ? 2 : -1);   // plan from the TOTAL size; the chunk pipeline runs without GLV
     if (rc) return rc;
+    // Every early return below first drains the copy stream: it may still be reading the caller's (possibly pinned) buffers.
+    auto bail = [&](int code) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamSynchronize(st);
+        return code;
+    };
+    // the copy stream must not run ahead of work already queued on the compute stream that still reads the staging buffers
+    SNARKV_CUDA_TRY(ctx, cudaEventRecord(ctx->copy_done[SNARKV_HOST_CHUNKS_MAX], st));
+    SNARKV_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_done[SNARKV_HOST_CHUNKS_MAX], 0));
     if (K == 1) {
         SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_s, scalars, n * 32, cudaMemcpyHostToDevice, st));
         rc = msm_sort_phase(ctx, wk, d_s, n, format, check);
-        if (rc) return rc;
-        SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_p, points, n * 64, cudaMemcpyHostToDevice, ctx->copy_stream));
-        SNARKV_CUDA_TRY(ctx, cudaEventRecord(ctx->copy_done[0], ctx->copy_stream));
-        SNARKV_CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->copy_done[0], 0));
-        rc = msm_accumulate_phase(ctx, wk, d_p, n, format, check);
-        if (rc) return rc;
+        if (rc) return bail(rc);
+        if (!resident) {
+            cudaError_t ce = cudaMemcpyAsync(d_p, points, n * 64, cudaMemcpyHostToDevice, ctx->copy_stream);
+            if (ce == cudaSuccess) ce = cudaEventRecord(ctx->copy_done[0], ctx->copy_stream);
+            if (ce == cudaSuccess) ce = cudaStreamWaitEvent(st, ctx->copy_done[0], 0);
+            if (ce != cudaSuccess) return bail(ctx->fail(SNARKV_ERR_CUDA, "host->device copy of the points", ce));
+        }
+        rc = msm_accumulate_phase(ctx, wk, d_p, n, pfmt, resident ? 0 : check, nullptr, 0, nullptr, resident);
+        if (rc) return bail(rc);
     } else {
         size_t lo[SNARKV_HOST_CHUNKS_MAX + 1];
         const double ratio = ctx->host_chunk_ratio_pct / 100.0;
@@ -863,32 +904,38 @@ int msm_run_host(snarkv_ctx* ctx, const uint8_t* scalars, const uint8_t* points,
             lo[k + 1] = (k == K - 1) ? n : (((size_t)((double)n * (acc_w / total_w))) & ~(size_t)255);
         }
         uint8_t* conv = nullptr;
-        if (format == SNARKV_CANONICAL) {
+        if (format == SNARKV_CANONICAL && !resident) {
             conv = (uint8_t*)ctx->wsget(WS_POINTS_MONT, n * 64);
             if (!conv) return SNARKV_ERR_CUDA;
         }
-        // the copy stream must not run ahead of work already queued on the compute stream that still reads the staging buffers
-        SNARKV_CUDA_TRY(ctx, cudaEventRecord(ctx->copy_done[K], st));
-        SNARKV_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_done[K], 0));
+        // Copies are issued one chunk AHEAD of the kernels that consume them (chunk k + 1 goes onto the copy stream right before
+        // chunk k's kernels are launched), so that with pageable host memory — where cudaMemcpyAsync blocks the calling thread
+        // while it stages — the SMs already have chunk k's work queued; real overlap needs PINNED host buffers.
+        auto issue_copy = [&](int k) -> cudaError_t {
+            const size_t len = lo[k + 1] - lo[k];
+            cudaError_t ce = cudaMemcpyAsync(d_s + lo[k] * 32, scalars + lo[k] * 32, len * 32, cudaMemcpyHostToDevice, ctx->copy_stream);
+            if (ce == cudaSuccess && !resident)
+                ce = cudaMemcpyAsync(d_p + lo[k] * 64, points + lo[k] * 64, len * 64, cudaMemcpyHostToDevice, ctx->copy_stream);
+            if (ce == cudaSuccess) ce = cudaEventRecord(ctx->copy_done[k], ctx->copy_stream);
+            return ce;
+        };
+        cudaError_t ce = issue_copy(0);
+        if (ce != cudaSuccess) return bail(ctx->fail(SNARKV_ERR_CUDA, "host->device copy (chunk 0)", ce));
         for (int k = 0; k < K; ++k) {
             const size_t len = lo[k + 1] - lo[k];
-            SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_s + lo[k] * 32, scalars + lo[k] * 32, len * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
-            SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_p + lo[k] * 64, points + lo[k] * 64, len * 64, cudaMemcpyHostToDevice, ctx->copy_stream));
-            SNARKV_CUDA_TRY(ctx, cudaEventRecord(ctx->copy_done[k], ctx->copy_stream));
-        }
-        for (int k = 0; k < K; ++k) {
-            const size_t len = lo[k + 1] - lo[k];
-            SNARKV_CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->copy_done[k], 0));
+            if (k + 1 < K && (ce = issue_copy(k + 1)) != cudaSuccess) return bail(ctx->fail(SNARKV_ERR_CUDA, "host->device copy (chunk)", ce));
+            if ((ce = cudaStreamWaitEvent(st, ctx->copy_done[k], 0)) != cudaSuccess) return bail(ctx->fail(SNARKV_ERR_CUDA, "cudaStreamWaitEvent", ce));
             MsmWork wc = wk;
             wc.status = d_status + k;
             rc = msm_sort_phase(ctx, wc, d_s + lo[k] * 32, len, format, check);
-            if (rc) return rc;
-            rc = msm_accumulate_phase(ctx, wc, d_p + lo[k] * 64, len, format, check, nullptr, k > 0, conv ? conv + lo[k] * 64 : nullptr);
-            if (rc) return rc;
+            if (rc) return bail(rc);
+            rc = msm_accumulate_phase(ctx, wc, d_p + lo[k] * 64, len, pfmt, resident ? 0 : check, nullptr, k > 0, conv ? conv + lo[k] * 64 : nullptr,
+                                      resident);
+            if (rc) return bail(rc);
         }
     }
     rc = msm_tail_phase(ctx, wk, 1, format, out ? d_o : nullptr, d_out_jacobian);
-    if (rc) return rc;
+    if (rc) return bail(rc);
     if (out) SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(out, d_o, 64, cudaMemcpyDeviceToHost, st));
     SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(status, d_status, 4 * K, cudaMemcpyDeviceToHost, st));
     SNARKV_CUDA_TRY(ctx, cudaStreamSynchronize(st));
@@ -898,9 +945,32 @@ int msm_run_host(snarkv_ctx* ctx, const uint8_t* scalars, const uint8_t* points,
     return SNARKV_OK;
 }
 
+// Resident base set: d_out (2 n x 64 B) <- [Montgomery P_i | phi(P_i)], validated when `check`; status word reports BAD_POINT.
+int msm_bases_prepare(snarkv_ctx* ctx, const void* d_in, size_t n, int format, int check, void* d_out, void* d_status) {
+    Stage sg(ctx, "msm_bases_prepare");
+    SNARKV_CUDA_TRY(ctx, cudaMemsetAsync(d_status, 0, 4, ctx->stream));
+    const size_t want = (n + 255) / 256, cap = (size_t)ctx->sm_count * 8;
+    k_points_prepare<<<(int)(want < cap ? want : cap), 256, 0, ctx->stream>>>((const uint8_t*)d_in, (uint8_t*)d_out, n, format, check, 1,
+                                                                             (int*)d_status);
+    SNARKV_LAUNCH_CHECK(ctx, "k_points_prepare");
+    sg.launched();
+    return SNARKV_OK;
+}
+
 void msm_plan_query(snarkv_ctx* ctx, size_t n, uint32_t out[4]) {
     const MsmPlan pl = make_plan(n ? n : 1, ctx->window_bits, ctx->glv_mode);
     out[0] = pl.c; out[1] = pl.W; out[2] = pl.NB; out[3] = pl.T;
+}
+
+int msm_fold_partials_peer(snarkv_ctx* ctx, const void* const* d_partials, size_t k, int format, void* d_out_affine) {
+    if (k == 0 || k > SNARKV_MAX_DEVICES) return ctx->fail(SNARKV_ERR_USAGE, "fold_partials_peer: bad k");
+    PartialPtrs src = {};
+    for (size_t i = 0; i < k; ++i) src.p[i] = (const uint8_t*)d_partials[i];
+    Stage sg(ctx, "msm_fold_partials_peer");
+    k_fold_partials_peer<<<1, 32, 0, ctx->stream>>>(src, (uint32_t)k, format, d_out_affine, nullptr);
+    SNARKV_LAUNCH_CHECK(ctx, "k_fold_partials_peer");
+    sg.launched();
+    return SNARKV_OK;
 }
 
 int msm_fold_partials_device(snarkv_ctx* ctx, const void* d_partials, size_t k, int format, void* d_out_affine) {
@@ -923,10 +993,10 @@ __global__ void __launch_bounds__(128) k_batch_term_mul(const uint8_t* __restric
     if (i >= total) return;
     Fr s = fp_load<FR>(scalars + i * 32);
     G1Affine p = g1_affine_load(points, i);
+    if (check && !fp_is_canonical(s)) atomicCAS(status, 0, SNARKV_ERR_BAD_SCALAR);
+    if (check && (!fp_is_canonical(p.x) || !fp_is_canonical(p.y))) atomicCAS(status, 0, SNARKV_ERR_BAD_POINT);
     if (format == SNARKV_MONTGOMERY) s = fp_from_mont(s);
     else {
-        if (check && !fp_is_canonical(s)) atomicCAS(status, 0, SNARKV_ERR_BAD_SCALAR);
-        if (check && (!fp_is_canonical(p.x) || !fp_is_canonical(p.y))) atomicCAS(status, 0, SNARKV_ERR_BAD_POINT);
         p.x = fp_to_mont(p.x);
         p.y = fp_to_mont(p.y);
     }
@@ -976,22 +1046,23 @@ int msm_batch_device(snarkv_ctx* ctx, const void* d_scalars, const void* d_point
 // ---------------------------------------------------------------------------------------------------------------------
 // r.powers(n)  (snark-verifier/src/loader.rs:71-78) on the device: out[i] = r^i in Montgomery form
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void k_fr_powers(const uint8_t* __restrict__ r_in, int format, size_t n, uint8_t* __restrict__ out) {
+__global__ void k_fr_powers(const uint8_t* __restrict__ r_in, int format, size_t n, uint64_t first, uint8_t* __restrict__ out) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Fr r = fp_load<FR>(r_in);
     if (format == SNARKV_CANONICAL) r = fp_to_mont(r);
     Fr acc = fp_one<FR>();
-    for (size_t e = i; e != 0; e >>= 1) {
+    for (uint64_t e = first + i; e != 0; e >>= 1) {
         if (e & 1) acc = fp_mul(acc, r);
         r = fp_sqr(r);
     }
     fp_store<FR>(out + i * 32, acc);
 }
 
-int fr_powers_device(snarkv_ctx* ctx, const void* d_r, int format, size_t n, void* d_out_mont) {
+// out[i] = r^(first + i): `first` > 0 is a shard of a longer power sequence (multi-device RLC batches, multi.cu)
+int fr_powers_device(snarkv_ctx* ctx, const void* d_r, int format, size_t n, void* d_out_mont, uint64_t first) {
     Stage sg(ctx, "fr_powers");
-    k_fr_powers<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((const uint8_t*)d_r, format, n, (uint8_t*)d_out_mont);
+    k_fr_powers<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((const uint8_t*)d_r, format, n, first, (uint8_t*)d_out_mont);
     SNARKV_LAUNCH_CHECK(ctx, "k_fr_powers");
     sg.launched();
     return SNARKV_OK;
@@ -1005,15 +1076,16 @@ int fr_powers_device(snarkv_ctx* ctx, const void* d_r, int format, size_t n, voi
 // in `scratch`, ONE inversion per chunk, then the backward sweep — 3 multiplications per value + 1/CHUNK of an inversion.
 // ---------------------------------------------------------------------------------------------------------------------
 #define SNARKV_INV_CHUNK 64
-__global__ void __launch_bounds__(128) k_fr_batch_invert(uint8_t* __restrict__ values, size_t n, int format, const uint8_t* __restrict__ coeff,
-                                                         uint8_t* __restrict__ scratch) {
+// `values` and `scratch` are written and read back by the same thread: plain (coherent) loads, no __restrict__ / __ldg on them.
+__global__ void __launch_bounds__(128) k_fr_batch_invert(uint8_t* values, size_t n, int format, const uint8_t* __restrict__ coeff,
+                                                         uint8_t* scratch) {
     const size_t chunk = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t lo = chunk * SNARKV_INV_CHUNK;
     if (lo >= n) return;
     const size_t hi = (lo + SNARKV_INV_CHUNK < n) ? lo + SNARKV_INV_CHUNK : n;
     Fr acc = fp_one<FR>();
     for (size_t i = lo; i < hi; ++i) {
-        Fr v = fp_load<FR>(values + i * 32);
+        Fr v = fp_load_rw<FR>(values + i * 32);
         if (format == SNARKV_CANONICAL) v = fp_to_mont(v);
         fp_store<FR>(scratch + i * 32, acc);             // product of the non-zero values before i
         if (!fp_is_zero(v)) acc = fp_mul(acc, v);
@@ -1025,10 +1097,10 @@ __global__ void __launch_bounds__(128) k_fr_batch_invert(uint8_t* __restrict__ v
         inv = fp_mul(inv, c);
     }
     for (size_t i = hi; i-- > lo;) {
-        Fr v = fp_load<FR>(values + i * 32);
+        Fr v = fp_load_rw<FR>(values + i * 32);
         if (format == SNARKV_CANONICAL) v = fp_to_mont(v);
         if (fp_is_zero(v)) continue;                     // `unwrap_or_else(|| value.clone())`: zero is left as it is
-        Fr out = fp_mul(inv, fp_load<FR>(scratch + i * 32));
+        Fr out = fp_mul(inv, fp_load_rw<FR>(scratch + i * 32));
         inv = fp_mul(inv, v);
         if (format == SNARKV_CANONICAL) out = fp_from_mont(out);
         fp_store<FR>(values + i * 32, out);
@@ -1045,9 +1117,9 @@ __global__ void __launch_bounds__(256) k_fr_mul_vec(const uint8_t* __restrict__ 
     fp_store<FR>(out + i * 32, fp_mul(x, y));            // Montgomery in -> Montgomery out; canonical in -> canonical out
 }
 
-__global__ void k_fr_from_mont(uint8_t* __restrict__ v, size_t n) {
+__global__ void k_fr_from_mont(uint8_t* v, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) fp_store<FR>(v + i * 32, fp_from_mont(fp_load<FR>(v + i * 32)));
+    if (i < n) fp_store<FR>(v + i * 32, fp_from_mont(fp_load_rw<FR>(v + i * 32)));
 }
 
 int fr_batch_invert_device(snarkv_ctx* ctx, void* d_values, size_t n, int format, const void* d_coeff, void* d_scratch) {
@@ -1089,18 +1161,16 @@ __global__ void __launch_bounds__(256) k_fr_scale_segments(const uint8_t* __rest
         if (offsets[mid] <= i) lo = mid; else hi = mid;
     }
     Fr s = fp_load<FR>(scalars + i * 32);
-    if (format == SNARKV_CANONICAL) {
-        if (check && !fp_is_canonical(s)) atomicCAS(status, 0, SNARKV_ERR_BAD_SCALAR);
-        s = fp_to_mont(s);
-    }
+    if (check && !fp_is_canonical(s)) atomicCAS(status, 0, SNARKV_ERR_BAD_SCALAR);
+    if (format == SNARKV_CANONICAL) s = fp_to_mont(s);
     fp_store<FR>(out_mont + i * 32, fp_mul(s, fp_load<FR>(powers_mont + lo * 32)));
 }
 
 int msm_batch_rlc_device(snarkv_ctx* ctx, const void* d_scalars, const void* d_points, const void* d_offsets, size_t m, size_t total,
                          const void* d_rho, int format, int flags, void* d_scaled /* total x 32 B scratch */, void* d_powers /* m x 32 B */,
-                         void* d_out_affine, void* d_status) {
+                         void* d_out_affine, void* d_status, uint64_t first_power, void* d_out_jacobian) {
     const int check = (flags & SNARKV_CHECK_INPUTS) ? 1 : 0;
-    int rc = fr_powers_device(ctx, d_rho, format, m, d_powers);
+    int rc = fr_powers_device(ctx, d_rho, format, m, d_powers, first_power);
     if (rc) return rc;
     SNARKV_CUDA_TRY(ctx, cudaMemsetAsync(d_status, 0, 8, ctx->stream));
     {
@@ -1112,7 +1182,7 @@ int msm_batch_rlc_device(snarkv_ctx* ctx, const void* d_scalars, const void* d_p
         sg.launched();
     }
     // the MSM keeps its own status word right after ours so that a scalar error found above is not overwritten
-    return msm_run_device(ctx, d_scaled, d_points, total, SNARKV_MONTGOMERY, format, format, flags, d_out_affine, nullptr,
+    return msm_run_device(ctx, d_scaled, d_points, total, SNARKV_MONTGOMERY, format, format, flags, d_out_affine, d_out_jacobian,
                           (uint8_t*)d_status + 4);
 }
 

@@ -15,7 +15,7 @@ of each `verify` are the loader's `multi_scalar_multiplication` — on a CudaLoa
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
-from . import KzgAccumulator, Msm, R_MODULUS
+from . import CHECK_INPUTS, KzgAccumulator, Msm, R_MODULUS
 
 Q_MODULUS = 0x30644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD47   # BN254 base field
 
@@ -277,6 +277,7 @@ class KzgBatchVerifier:
     def __init__(self, loader, kzg, svk_g: bytes, queries: Sequence[tuple], num_polys: int, scheme: str = "gwc19"):
         from .plonk_eval import compile_bdfg21_msm_scalars, compile_gwc19_msm_scalars
         self.loader, self.kzg, self.g, self.scheme = loader, kzg, bytes(svk_g), scheme
+        self.flags = CHECK_INPUTS   # checked by default; a caller that has already validated every point may clear it
         self.compiled = {"gwc19": compile_gwc19_msm_scalars, "bdfg21": compile_bdfg21_msm_scalars}[scheme](queries, num_polys)
 
     def _points(self, slots, proof):
@@ -303,8 +304,10 @@ class KzgBatchVerifier:
         lhs_s = np.ascontiguousarray(scal[:, :nl]).reshape(-1)
         rhs_s = np.ascontiguousarray(scal[:, nl:]).reshape(-1)
         rho_b = (rho % R_MODULUS).to_bytes(32, "little")
-        lhs = self.loader.msm_batch_rlc(lhs_s, lhs_points, np.arange(m + 1, dtype=np.uint64) * nl, rho_b)
-        rhs = self.loader.msm_batch_rlc(rhs_s, rhs_points, np.arange(m + 1, dtype=np.uint64) * nr, rho_b)
+        # proof-supplied points are validated on the device like the reference's `read_ec_point` / `from_xy` does before any
+        # arithmetic (canonical coordinates, on the curve): an invalid one surfaces as Error (SNARKV_ERR_BAD_POINT)
+        lhs = self.loader.msm_batch_rlc(lhs_s, lhs_points, np.arange(m + 1, dtype=np.uint64) * nl, rho_b, flags=self.flags)
+        rhs = self.loader.msm_batch_rlc(rhs_s, rhs_points, np.arange(m + 1, dtype=np.uint64) * nr, rho_b, flags=self.flags)
         return KzgAccumulator(lhs, rhs)
 
     def verify_batch(self, proofs: Sequence[dict], rho: int):
