@@ -157,3 +157,29 @@ def test_external_known_answers_from_ethereum_precompile_vectors():
     assert (x[1], x[0], y[1], y[0]) == two_g2_evm_words
     x1, x0, y1, y0 = two_g2_evm_words
     assert oracle.g2_mul(oracle.g2_generator(), le(2)) == le(x0) + le(x1) + le(y0) + le(y1)
+
+
+def test_eip196_eip197_public_vectors_pin_the_oracle(golden):
+    """EXTERNAL known answers: Ethereum's alt_bn128 precompile vectors (tests/golden/eip_vectors.json, validated by
+    oracle/gen_golden_eip.py) through the C++ restatement — scalar multiplication, addition, and three `bn256Pairing` accept cases
+    run as KZG decisions (g2 = Q1, s_g2 = -Q2) plus their public reject twins (second G1 operand negated)."""
+    from eip_helpers import as_deciding_key, g1_bytes, h, pairing_operands
+    g = golden("eip_vectors")
+    le = m.fe_to_le
+    for v in g["scalar_mul"]:
+        pt, exp = g1_bytes(v["x"], v["y"]), g1_bytes(v["out_x"], v["out_y"])
+        s = le(h(v["scalar"]) % m.R)
+        assert oracle.g1_mul(pt, s) == exp, v["name"]
+        assert oracle.msm_native(s, pt, 1) == exp, v["name"]
+        assert oracle.msm_pippenger(s, pt, 1) == exp, v["name"]
+    for v in g["add"]:
+        a, b, exp = g1_bytes(v["x1"], v["y1"]), g1_bytes(v["x2"], v["y2"]), g1_bytes(v["out_x"], v["out_y"])
+        assert oracle.g1_add(a, b) == exp, v["name"]
+        assert oracle.msm_native(le(1) * 2, a + b, 2) == exp, v["name"]
+    for v in g["pairing"]:
+        p1, q1, p2, q2 = pairing_operands(v["words"])
+        g2, s_g2 = as_deciding_key(q1, q2)
+        ok, gt = oracle.kzg_decide(m.g1_to_bytes(p1), m.g1_to_bytes(p2), g2, s_g2)
+        assert ok and gt == m.gt_to_bytes(m.f12_one()), v["name"]
+        ok, _ = oracle.kzg_decide(m.g1_to_bytes(p1), m.g1_to_bytes(m.g1_neg(p2)), g2, s_g2)
+        assert not ok, v["name"]
