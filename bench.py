@@ -359,6 +359,42 @@ class Aux:
                                       "pairing; verdict = AND over ranks; wall clock incl. H2D"}, m_proofs, "proofs_per_s"
         self.leg("batch_verify_gwc19", batch_verify_gwc19)
 
+        # BASELINE config 3, "independent mode": every proof keeps its own accumulator — 4096 separate 21-term / 3-term MSMs
+        # (snarkv_g1_msm_batch: the literal per-proof `Msm::evaluate`, util/msm.rs:81-98 -> native.rs:61-71) + 4096 separate pairing
+        # checks (decider.rs:84-93).  Terms are synthetic and consistent with the key s = 1: lhs_j and rhs_j evaluate to the same point.
+        def batch_verify_independent():
+            mp = len(my_proofs)
+            with torch.cuda.stream(stream):
+                sc = torch.empty(mp * 12 * 32, dtype=torch.uint8, device=dev)
+                pt = torch.empty(mp * 12 * 64, dtype=torch.uint8, device=dev)
+                L.synth_scalars_device(SEED + 2, rank * mp * 12, mp * 12, sc.data_ptr())
+                L.synth_points_device(SEED + 2, rank * mp * 12, mp * 12, pt.data_ptr())
+            stream.synchronize()
+            sc_h = sc.cpu().numpy().reshape(mp, 12, 32)
+            pt_h = pt.cpu().numpy().reshape(mp, 12, 64)
+            R_MOD = sv.R_MODULUS
+            neg = np.empty((mp, 9, 32), dtype=np.uint8)
+            for j in range(mp):                                    # r - s for the 9 cancelling pairs (host-side test-data prep)
+                for k in range(9):
+                    v = int.from_bytes(sc_h[j, 3 + k].tobytes(), "little")
+                    neg[j, k] = np.frombuffer(((R_MOD - v) % R_MOD).to_bytes(32, "little"), dtype=np.uint8)
+            lhs_s = np.concatenate([sc_h[:, :3], sc_h[:, 3:], neg], axis=1).reshape(-1)           # 3 + 9 + 9 = 21 terms
+            lhs_p = np.concatenate([pt_h[:, :3], pt_h[:, 3:], pt_h[:, 3:]], axis=1).reshape(-1)
+            rhs_s = np.ascontiguousarray(sc_h[:, :3]).reshape(-1)
+            rhs_p = np.ascontiguousarray(pt_h[:, :3]).reshape(-1)
+            lhs_off = [21 * j for j in range(mp + 1)]
+            rhs_off = [3 * j for j in range(mp + 1)]
+            res = {}
+
+            def call():
+                a = b"".join(L.msm_batch(lhs_s, lhs_p, lhs_off))
+                b = b"".join(L.msm_batch(rhs_s, rhs_p, rhs_off))
+                res["acc"], _ = kz.decide_batch(a, b, mp)
+            ms = self.timed_wall(call, 2, warm=1)
+            return ms, res["acc"] == b"\x01" * mp, {"proofs": m_proofs, "what": "BASELINE config 3, independent mode: 4096 separate (21-term lhs + 3-term rhs) "
+                    "MSMs (one accumulator per proof) + 4096 separate pairing checks, sharded by proof; host buffers in, wall clock incl. H2D"}, m_proofs, "proofs_per_s"
+        self.leg("batch_verify_independent", batch_verify_independent)
+
         # BASELINE config 4: one aggregation job = KzgAs::verify over 256 accumulators (accumulation.rs:41-63: two 256-term MSMs with
         # the powers of r computed on the device) + one decide (decider.rs:70-82); host buffers in, wall clock.  A single job does not
         # shard (latency-bound): REPLICAS — every rank runs its own jobs, jobs/s is the sum over ranks.

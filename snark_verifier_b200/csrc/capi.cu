@@ -113,6 +113,10 @@ int snarkv_init(int device, snarkv_ctx** out) {
     c->host_chunks = env_int("SNARKV_HOST_CHUNKS", 2, 7, c->host_chunks);
     c->host_chunk_ratio_pct = env_int("SNARKV_HOST_RATIO", 100, 400, c->host_chunk_ratio_pct);
     c->ba_min_load = env_int("SNARKV_BA_MIN_LOAD", 1, 1 << 20, c->ba_min_load);
+    c->bc_r = env_int("SNARKV_BC_R", 8, 16, c->bc_r);
+    if (c->bc_r != 8 && c->bc_r != 12) c->bc_r = 16;
+    c->bc_auto = env_int("SNARKV_BC_AUTO", 0, 1, c->bc_auto);
+    c->bc_min_load = env_int("SNARKV_BC_MIN_LOAD", 1, 1 << 20, c->bc_min_load);
     *out = c;
     return SNARKV_OK;
 }
@@ -159,7 +163,7 @@ int snarkv_set_pairing_mode(snarkv_ctx* ctx, int mode) {
 }
 
 int snarkv_set_accumulate_mode(snarkv_ctx* ctx, int mode) {
-    if (!ctx || mode < 0 || mode > 3) return SNARKV_ERR_USAGE;
+    if (!ctx || mode < 0 || mode > 5) return SNARKV_ERR_USAGE;
     ctx->accumulate_mode = mode;
     return SNARKV_OK;
 }

@@ -55,6 +55,10 @@ enum WsSlot : int {
     WS_TASK_OUT_CHECK,    // second task-result array (accumulate mode 3)
     WS_FR_REGS,           // fr_program register file: n_regs x m x 32 B
     WS_FR_PROG,           // fr_program: instructions | consts | out_regs
+    WS_SORT_PART,         // two-level sort: [partition sizes | offsets | run cursors], 3 x W x P u32
+    WS_SORT_REC_IDX,      // two-level sort: W x n u32 term references grouped by coarse partition
+    WS_SORT_REC_LO,       // two-level sort: W x n u16 low digit bits of the same records
+    WS_BC_SLAB,           // chained batched-affine accumulation: per resident warp R x 2 KB of running sums
     WS_SLOTS
 };
 
@@ -71,9 +75,10 @@ struct snarkv_ctx {
     int glv_mode = 0;       // 0 = GLV for n < 2^22 (default), 1 = always, 2 = never
     int pairing_mode = 0;   // 0 = choose from N, 1 = one thread per check, 2 = one block per check
     int host_chunks = 7, host_chunk_ratio_pct = 160;   // host entry pipeline: term-chunks of geometrically growing size (SNARKV_HOST_CHUNKS <= 7, SNARKV_HOST_RATIO in percent)
-    int accumulate_mode = 0;   // 0 = choose from the bucket load, 1 = XYZZ, 2 = batched affine, 3 = both + task-level self-check
+    int accumulate_mode = 0;   // 0 = choose from the bucket load, 1 = XYZZ, 2 = batched affine (tree), 3 = XYZZ + tree + task-level self-check, 4 = chained batched affine
     int ba_blocks_per_sm = 0;  // occupancy of k_bucket_accumulate_affine (queried once)
     int ba_k = 128, ba_pairs_min = 24, ba_q = 4, ba_min_load = 48;   // batched-affine tuning (developer knobs: SNARKV_BA_K, _PAIRS_MIN, _Q, _MIN_LOAD)
+    int bc_r = 16, bc_blocks_per_sm = 0, bc_blocks_r = 0, bc_auto = 0, bc_min_load = 32;   // chained batched-affine kernel (SNARKV_BC_R in {8, 12, 16}, SNARKV_BC_AUTO, SNARKV_BC_MIN_LOAD)
     uint64_t launches = 0;
     int sm_count = 148;
 

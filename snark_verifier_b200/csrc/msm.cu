@@ -21,6 +21,8 @@
 #include "g1.cuh"
 #include "glv.cuh"
 #include "bucket_affine.cuh"
+#include "bucket_chain.cuh"
+#include "sort.cuh"
 
 namespace snarkv {
 
@@ -35,6 +37,8 @@ struct MsmPlan {
     uint32_t T;    // max points per accumulate task (a bucket with more points is split into ceil(cnt / T) tasks)
     uint32_t cap;  // task slots per window: sum_b ceil(cnt_b / T) <= NB + n / T
     uint32_t glv;  // 1: every term is split into two half-length terms (P, k1), (phi(P), k2) — glv.cuh
+    uint32_t sort_P;        // two-level sort (sort.cuh): coarse partitions per window (0 = small-input path: histogram + scatter)
+    uint32_t sort_lo_bits;  // low digit bits resolved inside a partition: NB = sort_P << sort_lo_bits
 };
 // With GLV the pipeline sees nv = 2 n "virtual terms" (index i < n: P_i with k1, index n + i: phi(P_i) with k2) whose scalars
 // have 128 bits, so W = ceil(130 / c) windows instead of ceil(255 / c): the additions are the same in number, but the Horner
@@ -83,6 +87,21 @@ static MsmPlan make_plan(size_t n_terms, int c_override, int glv_mode) {
     if (T < 64) T = 64;
     p.T = (uint32_t)T;
     p.cap = p.NB + (uint32_t)(n / T) + 1;
+    // two-level sort for large inputs: partitions of ~32 K references (what one k_sort_buckets block stages in shared memory)
+    p.sort_P = 0;
+    p.sort_lo_bits = 0;
+    if (n >= ((size_t)1 << 18) && p.c >= 9) {
+        uint32_t P = 1;
+        while ((size_t)P * 32768 < n && P < p.NB) P <<= 1;
+        uint32_t lo = (p.c - 1);
+        for (uint32_t q = P; q > 1; q >>= 1) --lo;
+        while (lo > 11) { P <<= 1; --lo; }                       // <= 2048 buckets per partition (shared-memory histogram)
+        while ((size_t)p.W * P > 8192 && lo < 11) { P >>= 1; ++lo; }   // <= 32 KB of partition counters per k_digits block
+        if ((size_t)p.W * P <= 8192 && P >= 1 && ((uint32_t)P << lo) == p.NB) {
+            p.sort_P = P;
+            p.sort_lo_bits = lo;
+        }
+    }
     return p;
 }
 
@@ -145,12 +164,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // The scalar stream is staged through shared memory by TMA bulk copies: one elected thread issues an 8 KB
 // cp.async.bulk per 256-scalar tile into a double buffer while the block decomposes the previous tile.
 #define SNARKV_DIGIT_TILE 256
-template <bool GLV>
+// PART (large inputs, sort.cuh): no global histogram — `counters` is the W x P array of COARSE partition sizes, accumulated in
+// (dynamic) shared memory and flushed once per block; the bucket sizes proper come out of k_sort_buckets.
+template <bool GLV, bool PART>
 __global__ void __launch_bounds__(SNARKV_DIGIT_TILE) k_digits(const uint8_t* __restrict__ scalars, size_t n, int format, int check, uint32_t c,
                                                               uint32_t W, uint32_t NB, uint32_t* __restrict__ counters,
-                                                              uint32_t* __restrict__ digits, int* __restrict__ status) {
+                                                              uint32_t* __restrict__ digits, int* __restrict__ status, uint32_t P,
+                                                              uint32_t lo_bits) {
     __shared__ alignas(128) uint8_t tile[2][SNARKV_DIGIT_TILE * 32];
     __shared__ alignas(8) uint64_t bar[2];
+    extern __shared__ uint32_t part_hist[];   // PART: W x P
+    if (PART) {
+        for (uint32_t k = threadIdx.x; k < W * P; k += SNARKV_DIGIT_TILE) part_hist[k] = 0;
+    }
+    auto count = [&](uint32_t w, uint32_t d) {
+        if (PART) atomicAdd(&part_hist[w * P + ((d - 1u) >> lo_bits)], 1u);
+        else atomicAdd(&counters[w * NB + (d - 1u)], 1u);
+    };
     const uint32_t mask = (1u << c) - 1u;
     const uint32_t tid = threadIdx.x;
     const size_t ntiles = (n + SNARKV_DIGIT_TILE - 1) / SNARKV_DIGIT_TILE;
@@ -197,7 +227,7 @@ __global__ void __launch_bounds__(SNARKV_DIGIT_TILE) k_digits(const uint8_t* __r
                         carry = 1u;
                     } else carry = 0u;
                     digits[(size_t)w * n + i] = d | (neg << 31);
-                    if (d != 0) atomicAdd(&counters[w * NB + (d - 1u)], 1u);
+                    if (d != 0) count(w, d);
                 }
             } else {
                 // two half-length virtual terms: index i carries |k1| (sign neg1) for P_i, index n + i carries |k2| for phi(P_i)
@@ -219,12 +249,18 @@ __global__ void __launch_bounds__(SNARKV_DIGIT_TILE) k_digits(const uint8_t* __r
                             carry = 1u;
                         } else carry = 0u;
                         digits[(size_t)w * nv + i + (size_t)h * n] = d | ((neg ^ sgn[h]) << 31);
-                        if (d != 0) atomicAdd(&counters[w * NB + (d - 1u)], 1u);
+                        if (d != 0) count(w, d);
                     }
                 }
             }
         }
         __syncthreads();
+    }
+    if (PART) {
+        for (uint32_t k = threadIdx.x; k < W * P; k += SNARKV_DIGIT_TILE) {
+            const uint32_t v = part_hist[k];
+            if (v) atomicAdd(&counters[k], v);
+        }
     }
 }
 
@@ -588,6 +624,8 @@ struct MsmWork {
     MsmPlan pl;
     int* status;
     uint32_t *counts, *offsets, *cursor, *sorted, *digits;
+    uint32_t *part_count, *part_off, *part_cursor, *rec_idx;   // two-level sort (sort.cuh)
+    uint16_t* rec_lo;
     uint32_t *task_base, *window_tasks, *big;   // big = [count | list of bucket ids]
     uint2* tasks;
     uint32_t* order;
@@ -610,6 +648,17 @@ static int msm_alloc(snarkv_ctx* ctx, size_t n, void* d_status, MsmWork& wk, int
     const size_t nv = plan_virtual_terms(pl, n);
     wk.sorted = (uint32_t*)ctx->wsget(WS_SORTED, (size_t)pl.W * nv * 4);
     wk.digits = (uint32_t*)ctx->wsget(WS_DIGITS, (size_t)pl.W * nv * 4);
+    wk.part_count = wk.part_off = wk.part_cursor = wk.rec_idx = nullptr;
+    wk.rec_lo = nullptr;
+    if (pl.sort_P) {
+        uint32_t* pc = (uint32_t*)ctx->wsget(WS_SORT_PART, (size_t)3 * pl.W * pl.sort_P * 4);
+        wk.rec_idx = (uint32_t*)ctx->wsget(WS_SORT_REC_IDX, (size_t)pl.W * nv * 4 + 64);   // + slack: k_sort_buckets reads aligned vectors
+        wk.rec_lo = (uint16_t*)ctx->wsget(WS_SORT_REC_LO, (size_t)pl.W * nv * 2 + 64);
+        if (!pc || !wk.rec_idx || !wk.rec_lo) return SNARKV_ERR_CUDA;
+        wk.part_count = pc;
+        wk.part_off = pc + (size_t)pl.W * pl.sort_P;
+        wk.part_cursor = pc + (size_t)2 * pl.W * pl.sort_P;
+    }
     wk.buckets = (uint8_t*)ctx->wsget(WS_BUCKETS, (size_t)B * nbk * 128);
     wk.segpart = (uint8_t*)ctx->wsget(WS_SEGPART, (size_t)B * pl.W * pl.J * 128);
     wk.winsum = (uint8_t*)ctx->wsget(WS_WINSUM, (size_t)B * pl.W * 128);
@@ -632,16 +681,55 @@ static int msm_sort_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* d_scal
     const size_t want = (n + SNARKV_DIGIT_TILE - 1) / SNARKV_DIGIT_TILE, cap = (size_t)ctx->sm_count * 8;
     const int dig_blocks = (int)(want < cap ? want : cap);
     if ((reinterpret_cast<uintptr_t>(d_scalars) & 15u) != 0) return ctx->fail(SNARKV_ERR_USAGE, "scalar buffer must be 16-byte aligned");
-    {
+    const size_t nvt = plan_virtual_terms(pl, n);
+    if (pl.sort_P) {
+        // large inputs: two-level partition without per-element global atomics (sort.cuh)
+        const uint32_t P = pl.sort_P, lo = pl.sort_lo_bits;
+        {
+            Stage sg(ctx, "msm_digits");
+            SNARKV_CUDA_TRY(ctx, cudaMemsetAsync(wk.status, 0, 4, st));
+            SNARKV_CUDA_TRY(ctx, cudaMemsetAsync(wk.part_count, 0, (size_t)pl.W * P * 4, st));
+            const size_t hist_bytes = (size_t)pl.W * P * 4;
+            auto kd = pl.glv ? k_digits<true, true> : k_digits<false, true>;
+            SNARKV_CUDA_TRY(ctx, cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
+            kd<<<dig_blocks, 256, hist_bytes, st>>>((const uint8_t*)d_scalars, n, scalar_format, check, pl.c, pl.W, pl.NB, wk.part_count, wk.digits,
+                                                    wk.status, P, lo);
+            SNARKV_LAUNCH_CHECK(ctx, "k_digits<part>");
+            sg.launched();
+        }
+        {
+            Stage sg(ctx, "msm_sort_partition");
+            k_part_scan<<<pl.W < 64 ? pl.W : 64, 1024, 0, st>>>(wk.part_count, wk.part_off, wk.part_cursor, pl.W, P);
+            SNARKV_LAUNCH_CHECK(ctx, "k_part_scan");
+            sg.launched();
+            const size_t smem = (size_t)3 * P * 4 + (size_t)SNARKV_SORT_TILE * 8;
+            SNARKV_CUDA_TRY(ctx, cudaFuncSetAttribute(k_partition, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const size_t items = ((nvt + SNARKV_SORT_TILE - 1) / SNARKV_SORT_TILE) * pl.W;
+            const size_t want_b = items, cap_b = (size_t)ctx->sm_count * 4;
+            k_partition<<<(unsigned)(want_b < cap_b ? want_b : cap_b), SNARKV_SORT_THREADS, smem, st>>>(wk.digits, nvt, pl.W, P, lo, wk.part_off,
+                                                                                                       wk.part_cursor, wk.rec_idx, wk.rec_lo);
+            SNARKV_LAUNCH_CHECK(ctx, "k_partition");
+            sg.launched();
+        }
+        {
+            Stage sg(ctx, "msm_sort_buckets");
+            const size_t smem = ((size_t)2 * (1u << lo) + 1 + SNARKV_SORT_CAP) * 4;
+            SNARKV_CUDA_TRY(ctx, cudaFuncSetAttribute(k_sort_buckets, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_sort_buckets<<<dim3(P, pl.W), SNARKV_SORT_BUCKET_THREADS, smem, st>>>(wk.rec_idx, wk.rec_lo, nvt, P, lo, pl.NB, wk.part_off, wk.part_count,
+                                                                                   wk.counts, wk.sorted);
+            SNARKV_LAUNCH_CHECK(ctx, "k_sort_buckets");
+            sg.launched();
+        }
+    } else {
         Stage sg(ctx, "msm_digits_count");
         SNARKV_CUDA_TRY(ctx, cudaMemsetAsync(wk.status, 0, 4, st));
         SNARKV_CUDA_TRY(ctx, cudaMemsetAsync(wk.counts, 0, nbk * 4, st));
         if (pl.glv)
-            k_digits<true><<<dig_blocks, 256, 0, st>>>((const uint8_t*)d_scalars, n, scalar_format, check, pl.c, pl.W, pl.NB, wk.counts,
-                                                       wk.digits, wk.status);
+            k_digits<true, false><<<dig_blocks, 256, 0, st>>>((const uint8_t*)d_scalars, n, scalar_format, check, pl.c, pl.W, pl.NB, wk.counts,
+                                                              wk.digits, wk.status, 0, 0);
         else
-            k_digits<false><<<dig_blocks, 256, 0, st>>>((const uint8_t*)d_scalars, n, scalar_format, check, pl.c, pl.W, pl.NB, wk.counts,
-                                                        wk.digits, wk.status);
+            k_digits<false, false><<<dig_blocks, 256, 0, st>>>((const uint8_t*)d_scalars, n, scalar_format, check, pl.c, pl.W, pl.NB, wk.counts,
+                                                               wk.digits, wk.status, 0, 0);
         SNARKV_LAUNCH_CHECK(ctx, "k_digits");
         sg.launched();
     }
@@ -657,7 +745,7 @@ static int msm_sort_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* d_scal
         SNARKV_LAUNCH_CHECK(ctx, "k_order_tasks");
         sg.launched();
     }
-    {
+    if (!pl.sort_P) {
         Stage sg(ctx, "msm_digits_scatter");
         const size_t nv = plan_virtual_terms(pl, n);
         // 8 elements per thread; at most 65535 blocks per window
@@ -707,7 +795,7 @@ static int msm_accumulate_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* 
     // ~48 on (64 at 2^22 terms, c = 17: 10.5 vs 11.8 ms; e2e 2^24 from host memory 53.1 -> 51.5 ms).
     const int mode = ctx->accumulate_mode;
     const size_t mean_load = nv / pl.NB;
-    bool affine = mode >= 2 || (mode == 0 && (mean_load >= 256 || (mean_load >= (size_t)ctx->ba_min_load && nbk >= ((size_t)1 << 19))));
+    bool affine = mode == 2 || mode == 3 || (mode == 0 && (mean_load >= 256 || (mean_load >= (size_t)ctx->ba_min_load && nbk >= ((size_t)1 << 19))));
     const size_t stride_a = (nv + pl.cap) / 2 + 2, stride_b = (stride_a + pl.cap) / 2 + 2;
     if (affine && mode == 0) {
         // the tree levels need scratch (48 B per term and window: 12 GB at 2^24 terms, 48 GB at 2^26); when that does not fit
@@ -717,10 +805,37 @@ static int msm_accumulate_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* 
         size_t free_b = 0, total_b = 0;
         if (need > held && (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || need + need / 8 + ((size_t)2 << 30) > free_b + held)) affine = false;
     }
-    if (!affine || mode == 3) {
+    // mode 4 (and the automatic choice once measured): chained batched-affine kernel (bucket_chain.cuh) — no scratch regions
+    const bool chain = mode == 4 || mode == 5 || (mode == 0 && ctx->bc_auto && mean_load >= (size_t)ctx->bc_min_load);
+    if (chain) {
+        Stage sg(ctx, "msm_bucket_accumulate_chain");
+        const int R = ctx->bc_r;
+        auto kernel = R == 8 ? k_bucket_accumulate_chain<8> : R == 12 ? k_bucket_accumulate_chain<12> : k_bucket_accumulate_chain<16>;
+        const size_t smem = (size_t)(SNARKV_BC_THREADS / 32) * R * 1024;
+        if (ctx->bc_blocks_per_sm == 0 || ctx->bc_blocks_r != R) {
+            SNARKV_CUDA_TRY(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int per_sm = 0;
+            SNARKV_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SNARKV_BC_THREADS, smem));
+            ctx->bc_blocks_per_sm = per_sm > 0 ? per_sm : 1;
+            ctx->bc_blocks_r = R;
+        }
+        const uint32_t units = ((pl.cap + 31) / 32) * pl.W * (uint32_t)B;   // 32 tasks each
+        uint32_t blocks = (uint32_t)(ctx->sm_count * ctx->bc_blocks_per_sm);
+        if (blocks > (units + 3) / 4) blocks = (units + 3) / 4;
+        uint4* slab = (uint4*)ctx->wsget(WS_BC_SLAB, (size_t)ctx->sm_count * ctx->bc_blocks_per_sm * (SNARKV_BC_THREADS / 32) * R * 2048);
+        uint32_t* ctr = (uint32_t*)ctx->wsget(WS_BA_COUNTER, 32);
+        if (!slab || !ctr) return SNARKV_ERR_CUDA;
+        SNARKV_CUDA_TRY(ctx, cudaMemsetAsync(ctr, 0, 32, st));
+        kernel<<<blocks, SNARKV_BC_THREADS, smem, st>>>(pts[0], pts[1], wk.sorted, wk.offsets, wk.counts, wk.tasks, wk.window_tasks, wk.order, nv,
+                                                        pl.NB, pl.T, pl.cap, pl.W, (uint32_t)B, wk.task_out, slab, ctr);
+        SNARKV_LAUNCH_CHECK(ctx, "k_bucket_accumulate_chain");
+        sg.launched();
+        affine = false;
+    }
+    if ((!affine && !chain) || mode == 3 || mode == 5) {
         Stage sg(ctx, "msm_bucket_accumulate");
         uint8_t* dst = wk.task_out;
-        if (mode == 3) {
+        if (mode == 3 || mode == 5) {
             dst = (uint8_t*)ctx->wsget(WS_TASK_OUT_CHECK, (size_t)B * pl.W * pl.cap * 128);
             if (!dst) return SNARKV_ERR_CUDA;
         }
@@ -753,21 +868,23 @@ static int msm_accumulate_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* 
                                                                         (uint32_t)ctx->ba_pairs_min, (uint32_t)ctx->ba_q);
         SNARKV_LAUNCH_CHECK(ctx, "k_bucket_accumulate_affine");
         sg.launched();
-        if (mode == 3) {   // debugging aid: both kernels ran; compare every task result as a group element (synchronous)
-            dim3 grid((pl.cap + 127) / 128, pl.W, B);
-            k_compare_task_results<<<grid, 128, 0, st>>>(wk.task_out, (const uint8_t*)ctx->ws[WS_TASK_OUT_CHECK], wk.window_tasks, wk.order, pl.cap,
-                                                        pl.W, ctr + 1);
-            SNARKV_LAUNCH_CHECK(ctx, "k_compare_task_results");
-            sg.launched();
-            uint32_t rec[4] = {};
-            SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(rec, ctr + 1, 16, cudaMemcpyDeviceToHost, st));
-            SNARKV_CUDA_TRY(ctx, cudaStreamSynchronize(st));
-            if (rec[0] != 0) {
-                char msg[160];
-                snprintf(msg, sizeof msg, "batched-affine self-check: %u task result(s) differ from the XYZZ kernel; first: window %u, slot %u, set %u",
-                         rec[0], rec[1], rec[2], rec[3]);
-                return ctx->fail(SNARKV_ERR_CUDA, msg);
-            }
+    }
+    if (mode == 3 || mode == 5) {   // debugging aid: both kernels ran; compare every task result as a group element (synchronous)
+        Stage sg(ctx, "msm_bucket_accumulate_check");
+        uint32_t* ctr = (uint32_t*)ctx->ws[WS_BA_COUNTER];
+        dim3 grid((pl.cap + 127) / 128, pl.W, B);
+        k_compare_task_results<<<grid, 128, 0, st>>>(wk.task_out, (const uint8_t*)ctx->ws[WS_TASK_OUT_CHECK], wk.window_tasks, wk.order, pl.cap,
+                                                    pl.W, ctr + 1);
+        SNARKV_LAUNCH_CHECK(ctx, "k_compare_task_results");
+        sg.launched();
+        uint32_t rec[4] = {};
+        SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(rec, ctr + 1, 16, cudaMemcpyDeviceToHost, st));
+        SNARKV_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        if (rec[0] != 0) {
+            char msg[160];
+            snprintf(msg, sizeof msg, "batched-affine self-check: %u task result(s) differ from the XYZZ kernel; first: window %u, slot %u, set %u",
+                     rec[0], rec[1], rec[2], rec[3]);
+            return ctx->fail(SNARKV_ERR_CUDA, msg);
         }
     }
     {

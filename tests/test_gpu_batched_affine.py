@@ -1,6 +1,6 @@
-"""GPU parity of the batched-affine bucket accumulation (csrc/bucket_affine.cuh) — accumulate mode 2 forces it at every size,
-mode 3 additionally runs the XYZZ kernel and compares every task result on the device (the library reports the first differing
-task).  Same oracle / checksum bar as tests/test_gpu_parity.py: bit-exact."""
+"""GPU parity of the batched-affine bucket accumulation kernels — the tree kernel (csrc/bucket_affine.cuh, accumulate mode 2) and
+the chained kernel (csrc/bucket_chain.cuh, mode 4) forced at every size; modes 3 / 5 additionally run the XYZZ kernel and compare
+every task result on the device (the library reports the first differing task).  Same oracle / checksum bar as tests/test_gpu_parity.py: bit-exact."""
 import numpy as np
 import pytest
 
@@ -19,7 +19,7 @@ def loader():
     L.close()
 
 
-@pytest.fixture(params=[2, 3], ids=["affine", "affine_selfcheck"])
+@pytest.fixture(params=[2, 3, 4, 5], ids=["affine", "affine_selfcheck", "chain", "chain_selfcheck"])
 def mode(request, loader):
     loader.set_accumulate_mode(request.param)
     yield request.param
@@ -129,7 +129,7 @@ def test_headline_size_device_and_host_paths_checksum():
         L.profile(True)
         L.msm_device(ds.data_ptr(), dp.data_ptr(), n, d_out_affine=out.data_ptr())
         torch.cuda.synchronize()
-        assert any(name == "msm_bucket_accumulate_affine" for name, _, _ in L.stage_times())
+        assert any(name in ("msm_bucket_accumulate_affine", "msm_bucket_accumulate_chain") for name, _, _ in L.stage_times())
         L.profile(False)
         hs, hp = ds.cpu().numpy(), dp.cpu().numpy()
         exp = oracle.msm_expected_from_dlogs(hs, oracle.synth_point_scalars(91, 0, n), n)
@@ -139,10 +139,11 @@ def test_headline_size_device_and_host_paths_checksum():
         L.close()
 
 
-def test_heavily_skewed_large(loader):
+@pytest.mark.parametrize("big_mode", [2, 4], ids=["affine", "chain"])
+def test_heavily_skewed_large(loader, big_mode):
     """2^20 terms with scalar 1: one bucket holds every term -> thousands of full-length tasks, all levels of the tree."""
     import torch
-    loader.set_accumulate_mode(2)
+    loader.set_accumulate_mode(big_mode)
     try:
         n = 1 << 20
         dp = torch.empty(n * 64, dtype=torch.uint8, device="cuda")
@@ -154,3 +155,19 @@ def test_heavily_skewed_large(loader):
         assert loader.msm(s, pts, n) == oracle.msm_expected_from_dlogs(s, t, n)
     finally:
         loader.set_accumulate_mode(0)
+
+
+@pytest.mark.parametrize("r", [8, 12, 16])
+def test_chain_kernel_every_chain_count(r, monkeypatch):
+    """SNARKV_BC_R selects the number of running sums per lane (the template instances of k_bucket_accumulate_chain)."""
+    monkeypatch.setenv("SNARKV_BC_R", str(r))
+    L = sv.CudaLoader(0)
+    try:
+        L.set_accumulate_mode(5)
+        for n, c in ((3000, 4), (3000, 7), (1 << 14, 0), (50, 2)):
+            s = oracle.synth_scalars(36, 0, n)
+            p = oracle.synth_points(36, 0, n, 8)
+            L.set_window_bits(c)
+            assert L.msm(s, p, n) == oracle.msm_pippenger(s, p, n, 8), (r, n, c)
+    finally:
+        L.close()
