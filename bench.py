@@ -86,10 +86,11 @@ def per_kernel_hbm(stages, n, windows, hbm_peak, cap, acc_ms):
         if ms:
             gbs = bytes_per_term * n / (ms / 1e3) / 1e9
             rows.append({"kernel": kernel, "ms": ms, "algorithmic_bytes_per_term": bytes_per_term, "achieved_gbs": gbs, "frac": gbs / hbm_peak, "what": what})
-    row("k_digits", "msm_digits_count", 32 + 4 * windows, "scalar read once, one 4-byte signed digit per window written (+ histogram atomics in L2)")
-    row("k_scatter", "msm_digits_scatter", 8 * windows, "digits read, 4-byte term references written at random inside one window's L2-resident region")
-    row("k_sort_partition", "msm_sort_partition", 32 + 8 * windows, "scalar read once, one 8-byte (digit, term) record per window written into its coarse partition")
-    row("k_sort_buckets", "msm_sort_buckets", 12 * windows, "8-byte records read, 4-byte term references written into their bucket runs (+ bucket counts)")
+    row("k_digits", "msm_digits_count", 32 + 4 * windows, "small inputs: scalar read once, one 4-byte signed digit per window written (+ histogram atomics in L2)")
+    row("k_scatter", "msm_digits_scatter", 8 * windows, "small inputs: digits read, 4-byte term references written at random inside one window's L2-resident region")
+    row("k_digits<part>", "msm_digits", 32 + 4 * windows, "scalar read once, one 4-byte signed digit per window written; coarse-partition histogram in shared memory")
+    row("k_partition", "msm_sort_partition", 10 * windows, "4-byte digits read, one 6-byte (term reference, low digit bits) record per window written into its coarse partition")
+    row("k_sort_buckets", "msm_sort_buckets", 10 * windows, "6-byte records read, 4-byte term references written into their bucket runs (+ bucket counts)")
     row("k_points_prepare", "msm_points_prepare", 128, "canonical affine points read, Montgomery copy written")
     if cap:
         gbs = cap["dram_bytes_per_launch"] / (acc_ms / 1e3) / 1e9
