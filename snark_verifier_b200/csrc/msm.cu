@@ -981,7 +981,9 @@ int msm_run_host(snarkv_ctx* ctx, const uint8_t* scalars, const uint8_t* points,
     cudaStream_t st = ctx->stream;
     // measured: below 2^22 terms the per-chunk fixed costs (scan, merges, launches) eat the copy/compute overlap (2^21: 12.1 ms
     // chunked vs 11.9 ms in one pass), so smaller inputs keep the single-pass path
-    const int K = n >= ((size_t)1 << 22) ? ctx->host_chunks : 1;
+    // (SNARKV_HOST_CHUNK_MIN lowers the threshold: when several GPUs of one box copy at the same time the host side of PCIe is the
+    // bottleneck and a short pipeline pays earlier)
+    const int K = n >= ((size_t)1 << ctx->host_chunk_min_log_n) ? (n >= ((size_t)1 << 22) ? ctx->host_chunks : ctx->host_chunks_small) : 1;
     int status[SNARKV_HOST_CHUNKS_MAX] = {};
     int* d_status = (int*)(d_o + 512);
     MsmWork wk;

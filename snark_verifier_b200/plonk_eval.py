@@ -544,16 +544,12 @@ class MsmScalarProgram:
     input_layout: Dict[str, int]
 
 
-def compile_gwc19_msm_scalars(queries: Sequence[Tuple[int, int]], num_polys: int) -> MsmScalarProgram:
-    """`Gwc19::verify` (pcs/kzg/multiopen/gwc19.rs:45-82) as a program.  `queries`: (poly, shift) in protocol order; every
-    commitment is a plain base (`Msm::base`), which is what the halo2 system produces without linearization.  Per-proof input row:
-    [z | v | u | one evaluation per query, in query order]."""
-    b = ProgramBuilder()
-    lay = {"z": 0, "v": 1, "u": 2, "evals": 3, "total": 3 + len(queries)}
-    z, v, u = b.input(0), b.input(1), b.input(2)
+def gwc19_symbolic(b: ProgramBuilder, commitments, z: int, queries: Sequence[Tuple[int, int, int]], v: int, u: int, w_slot=lambda i: ("w", i)):
+    """`Gwc19::verify` (pcs/kzg/multiopen/gwc19.rs:45-82) over builder values.  `commitments`: list of SymbolicMsm (or a callable
+    returning it — evaluated where the reference first touches the commitments, which fixes the instruction order); `queries`:
+    (poly, shift constant, evaluation VALUE) in protocol order.  -> (lhs, rhs) SymbolicMsm"""
     sets = []                                                           # gwc19.rs:140-160
-    for k, (poly, shift) in enumerate(queries):
-        ev = b.input(lay["evals"] + k)
+    for poly, shift, ev in queries:
         for st in sets:
             if st["shift"] == shift:
                 st["polys"].append(poly); st["evals"].append(ev)
@@ -562,7 +558,8 @@ def compile_gwc19_msm_scalars(queries: Sequence[Tuple[int, int]], num_polys: int
             sets.append({"shift": shift, "polys": [poly], "evals": [ev]})
     powers_of_u = _powers(b, u, len(sets))
     powers_of_v = _powers(b, v, max(len(st["polys"]) for st in sets))
-    commitments = [SymbolicMsm.base(b, ("c", j)) for j in range(num_polys)]
+    if callable(commitments):
+        commitments = commitments()
     f = SymbolicMsm(b)
     for st, pu in zip(sets, powers_of_u):
         set_msm = SymbolicMsm(b)
@@ -570,9 +567,25 @@ def compile_gwc19_msm_scalars(queries: Sequence[Tuple[int, int]], num_polys: int
             set_msm = set_msm + (commitments[poly] - SymbolicMsm.constant_(b, ev)) * pv
         f = f + set_msm * pu
     z_omegas = [b.mul(b.const(st["shift"]), z) for st in sets]
-    rhs = [SymbolicMsm.base(b, ("w", i)) * pu for i, pu in enumerate(powers_of_u)]
+    rhs = [SymbolicMsm.base(b, w_slot(i)) * pu for i, pu in enumerate(powers_of_u)]
     lhs = f + SymbolicMsm.sum(b, [uw * zo for uw, zo in zip(rhs, z_omegas)])
-    rhs_sum = SymbolicMsm.sum(b, rhs)
+    return lhs, SymbolicMsm.sum(b, rhs)
+
+
+def gwc19_num_sets(queries) -> int:
+    """number of opening-proof points `Gwc19Proof::read` reads (gwc19.rs:103-107): one per distinct shift"""
+    return len({q[1] for q in queries})
+
+
+def compile_gwc19_msm_scalars(queries: Sequence[Tuple[int, int]], num_polys: int) -> MsmScalarProgram:
+    """`Gwc19::verify` as a program for plain commitments.  `queries`: (poly, shift) in protocol order; every
+    commitment is a plain base (`Msm::base`), which is what the halo2 system produces without linearization.  Per-proof input row:
+    [z | v | u | one evaluation per query, in query order]."""
+    b = ProgramBuilder()
+    lay = {"z": 0, "v": 1, "u": 2, "evals": 3, "total": 3 + len(queries)}
+    z, v, u = b.input(0), b.input(1), b.input(2)
+    qs = [(poly, shift, b.input(lay["evals"] + k)) for k, (poly, shift) in enumerate(queries)]
+    lhs, rhs_sum = gwc19_symbolic(b, lambda: [SymbolicMsm.base(b, ("c", j)) for j in range(num_polys)], z, qs, v, u)
     return _finish_msm_program(b, lhs, rhs_sum, lay)
 
 
@@ -592,19 +605,27 @@ def _finish_msm_program(b, lhs: SymbolicMsm, rhs: SymbolicMsm, lay) -> MsmScalar
 
 
 def compile_bdfg21_msm_scalars(queries: Sequence[Tuple[int, int]], num_polys: int) -> MsmScalarProgram:
-    """`Bdfg21::verify` (pcs/kzg/multiopen/bdfg21.rs:51-83; query sets :123-175, coefficients :177-371) as a program.  `queries`:
-    (poly, shift) in protocol order.  Per-proof input row: [z | mu | gamma | z' | one evaluation per query, in query order].
-    Opening-proof slots: ("w", 0) = W, ("w", 1) = W'.  The shift arithmetic (normalised ell', set grouping) depends only on the
-    protocol and is done here on the host; everything that depends on z, z', mu, gamma or the evaluations becomes instructions,
-    with the two rounds of `L::batch_invert` (bdfg21.rs:218-219) as two shared inversions."""
-    R = R_MODULUS
+    """`Bdfg21::verify` as a program for plain commitments.  `queries`: (poly, shift) in protocol order.  Per-proof input row:
+    [z | mu | gamma | z' | one evaluation per query, in query order].  Opening-proof slots: ("w", 0) = W, ("w", 1) = W'."""
     b = ProgramBuilder()
     lay = {"z": 0, "mu": 1, "gamma": 2, "z_prime": 3, "evals": 4, "total": 4 + len(queries)}
     z, mu, gamma, z_prime = (b.input(i) for i in range(4))
+    qs = [(poly, shift, b.input(lay["evals"] + k)) for k, (poly, shift) in enumerate(queries)]
+    lhs, rhs = bdfg21_symbolic(b, lambda: [SymbolicMsm.base(b, ("c", j)) for j in range(num_polys)], z, qs, mu, gamma, z_prime)
+    return _finish_msm_program(b, lhs, rhs, lay)
+
+
+def bdfg21_symbolic(b: ProgramBuilder, commitments, z: int, queries: Sequence[Tuple[int, int, int]], mu: int, gamma: int, z_prime: int,
+                    w_slot=lambda i: ("w", i)):
+    """`Bdfg21::verify` (pcs/kzg/multiopen/bdfg21.rs:51-83; query sets :123-175, coefficients :177-371) over builder values.
+    `queries`: (poly, shift constant, evaluation VALUE) in protocol order.  The shift arithmetic (normalised ell', set grouping)
+    depends only on the protocol and is done here on the host; everything that depends on z, z', mu, gamma or the evaluations
+    becomes instructions, with the two rounds of `L::batch_invert` (bdfg21.rs:218-219) as two shared inversions.
+    -> (lhs, rhs) SymbolicMsm"""
+    R = R_MODULUS
     # ---- query_sets (bdfg21.rs:123-175) on (poly, shift, eval register) ----
     poly_shifts = []
-    for k, (poly, shift) in enumerate(queries):
-        ev = b.input(lay["evals"] + k)
+    for poly, shift, ev in queries:
         for ps in poly_shifts:
             if ps[0] == poly:
                 if shift not in ps[1]:
@@ -675,7 +696,8 @@ def compile_bdfg21_msm_scalars(queries: Sequence[Tuple[int, int]], num_polys: in
     # ---- verify (bdfg21.rs:58-82) ----
     powers_of_mu = _powers(b, mu, max(len(st["polys"]) for st in sets))
     powers_of_gamma = _powers(b, gamma, len(sets))
-    commitments = [SymbolicMsm.base(b, ("c", j)) for j in range(num_polys)]
+    if callable(commitments):
+        commitments = commitments()
     f = SymbolicMsm(b)
     for st, co, pg in zip(sets, coeffs, powers_of_gamma):
         set_msm = SymbolicMsm(b)
@@ -688,7 +710,7 @@ def compile_bdfg21_msm_scalars(queries: Sequence[Tuple[int, int]], num_polys: in
             r_eval = b.mul(r_eval, co["r_eval_coeff"])
             set_msm = set_msm + (commitment - SymbolicMsm.constant_(b, r_eval)) * pm
         f = f + set_msm * pg
-    f = f - SymbolicMsm.base(b, ("w", 0)) * coeffs[0]["z_s"]
-    rhs = SymbolicMsm.base(b, ("w", 1))
+    f = f - SymbolicMsm.base(b, w_slot(0)) * coeffs[0]["z_s"]
+    rhs = SymbolicMsm.base(b, w_slot(1))
     lhs = f + rhs * z_prime
-    return _finish_msm_program(b, lhs, rhs, lay)
+    return lhs, rhs

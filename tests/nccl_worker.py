@@ -23,7 +23,10 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     L = sv.CudaLoader(local)
-    stream = torch.cuda.current_stream()
+    # one explicit stream for torch, NCCL and the library (as bench.py does): the legacy default stream handle is 0, which
+    # snarkv_set_stream reads as "use the context's own stream" — the library would then race with torch's fills and NCCL
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     L.set_stream(stream.cuda_stream)
     ok = True
     for n in (7, 1000, (1 << 15) + 3):
