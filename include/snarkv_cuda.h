@@ -244,6 +244,28 @@ int snarkv_multi_kzg_set_deciding_key(snarkv_multi* m, const uint8_t g1[64], con
 int snarkv_multi_kzg_decide_batch(snarkv_multi* m, const uint8_t* lhs, const uint8_t* rhs, size_t N, int format, uint8_t* accept,
                                   uint8_t* gt_out);
 
+/* ---- (next row f4) Pallas: the IPA decider and the large MSM behind it ---------------------------------------------------
+ * The reference's only in-tree consumer of a 2^k-term MSM is `IpaAs::decide` over the Pasta curves (pcs/ipa/decider.rs:47-70):
+ *     h = h_coeffs(&xi, 1)  (pcs/ipa.rs:401-417);   accept  <=>  u == util::msm::multi_scalar_multiplication(&h, &dk.g).to_affine()
+ * (util/msm.rs:259-343, the Pippenger this library restates for BN254 as well).  The same pipeline is compiled a second time over
+ * Pallas (y^2 = x^3 + 5, generator (-1, 2); csrc/msm_pasta.cu).  Byte formats as above with Fq = Pallas base field, Fr = Pallas
+ * scalar field: scalars n x 32 B, affine points n x 64 B, identity (0, 0); SNARKV_MONTGOMERY = halo2curves' in-memory limbs.
+ *   snarkv_pallas_msm / _device   Sum scalar_i * point_i over Pallas (host / device operands; `_device` like snarkv_g1_msm_device)
+ *   snarkv_pallas_h_coeffs        out[j] = scalar * prod_{bit i of j} xi[k - 1 - i], 2^k values (parity entry; decide does this on the device)
+ *   snarkv_ipa_set_deciding_key   `IpaDecidingKey::g` (decider.rs:3-16): 2^k points uploaded ONCE, validated with SNARKV_CHECK_INPUTS
+ *   snarkv_ipa_decide_batch       N accumulators (u: N x 64 B, xi: N x k x 32 B, SNARKV_CANONICAL) -> accept[a] = 1 iff accumulator a decides;
+ *                                 rejection is data — the glue maps it to Error::AssertionFailure("U == commit(G, h)") (decider.rs:57) */
+int snarkv_pallas_msm(snarkv_ctx* ctx, const uint8_t* scalars, const uint8_t* points, size_t n, int format, int flags, uint8_t out_affine[64]);
+int snarkv_pallas_msm_device(snarkv_ctx* ctx, const void* d_scalars, const void* d_points, size_t n, int format, int flags, void* d_out_affine,
+                             void* d_out_jacobian, void* d_status);
+int snarkv_pallas_h_coeffs(snarkv_ctx* ctx, const uint8_t* xi, size_t k, const uint8_t scalar[32], int format, uint8_t* out);
+int snarkv_ipa_set_deciding_key(snarkv_ctx* ctx, const uint8_t* g, size_t n, int format, int flags);
+int snarkv_ipa_decide_batch(snarkv_ctx* ctx, const uint8_t* u, const uint8_t* xi, size_t k, size_t N, int format, uint8_t* accept);
+/* synthetic workload and field-op parity entry over the Pallas fields (same definitions as the BN254 ones below, G = (-1, 2)) */
+int snarkv_pallas_synth_scalars_device(snarkv_ctx* ctx, uint64_t seed, uint64_t start, size_t n, int format, void* d_out);
+int snarkv_pallas_synth_points_device(snarkv_ctx* ctx, uint64_t seed, uint64_t start, size_t n, int format, void* d_out);
+int snarkv_pallas_debug_field_op(snarkv_ctx* ctx, int field, int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out);
+
 /* ---- synthetic workload (bench / tests) ----------------------------------------------------------------------------------
  * Deterministic inputs (the test suite restates the same definition independently):
  *   scalar_i: 4 x splitmix64 limbs, top limb masked to 62 bits, one conditional subtraction of r;

@@ -89,6 +89,14 @@ C_ABI = {
     "snarkv_kzg_decide_batch": (_i, [_vp, _vp, _vp, _sz, _i, _vp, _vp]),
     "snarkv_kzg_decide_all_fused": (_i, [_vp, _vp, _vp, _sz, _vp, _i, _vp, _vp, _vp]),
     "snarkv_kzg_decide_batch_device": (_i, [_vp, _vp, _vp, _sz, _i, _vp, _vp]),
+    "snarkv_pallas_msm": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp]),
+    "snarkv_pallas_msm_device": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp, _vp, _vp]),
+    "snarkv_pallas_h_coeffs": (_i, [_vp, _vp, _sz, _vp, _i, _vp]),
+    "snarkv_ipa_set_deciding_key": (_i, [_vp, _vp, _sz, _i, _i]),
+    "snarkv_ipa_decide_batch": (_i, [_vp, _vp, _vp, _sz, _sz, _i, _vp]),
+    "snarkv_pallas_synth_scalars_device": (_i, [_vp, _u64, _u64, _sz, _i, _vp]),
+    "snarkv_pallas_synth_points_device": (_i, [_vp, _u64, _u64, _sz, _i, _vp]),
+    "snarkv_pallas_debug_field_op": (_i, [_vp, _i, _i, _vp, _vp, _sz, _vp]),
     "snarkv_synth_scalars_device": (_i, [_vp, _u64, _u64, _sz, _i, _vp]),
     "snarkv_synth_points_device": (_i, [_vp, _u64, _u64, _sz, _i, _vp]),
     "snarkv_debug_field_op": (_i, [_vp, _i, _i, _vp, _vp, _sz, _vp]),

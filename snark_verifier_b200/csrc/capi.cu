@@ -128,6 +128,7 @@ void snarkv_destroy(snarkv_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     kzg_free_key(ctx);
+    if (ctx->d_ipa_g) cudaFree(ctx->d_ipa_g);
     for (int i = 0; i < WS_SLOTS; ++i)
         if (ctx->ws[i]) cudaFree(ctx->ws[i]);
     for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);

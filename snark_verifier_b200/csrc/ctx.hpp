@@ -13,13 +13,16 @@
 
 #define SNARKV_MAX_DEVICES 16   // devices of one multi-device context (one box: 8)
 
-namespace snarkv {
-
-struct StageRecord {
+// global (not in the namespace): translation units built for another curve rename the namespace (msm_pasta.cu) but share snarkv_ctx
+struct snarkv_stage_record {
     const char* name;
     cudaEvent_t start, stop;
     int launches;
 };
+
+namespace snarkv {
+
+using StageRecord = ::snarkv_stage_record;
 
 enum WsSlot : int {
     WS_POINTS_MONT = 0,   // n x 64 B   Montgomery copy of CANONICAL points
@@ -87,9 +90,13 @@ struct snarkv_ctx {
     size_t ws_bytes[snarkv::WS_SLOTS] = {};
 
     bool profiling = false;
-    std::vector<snarkv::StageRecord> stages;       // records of the call in flight / last call
+    std::vector<snarkv_stage_record> stages;       // records of the call in flight / last call
     std::vector<cudaEvent_t> event_pool;
     size_t event_next = 0;
+
+    // IPA deciding key (pcs/ipa/decider.rs:3-16): the committing key g as resident Pallas points (capi_pasta.cu)
+    void* d_ipa_g = nullptr;
+    size_t ipa_n = 0;
 
     // KZG deciding key (pairing.cu)
     bool has_key = false;

@@ -12,7 +12,18 @@
 #include <cstdint>
 
 #include "fp_inv.cuh"
+// Curve configuration of this translation unit.  The default build is BN254 (FQ = base field, FR = scalar field).  A unit that
+// defines SNARKV_CURVE_PALLAS before any include (msm_pasta.cu, which also renames the namespace) gets the same code over the
+// Pallas fields — SURVEY §8 f4: the IPA decider's MSM (pcs/ipa/decider.rs:47-55) — with y^2 = x^3 + 5 and 255-bit moduli.
+#ifdef SNARKV_CURVE_PALLAS
+#include "fp_ptx_pallas.inc"
+#define SNARKV_FIELD_BITS 255
+#define SNARKV_CURVE_B 5
+#else
 #include "fp_ptx.inc"
+#define SNARKV_FIELD_BITS 254
+#define SNARKV_CURVE_B 3
+#endif
 
 namespace snarkv {
 
@@ -144,7 +155,7 @@ template <Field F> __device__ __noinline__ Fp<F> fp_inv(const Fp<F>& a) {
         borrow = (e[i] < borrow) ? 1u : 0u;
         e[i] = t;
     }
-    for (int i = 253; i >= 0; --i) {   // both moduli are 254-bit
+    for (int i = SNARKV_FIELD_BITS - 1; i >= 0; --i) {   // BN254: 254-bit moduli, Pasta: 255-bit
         r = fp_sqr(r);
         if ((e[i >> 5] >> (i & 31)) & 1u) r = fp_mul(r, a);
     }

@@ -271,13 +271,14 @@ static __device__ __noinline__ G1Affine xyzz_to_affine_serial(const G1Xyzz& p) {
     return r;
 }
 
-// y^2 == x^3 + 3 (Montgomery-form inputs); the identity (0,0) is accepted — `CurveAffine::from_xy` semantics plus
+// y^2 == x^3 + b, b = SNARKV_CURVE_B (Montgomery-form inputs); the identity (0,0) is accepted — `CurveAffine::from_xy` semantics plus
 // halo2curves' identity encoding
 __device__ __forceinline__ bool g1_affine_is_on_curve(const G1Affine& p) {
     if (g1_affine_is_identity(p)) return true;
-    Fq three = fp_one<FQ>();
-    three = fp_add(fp_dbl(three), three);
-    Fq rhs = fp_add(fp_mul(fp_sqr(p.x), p.x), three);
+    Fq b = fp_one<FQ>();                     // the curve constant: 3 (BN254 G1) or 5 (Pallas), fp.cuh
+#pragma unroll
+    for (int k = 1; k < SNARKV_CURVE_B; ++k) b = fp_add(b, fp_one<FQ>());
+    Fq rhs = fp_add(fp_mul(fp_sqr(p.x), p.x), b);
     return fp_eq(fp_sqr(p.y), rhs);
 }
 

@@ -67,12 +67,15 @@ static int choose_window_bits(size_t n, bool glv) {
 static MsmPlan make_plan(size_t n_terms, int c_override, int glv_mode) {
     MsmPlan p;
     p.glv = (glv_mode == 1 || (glv_mode == 0 && n_terms < ((size_t)1 << 23))) ? 1u : 0u;
+#ifdef SNARKV_CURVE_PALLAS
+    p.glv = 0;   // glv.cuh holds BN254's lattice; the Pallas build runs the plain pipeline
+#endif
     const size_t n = p.glv ? 2 * n_terms : n_terms;
     int c = c_override > 0 ? c_override : choose_window_bits(n, p.glv != 0);
     if (c < 2) c = 2;
     if (c > 22) c = 22;
     p.c = (uint32_t)c;
-    p.W = ((p.glv ? 130u : 255u) + p.c - 1) / p.c;
+    p.W = ((p.glv ? 130u : (uint32_t)SNARKV_FIELD_BITS + 1u) + p.c - 1) / p.c;   // scalar bits + the signed-digit carry
     p.NB = 1u << (p.c - 1);
     // bucket-reduce segment length: each thread's chain is 2 seg additions + one small scalar multiple; short segments cut that
     // latency, long ones cut the total work (the small multiples) once there are enough buckets to fill the machine
@@ -1122,7 +1125,7 @@ __global__ void __launch_bounds__(128) k_batch_term_mul(const uint8_t* __restric
     if (check && !g1_affine_is_on_curve(p)) atomicCAS(status, 0, SNARKV_ERR_BAD_POINT);
     G1Xyzz acc = xyzz_identity();
     if (!g1_affine_is_identity(p)) {
-        for (int b = 253; b >= 0; --b) {
+        for (int b = SNARKV_FIELD_BITS - 1; b >= 0; --b) {
             acc = xyzz_dbl(acc);
             if ((s.v[b >> 5] >> (b & 31)) & 1u) xyzz_madd(acc, p.x, p.y);
         }
@@ -1375,6 +1378,9 @@ __global__ void __launch_bounds__(128) k_synth_points(uint64_t seed, uint64_t st
     const uint64_t t = splitmix64(seed * 0x100000001B3ull + 0x5151515151515151ull + start + i) | 1ull;
     Fq gx = fp_one<FQ>();
     Fq gy = fp_dbl(gx);
+#ifdef SNARKV_CURVE_PALLAS
+    gx = fp_neg(gx);      // Pallas generator (-1, 2); BN254 G1: (1, 2)
+#endif
     G1Xyzz acc = xyzz_identity();
     for (int b = 63 - __clzll((long long)t); b >= 0; --b) {
         acc = xyzz_dbl(acc);

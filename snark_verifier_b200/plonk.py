@@ -335,19 +335,23 @@ class PlonkBatchVerifier:
 
     # -- PlonkProof::read for a batch (proof.rs:52-169) -------------------------------------------------------------------
     def _streams(self, instances: Sequence[Sequence[Sequence[int]]], proofs: Sequence[bytes]) -> np.ndarray:
+        """m x (absorbed stream) bytes: [initial state | instances | proof], everything a 32-byte big-endian word"""
         tl, pr = self.tl, self.protocol
         m = len(proofs)
-        st = np.zeros((m, tl.total * 32), dtype=np.uint8)
-        head = b""
-        if tl.initial_state is not None:
-            head = (pr.transcript_initial_state % R_MODULUS).to_bytes(32, "big")
+        plen, shape = tl.proof_len(), list(pr.num_instance)
         for j, (inst, proof) in enumerate(zip(instances, proofs)):
-            if [len(col) for col in inst] != list(pr.num_instance):
+            if [len(col) for col in inst] != shape:
                 raise InvalidInstances("proof %d: instance column lengths %r != %r" % (j, [len(c) for c in inst], pr.num_instance))
-            if len(proof) != tl.proof_len():
-                raise TranscriptError("proof %d: %d bytes, the protocol's transcript reads %d" % (j, len(proof), tl.proof_len()))
-            row = head + b"".join((v % R_MODULUS).to_bytes(32, "big") for col in inst for v in col) + bytes(proof)
-            st[j] = np.frombuffer(row, dtype=np.uint8)
+            if len(proof) != plen:
+                raise TranscriptError("proof %d: %d bytes, the protocol's transcript reads %d" % (j, len(proof), plen))
+        st = np.empty((m, tl.total * 32), dtype=np.uint8)
+        if tl.initial_state is not None:
+            st[:, :32] = np.frombuffer((pr.transcript_initial_state % R_MODULUS).to_bytes(32, "big"), dtype=np.uint8)
+        n_inst = sum(shape)
+        if n_inst:
+            words = b"".join((v % R_MODULUS).to_bytes(32, "big") for inst in instances for col in inst for v in col)
+            st[:, 32 * tl.instances:32 * tl.proof_start] = np.frombuffer(words, dtype=np.uint8).reshape(m, 32 * n_inst)
+        st[:, 32 * tl.proof_start:] = np.frombuffer(b"".join(proofs), dtype=np.uint8).reshape(m, plen)
         return st
 
     def read_proofs(self, instances, proofs) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
@@ -370,14 +374,13 @@ class PlonkBatchVerifier:
 
     @staticmethod
     def _require_canonical(words_le: np.ndarray, what: str):
-        r = np.frombuffer(R_MODULUS.to_bytes(32, "little"), dtype=np.uint8)
+        """`read_scalar` (transcript/evm.rs:230-245): a scalar the proof carries must be < r"""
         flat = words_le.reshape(-1, 32)
-        # lexicographic compare from the most significant byte: value < r
-        diff = flat[:, ::-1].astype(np.int16) - r[::-1].astype(np.int16)
-        first = np.argmax(diff != 0, axis=1)
-        sign = diff[np.arange(len(flat)), first]
-        if np.any(sign >= 0) and len(flat):
-            raise TranscriptError("Invalid scalar encoding in proof (%s >= r)" % what)
+        r = R_MODULUS.to_bytes(32, "little")
+        suspects = flat[flat[:, 31] >= r[31]]                            # everything with a smaller top byte is < r
+        for row in suspects:
+            if int.from_bytes(row.tobytes(), "little") >= R_MODULUS:
+                raise TranscriptError("Invalid scalar encoding in proof (%s >= r)" % what)
 
     def _points(self, st: np.ndarray, side: str) -> np.ndarray:
         """m x n_slots x 64 B little-endian affine points for the slots of one MSM side"""
