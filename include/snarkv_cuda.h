@@ -185,6 +185,25 @@ int snarkv_fr_mul_vec(snarkv_ctx* ctx, const uint8_t* a, const uint8_t* b, size_
 int snarkv_evm_transcript_challenges(snarkv_ctx* ctx, const uint8_t* streams, size_t stream_len, const uint32_t* seg_end, size_t k, size_t m,
                                      int format, uint8_t* challenges);
 
+/* ---- (next row f2) Poseidon transcript challenges and compressed proof points for m proofs of one transcript shape --------------
+ * Replaces util/hash/poseidon.rs:117-203 (Poseidon<F, L, 5, 4> with R_F = 8, R_P = 60: the instance snark-verifier-sdk/src/halo2.rs:53-56
+ * uses) and the native PoseidonTranscript of system/halo2/transcript/halo2.rs:201-274 for a batch.
+ *   snarkv_poseidon_transcript_challenges  `elements`: m x stream_len scalar-field elements (32 B each, `format`) in the order each
+ *       proof absorbs them — common_scalar = 1 element, common_ec_point = (x mod r, y mod r); `seg_end[i]`: ELEMENT offset after which
+ *       the i-th challenge is squeezed.  Per squeeze the buffered elements are absorbed RATE at a time (a padding 1 behind the last
+ *       one, one extra permutation when their number is a multiple of RATE) and state[1] is the challenge.  `challenges`: m x k x 32 B.
+ *   snarkv_g1_decompress_batch  `C::from_bytes` (read_ec_point, halo2.rs:258-272) for n compressed bn256 G1 points: 32 B = x little-endian,
+ *       bit 255 = parity of y, bit 254 = identity flag.  `points`: n x 64 B affine in `format`; `fr_elements` (may be NULL): n x 2 x 32 B,
+ *       (x mod r, y mod r) — what common_ec_point absorbs; `valid[i]` = 0 for a non-canonical x, a point off the curve or the
+ *       identity (which the reference's transcript rejects as well, halo2.rs:226-241).
+ *   snarkv_poseidon_permute  parity entry: m states of 5 elements -> permuted states (pins the device permutation against the public
+ *       Poseidon test vectors). */
+int snarkv_poseidon_transcript_challenges(snarkv_ctx* ctx, const uint8_t* elements, size_t stream_len, const uint32_t* seg_end, size_t k, size_t m,
+                                          int format, uint8_t* challenges);
+int snarkv_g1_decompress_batch(snarkv_ctx* ctx, const uint8_t* compressed, size_t n, int format, uint8_t* points, uint8_t* fr_elements,
+                               uint8_t* valid);
+int snarkv_poseidon_permute(snarkv_ctx* ctx, const uint8_t* states, size_t m, int format, uint8_t* out);
+
 /* ---- (row a13) `LimbsEncoding<LIMBS, BITS>::from_repr` for m accumulators -----------------------------------------------------
  * Replaces pcs/kzg/accumulator.rs:57-81 (+ util/arithmetic.rs:270-282 fe_from_limbs): `limbs` = m x 4 x num_limbs x 32 B scalars in
  * `format`, per accumulator the limbs of lhs.x, lhs.y, rhs.x, rhs.y (limb i weighs 2^(limb_bits i); the SDK uses 4 x 68).

@@ -81,6 +81,9 @@ C_ABI = {
     "snarkv_fr_batch_invert": (_i, [_vp, _vp, _sz, _vp, _i]),
     "snarkv_fr_mul_vec": (_i, [_vp, _vp, _vp, _sz, _i, _vp]),
     "snarkv_evm_transcript_challenges": (_i, [_vp, _vp, _sz, _vp, _sz, _sz, _i, _vp]),
+    "snarkv_poseidon_transcript_challenges": (_i, [_vp, _vp, _sz, _vp, _sz, _sz, _i, _vp]),
+    "snarkv_g1_decompress_batch": (_i, [_vp, _vp, _sz, _i, _vp, _vp, _vp]),
+    "snarkv_poseidon_permute": (_i, [_vp, _vp, _sz, _i, _vp]),
     "snarkv_kzg_accumulators_from_limbs": (_i, [_vp, _vp, _sz, ctypes.c_uint32, ctypes.c_uint32, _i, _vp, _vp, _vp]),
     "snarkv_fr_program_eval_batch": (_i, [_vp, _vp, _sz, ctypes.c_uint32, _vp, _sz, _vp, _sz, _sz, _vp, _sz, _i, _vp]),
     "snarkv_fr_program_eval_batch_device": (_i, [_vp, _vp, _sz, ctypes.c_uint32, _vp, _sz, _vp, _sz, _sz, _vp, _sz, _i, _vp]),
@@ -311,6 +314,28 @@ class CudaLoader:
         out = ctypes.create_string_buffer(32 * k * m)
         self._check(self.lib.snarkv_evm_transcript_challenges(self.h, _addr(streams) if stream_len else None, stream_len,
                                                               ctypes.cast(se, ctypes.c_void_p), k, m, self.fmt, out), "evm_transcript")
+        return out.raw
+
+    def poseidon_transcript_challenges(self, elements, stream_len, seg_end, m):
+        """Poseidon transcript challenges (util/hash/poseidon.rs:117-203, transcript/halo2.rs:201-242) for m proofs sharing one
+        transcript shape: `elements` = m x stream_len x 32 B absorbed scalar-field elements, `seg_end` = element offsets -> m*k*32 bytes."""
+        k = len(seg_end)
+        se = (ctypes.c_uint32 * k)(*seg_end)
+        out = ctypes.create_string_buffer(32 * k * m)
+        self._check(self.lib.snarkv_poseidon_transcript_challenges(self.h, _addr(elements) if stream_len else None, stream_len,
+                                                                   ctypes.cast(se, ctypes.c_void_p), k, m, self.fmt, out), "poseidon_transcript")
+        return out.raw
+
+    def g1_decompress(self, compressed, n, want_elements=True):
+        """`C::from_bytes` for n compressed G1 points (transcript/halo2.rs:258-272) -> (points n*64 B, elements n*64 B | None, valid n bytes)"""
+        pts, valid = ctypes.create_string_buffer(64 * n), ctypes.create_string_buffer(max(n, 1))
+        el = ctypes.create_string_buffer(64 * n) if want_elements else None
+        self._check(self.lib.snarkv_g1_decompress_batch(self.h, _addr(compressed), n, self.fmt, pts, el, valid), "g1_decompress")
+        return pts.raw, (el.raw if want_elements else None), valid.raw[:n]
+
+    def poseidon_permute(self, states, m):
+        out = ctypes.create_string_buffer(32 * 5 * m)
+        self._check(self.lib.snarkv_poseidon_permute(self.h, _addr(states), m, self.fmt, out), "poseidon_permute")
         return out.raw
 
     def accumulators_from_limbs(self, limbs, m, num_limbs=4, limb_bits=68):

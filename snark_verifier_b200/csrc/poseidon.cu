@@ -1,0 +1,290 @@
+// poseidon.cu — batched Poseidon transcript challenges and compressed-point parsing.
+//
+// Replaces, for a batch of proofs that share one transcript shape (paths relative to snark-verifier/src):
+//   util/hash/poseidon.rs:117-203                 Poseidon<F, L, T, RATE>::{update, squeeze} (T = 5, RATE = 4, R_F = 8, R_P = 60:
+//                                                 what snark-verifier-sdk/src/halo2.rs:53-56 instantiates)
+//   system/halo2/transcript/halo2.rs:201-242      native PoseidonTranscript::{common_scalar, common_ec_point, squeeze_challenge}
+//   system/halo2/transcript/halo2.rs:244-274      read_scalar (32-byte little-endian repr) / read_ec_point (`C::from_bytes`, compressed)
+// A proof's transcript is the stream of scalar-field ELEMENTS it absorbs (a scalar = 1 element, a point = x mod r, y mod r) cut at
+// the squeeze points.  Fiat-Shamir is sequential inside one proof and independent across proofs: one thread per proof.
+// The permutation is the textbook one (add round constants, x^5 on all / the first word, MDS); the reference's optimised form
+// (pre-sparse / sparse matrices) computes the same function.  Constants: poseidon_consts.inc (gen_poseidon_consts.py: Grain LFSR,
+// verified against the public Poseidon test vectors at generation time).
+#include "ctx.hpp"
+#include "g1.cuh"
+#include "poseidon_consts.inc"
+
+namespace snarkv {
+
+__device__ const uint32_t POSEIDON_RC[(SNARKV_POSEIDON_RF + SNARKV_POSEIDON_RP) * SNARKV_POSEIDON_T][8] = SNARKV_POSEIDON_RC_INIT;
+__device__ const uint32_t POSEIDON_MDS[SNARKV_POSEIDON_T * SNARKV_POSEIDON_T][8] = SNARKV_POSEIDON_MDS_INIT;
+
+__device__ __forceinline__ Fr fr_const(const uint32_t (&l)[8]) {
+    Fr r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.v[i] = l[i];
+    return r;
+}
+__device__ __forceinline__ Fr fr_pow5(const Fr& x) {
+    const Fr x2 = fp_sqr(x);
+    return fp_mul(fp_sqr(x2), x);
+}
+
+// state <- Poseidon permutation(state), Montgomery form
+__device__ void poseidon_permute(Fr (&s)[SNARKV_POSEIDON_T]) {
+    constexpr int T = SNARKV_POSEIDON_T, RF = SNARKV_POSEIDON_RF, RP = SNARKV_POSEIDON_RP;
+#pragma unroll 1
+    for (int r = 0; r < RF + RP; ++r) {
+#pragma unroll
+        for (int i = 0; i < T; ++i) s[i] = fp_add(s[i], fr_const(POSEIDON_RC[r * T + i]));
+        if (r < RF / 2 || r >= RF / 2 + RP) {
+#pragma unroll
+            for (int i = 0; i < T; ++i) s[i] = fr_pow5(s[i]);
+        } else {
+            s[0] = fr_pow5(s[0]);
+        }
+        Fr n[T];
+#pragma unroll
+        for (int i = 0; i < T; ++i) {
+            Fr acc = fp_mul(fr_const(POSEIDON_MDS[i * T]), s[0]);
+#pragma unroll
+            for (int j = 1; j < T; ++j) acc = fp_add(acc, fp_mul(fr_const(POSEIDON_MDS[i * T + j]), s[j]));
+            n[i] = acc;
+        }
+#pragma unroll
+        for (int i = 0; i < T; ++i) s[i] = n[i];
+    }
+}
+
+// util/hash/poseidon.rs:46-80 + :159-173: add up to RATE inputs to state[1..], a padding 1 behind them, permute
+__device__ __forceinline__ void poseidon_absorb(Fr (&s)[SNARKV_POSEIDON_T], const uint8_t* elems, uint32_t cnt, int format) {
+    constexpr int RATE = SNARKV_POSEIDON_T - 1;
+#pragma unroll
+    for (int q = 0; q < RATE; ++q) {
+        if ((uint32_t)q < cnt) {
+            Fr e = fp_load<FR>(elems + (size_t)q * 32);
+            if (format == SNARKV_CANONICAL) e = fp_to_mont(e);
+            s[1 + q] = fp_add(s[1 + q], e);
+        } else if ((uint32_t)q == cnt) {
+            s[1 + q] = fp_add(s[1 + q], fp_one<FR>());
+        }
+    }
+    poseidon_permute(s);
+}
+
+__global__ void __launch_bounds__(64) k_poseidon_transcript(const uint8_t* __restrict__ elements, size_t stream_len, const uint32_t* __restrict__ seg_end,
+                                                            uint32_t k, size_t m, int format, uint8_t* __restrict__ out) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    constexpr uint32_t RATE = SNARKV_POSEIDON_T - 1;
+    const uint8_t* st = elements + j * stream_len * 32;
+    Fr s[SNARKV_POSEIDON_T];
+    {
+        constexpr uint32_t cap[8] = SNARKV_POSEIDON_CAPACITY;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[0].v[i] = cap[i];
+#pragma unroll
+        for (int i = 1; i < SNARKV_POSEIDON_T; ++i) s[i] = fp_zero<FR>();
+    }
+    uint32_t prev = 0;
+    for (uint32_t i = 0; i < k; ++i) {
+        const uint32_t e = seg_end[i];
+        for (uint32_t pos = prev; pos < e; pos += RATE) poseidon_absorb(s, st + (size_t)pos * 32, min(RATE, e - pos), format);
+        if ((e - prev) % RATE == 0) poseidon_absorb(s, st, 0, format);      // `exact`: one more permutation on an empty chunk
+        prev = e;
+        Fr c = s[1];
+        if (format == SNARKV_CANONICAL) c = fp_from_mont(c);
+        fp_store<FR>(out + (j * k + i) * 32, c);
+    }
+}
+
+// parity entry: m states of T elements -> permuted states
+__global__ void __launch_bounds__(64) k_poseidon_permute(const uint8_t* __restrict__ in, size_t m, int format, uint8_t* __restrict__ out) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    Fr s[SNARKV_POSEIDON_T];
+#pragma unroll
+    for (int i = 0; i < SNARKV_POSEIDON_T; ++i) {
+        s[i] = fp_load<FR>(in + (j * SNARKV_POSEIDON_T + i) * 32);
+        if (format == SNARKV_CANONICAL) s[i] = fp_to_mont(s[i]);
+    }
+    poseidon_permute(s);
+#pragma unroll
+    for (int i = 0; i < SNARKV_POSEIDON_T; ++i) {
+        Fr c = s[i];
+        if (format == SNARKV_CANONICAL) c = fp_from_mont(c);
+        fp_store<FR>(out + (j * SNARKV_POSEIDON_T + i) * 32, c);
+    }
+}
+
+// `C::from_bytes` for bn256 G1 (halo2curves): 32 bytes = x little-endian, bit 255 = parity of y, bit 254 = identity flag.
+// valid[i] = 1 iff the encoding is a canonical x with a point on the curve; the identity is reported INVALID, as the reference's
+// transcript rejects it one line later (`coordinates()` of the identity is None, halo2.rs:226-241) — so the two historical
+// layouts of the identity (all zeros / flag bit) need not be told apart.  points: affine (x, y) in `format`;
+// elements (optional): x mod r, y mod r in `format` — what common_ec_point absorbs (fe_to_fe).
+__global__ void __launch_bounds__(128) k_g1_decompress(const uint8_t* __restrict__ compressed, size_t n, int format, uint8_t* __restrict__ points,
+                                                       uint8_t* __restrict__ elements, uint8_t* __restrict__ valid) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fq x = fp_load<FQ>(compressed + i * 32);
+    const uint32_t sign = x.v[7] >> 31, ident = (x.v[7] >> 30) & 1u;
+    x.v[7] &= 0x3fffffffu;
+    bool ok = !ident && fp_is_canonical(x);
+    const Fq xc = x;
+    Fq xm = fp_to_mont(x);
+    Fq b = fp_one<FQ>();
+#pragma unroll
+    for (int k = 1; k < SNARKV_CURVE_B; ++k) b = fp_add(b, fp_one<FQ>());
+    const Fq rhs = fp_add(fp_mul(fp_sqr(xm), xm), b);
+    // y = rhs^((p + 1) / 4)  (p = 3 mod 4)
+    uint32_t e[8];
+    uint32_t carry = 1;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint64_t t = (uint64_t)fp_mod_limb<FQ>(k) + carry;
+        e[k] = (uint32_t)t;
+        carry = (uint32_t)(t >> 32);
+    }
+#pragma unroll
+    for (int k = 0; k < 7; ++k) e[k] = (e[k] >> 2) | (e[k + 1] << 30);
+    e[7] >>= 2;
+    Fq y = fp_one<FQ>();
+#pragma unroll 1
+    for (int bit = 253; bit >= 0; --bit) {
+        y = fp_sqr(y);
+        if ((e[bit >> 5] >> (bit & 31)) & 1u) y = fp_mul(y, rhs);
+    }
+    ok = ok && fp_eq(fp_sqr(y), rhs);
+    Fq yc = fp_from_mont(y);
+    if ((yc.v[0] & 1u) != sign) {
+        y = fp_neg(y);
+        yc = fp_from_mont(y);
+    }
+    ok = ok && !(fp_is_zero(yc) && sign);                        // y = 0 has no odd twin
+    if (!ok) {
+        valid[i] = 0;
+        fp_store<FQ>(points + i * 64, fp_zero<FQ>());
+        fp_store<FQ>(points + i * 64 + 32, fp_zero<FQ>());
+        if (elements) {
+            fp_store<FQ>(elements + i * 64, fp_zero<FQ>());
+            fp_store<FQ>(elements + i * 64 + 32, fp_zero<FQ>());
+        }
+        return;
+    }
+    valid[i] = 1;
+    fp_store<FQ>(points + i * 64, format == SNARKV_CANONICAL ? xc : xm);
+    fp_store<FQ>(points + i * 64 + 32, format == SNARKV_CANONICAL ? yc : y);
+    if (elements) {
+        // fe_to_fe: reduce the base-field coordinate into the scalar field (p < 2 r: one conditional subtraction)
+        Fr ex, ey;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { ex.v[k] = xc.v[k]; ey.v[k] = yc.v[k]; }
+        Fr* both[2] = {&ex, &ey};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            Fr& v = *both[h];
+            if (!fp_is_canonical(v)) {
+                uint32_t borrow = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint64_t d = (uint64_t)v.v[k] - fp_mod_limb<FR>(k) - borrow;
+                    v.v[k] = (uint32_t)d;
+                    borrow = (uint32_t)(d >> 63);
+                }
+            }
+            if (format == SNARKV_MONTGOMERY) v = fp_to_mont(v);
+        }
+        fp_store<FR>(elements + i * 64, ex);
+        fp_store<FR>(elements + i * 64 + 32, ey);
+    }
+}
+
+}  // namespace snarkv
+
+using namespace snarkv;
+
+#define QCTX_GUARD(ctx)                                                                  \
+    do {                                                                                 \
+        if (!(ctx)) return SNARKV_ERR_USAGE;                                             \
+        (ctx)->err.clear();                                                              \
+        cudaError_t _g = cudaSetDevice((ctx)->device);                                   \
+        if (_g != cudaSuccess) return (ctx)->fail(SNARKV_ERR_CUDA, "cudaSetDevice", _g); \
+    } while (0)
+static int pos_bad_format(int f) { return f != SNARKV_CANONICAL && f != SNARKV_MONTGOMERY; }
+
+extern "C" {
+
+int snarkv_poseidon_transcript_challenges(snarkv_ctx* ctx, const uint8_t* elements, size_t stream_len, const uint32_t* seg_end, size_t k, size_t m,
+                                          int format, uint8_t* challenges) {
+    QCTX_GUARD(ctx);
+    if (m == 0 || k == 0) return SNARKV_OK;
+    if (!seg_end || !challenges || (!elements && stream_len) || pos_bad_format(format))
+        return ctx->fail(SNARKV_ERR_USAGE, "snarkv_poseidon_transcript_challenges: bad argument");
+    uint32_t prev = 0;
+    for (size_t i = 0; i < k; ++i) {
+        if (seg_end[i] < prev || seg_end[i] > stream_len) return ctx->fail(SNARKV_ERR_USAGE, "seg_end must be non-decreasing element offsets within the stream");
+        prev = seg_end[i];
+    }
+    ctx->profile_begin_call();
+    uint8_t* d_st = (uint8_t*)ctx->wsget(WS_IO_A, m * stream_len * 32 + 32);
+    uint8_t* d_seg = (uint8_t*)ctx->wsget(WS_IO_C, k * 4);
+    uint8_t* d_out = (uint8_t*)ctx->wsget(WS_IO_B, m * k * 32);
+    if (!d_st || !d_seg || !d_out) return SNARKV_ERR_CUDA;
+    cudaStream_t st = ctx->stream;
+    if (stream_len) SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_st, elements, m * stream_len * 32, cudaMemcpyHostToDevice, st));
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_seg, seg_end, k * 4, cudaMemcpyHostToDevice, st));
+    {
+        Stage sg(ctx, "poseidon_transcript");
+        k_poseidon_transcript<<<(unsigned)((m + 63) / 64), 64, 0, st>>>(d_st, stream_len, (const uint32_t*)d_seg, (uint32_t)k, m, format, d_out);
+        SNARKV_LAUNCH_CHECK(ctx, "k_poseidon_transcript");
+        sg.launched();
+    }
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(challenges, d_out, m * k * 32, cudaMemcpyDeviceToHost, st));
+    SNARKV_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return SNARKV_OK;
+}
+
+int snarkv_poseidon_permute(snarkv_ctx* ctx, const uint8_t* states, size_t m, int format, uint8_t* out) {
+    QCTX_GUARD(ctx);
+    if (m == 0) return SNARKV_OK;
+    if (!states || !out || pos_bad_format(format)) return ctx->fail(SNARKV_ERR_USAGE, "snarkv_poseidon_permute: bad argument");
+    const size_t bytes = m * SNARKV_POSEIDON_T * 32;
+    uint8_t* d_in = (uint8_t*)ctx->wsget(WS_IO_A, bytes);
+    uint8_t* d_out = (uint8_t*)ctx->wsget(WS_IO_B, bytes);
+    if (!d_in || !d_out) return SNARKV_ERR_CUDA;
+    cudaStream_t st = ctx->stream;
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_in, states, bytes, cudaMemcpyHostToDevice, st));
+    k_poseidon_permute<<<(unsigned)((m + 63) / 64), 64, 0, st>>>(d_in, m, format, d_out);
+    SNARKV_LAUNCH_CHECK(ctx, "k_poseidon_permute");
+    ctx->launches++;
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, st));
+    SNARKV_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return SNARKV_OK;
+}
+
+int snarkv_g1_decompress_batch(snarkv_ctx* ctx, const uint8_t* compressed, size_t n, int format, uint8_t* points, uint8_t* fr_elements, uint8_t* valid) {
+    QCTX_GUARD(ctx);
+    if (n == 0) return SNARKV_OK;
+    if (!compressed || !points || !valid || pos_bad_format(format)) return ctx->fail(SNARKV_ERR_USAGE, "snarkv_g1_decompress_batch: bad argument");
+    ctx->profile_begin_call();
+    uint8_t* d_in = (uint8_t*)ctx->wsget(WS_IO_A, n * 32);
+    uint8_t* d_pts = (uint8_t*)ctx->wsget(WS_IO_B, n * 128);
+    uint8_t* d_valid = (uint8_t*)ctx->wsget(WS_IO_C, n);
+    if (!d_in || !d_pts || !d_valid) return SNARKV_ERR_CUDA;
+    uint8_t* d_el = fr_elements ? d_pts + n * 64 : nullptr;
+    cudaStream_t st = ctx->stream;
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_in, compressed, n * 32, cudaMemcpyHostToDevice, st));
+    {
+        Stage sg(ctx, "g1_decompress");
+        k_g1_decompress<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_in, n, format, d_pts, d_el, d_valid);
+        SNARKV_LAUNCH_CHECK(ctx, "k_g1_decompress");
+        sg.launched();
+    }
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(points, d_pts, n * 64, cudaMemcpyDeviceToHost, st));
+    if (fr_elements) SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(fr_elements, d_el, n * 64, cudaMemcpyDeviceToHost, st));
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(valid, d_valid, n, cudaMemcpyDeviceToHost, st));
+    SNARKV_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return SNARKV_OK;
+}
+
+}  // extern "C"

@@ -173,13 +173,14 @@ class TranscriptLayout:
             pos += 2
         self.total = pos
         self.proof_words = pos - self.proof_start
+        # the proof's own items in stream order: (kind, word offset).  EvmTranscript serialises a point as two 32-byte big-endian
+        # words; the Poseidon transcript reads 32-byte compressed points and 32-byte little-endian scalars (halo2.rs:244-274) but
+        # ABSORBS the same count of field elements per item, so the word offsets double as element offsets.
+        self.items = sorted([("point", o) for o in self.witnesses + self.quotients + self.ws]
+                            + [("scalar", self.evaluations + i) for i in range(len(protocol.evaluations))], key=lambda it: it[1])
 
-    def proof_len(self) -> int:
-        return 32 * self.proof_words
-
-
-def _be_words(data: bytes) -> List[int]:
-    return [int.from_bytes(data[i:i + 32], "big") for i in range(0, len(data), 32)]
+    def proof_len(self, transcript: str = "evm") -> int:
+        return 32 * (self.proof_words if transcript == "evm" else len(self.items))
 
 
 def _from_xy(x: int, y: int) -> bytes:
@@ -326,42 +327,71 @@ class PlonkBatchVerifier:
     the m accumulators (and their old accumulators) fused by a random linear combination (pcs/kzg/decider.rs:146-185) into one
     pairing check.  `kzg`: a `KzgAs` holding the deciding key; `svk_g`: the SRS generator."""
 
-    def __init__(self, loader, kzg, svk_g: bytes, protocol: PlonkProtocol, scheme: str = "gwc19", limbs: Tuple[int, int] = (4, 68)):
-        self.loader, self.kzg, self.svk_g, self.protocol, self.scheme = loader, kzg, bytes(svk_g), protocol, scheme
+    def __init__(self, loader, kzg, svk_g: bytes, protocol: PlonkProtocol, scheme: str = "gwc19", limbs: Tuple[int, int] = (4, 68),
+                 transcript: str = "evm"):
+        # transcript: Keccak `EvmTranscript` (transcript/evm.rs) | "poseidon" = PoseidonTranscript<_, _, _, 5, 4, 8, 60> (transcript/halo2.rs)
+        assert transcript in ("evm", "poseidon")
+        self.loader, self.kzg, self.svk_g, self.protocol, self.scheme, self.transcript = loader, kzg, bytes(svk_g), protocol, scheme, transcript
         self.compiled = compile_plonk_verifier(protocol, scheme)
         self.tl = self.compiled.transcript
         self.encoding = LimbsEncoding(*limbs)
         self._slots = {"lhs": self.compiled.msm.lhs_slots, "rhs": self.compiled.msm.rhs_slots}
 
     # -- PlonkProof::read for a batch (proof.rs:52-169) -------------------------------------------------------------------
-    def _streams(self, instances: Sequence[Sequence[Sequence[int]]], proofs: Sequence[bytes]) -> np.ndarray:
-        """m x (absorbed stream) bytes: [initial state | instances | proof], everything a 32-byte big-endian word"""
-        tl, pr = self.tl, self.protocol
+    def _parse(self, instances: Sequence[Sequence[Sequence[int]]], proofs: Sequence[bytes]):
+        """-> (stream handed to the transcript kernel, m x total little-endian words, point lookup: word offset -> m x 64 B affine LE).
+        EvmTranscript: the stream is [initial state | instances | proof] as 32-byte big-endian words, points are x || y in the proof.
+        Poseidon: the stream is the absorbed field ELEMENTS; the proof's compressed points are decompressed and validated on the
+        device (`C::from_bytes`), which also yields the two elements each point absorbs."""
+        tl, pr, tr = self.tl, self.protocol, self.transcript
         m = len(proofs)
-        plen, shape = tl.proof_len(), list(pr.num_instance)
+        plen, shape = tl.proof_len(tr), list(pr.num_instance)
         for j, (inst, proof) in enumerate(zip(instances, proofs)):
             if [len(col) for col in inst] != shape:
                 raise InvalidInstances("proof %d: instance column lengths %r != %r" % (j, [len(c) for c in inst], pr.num_instance))
             if len(proof) != plen:
                 raise TranscriptError("proof %d: %d bytes, the protocol's transcript reads %d" % (j, len(proof), plen))
-        st = np.empty((m, tl.total * 32), dtype=np.uint8)
+        order = "big" if tr == "evm" else "little"
+        st = np.zeros((m, tl.total, 32), dtype=np.uint8)
         if tl.initial_state is not None:
-            st[:, :32] = np.frombuffer((pr.transcript_initial_state % R_MODULUS).to_bytes(32, "big"), dtype=np.uint8)
+            st[:, 0] = np.frombuffer((pr.transcript_initial_state % R_MODULUS).to_bytes(32, order), dtype=np.uint8)
         n_inst = sum(shape)
         if n_inst:
-            words = b"".join((v % R_MODULUS).to_bytes(32, "big") for inst in instances for col in inst for v in col)
-            st[:, 32 * tl.instances:32 * tl.proof_start] = np.frombuffer(words, dtype=np.uint8).reshape(m, 32 * n_inst)
-        st[:, 32 * tl.proof_start:] = np.frombuffer(b"".join(proofs), dtype=np.uint8).reshape(m, plen)
-        return st
+            words = b"".join((v % R_MODULUS).to_bytes(32, order) for inst in instances for col in inst for v in col)
+            st[:, tl.instances:tl.proof_start] = np.frombuffer(words, dtype=np.uint8).reshape(m, n_inst, 32)
+        raw = np.frombuffer(b"".join(proofs), dtype=np.uint8).reshape(m, plen // 32, 32)
+        if tr == "evm":
+            st[:, tl.proof_start:] = raw
+            words_le = st[:, :, ::-1]
+            return st.reshape(m, -1), words_le, lambda w: np.concatenate([words_le[:, w], words_le[:, w + 1]], axis=1)
+        pt_items = [i for i, (kind, _) in enumerate(tl.items) if kind == "point"]
+        pts, els, valid = self.loader.g1_decompress(np.ascontiguousarray(raw[:, pt_items]).tobytes(), m * len(pt_items))
+        if any(v != 1 for v in valid):
+            raise TranscriptError("Invalid elliptic curve point encoding in proof")            # halo2.rs:263-268
+        pts = np.frombuffer(pts, dtype=np.uint8).reshape(m, len(pt_items), 64)
+        els = np.frombuffer(els, dtype=np.uint8).reshape(m, len(pt_items), 2, 32)
+        by_off = {}
+        for k, i in enumerate(pt_items):
+            off = tl.items[i][1]
+            st[:, off] = els[:, k, 0]
+            st[:, off + 1] = els[:, k, 1]
+            by_off[off] = pts[:, k]
+        for i, (kind, off) in enumerate(tl.items):
+            if kind == "scalar":
+                st[:, off] = raw[:, i]
+        return st.reshape(m, -1), st, lambda w: by_off[w]
 
-    def read_proofs(self, instances, proofs) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
-        """-> (input rows m x n_inputs x 32 B LE, streams, challenges as m x k x 32 B LE).  Scalars the proofs carry must be
-        canonical (`read_scalar`, transcript/evm.rs:230-245); points are validated on the device by the MSM (`from_xy`)."""
+    def read_proofs(self, instances, proofs):
+        """PlonkProof::read for the batch -> (input rows m x n_inputs x 32 B LE, point lookup, challenges m x k x 32 B LE).  Scalars
+        the proofs carry must be canonical (`read_scalar`); points are validated on the device — by the decompression kernel
+        (Poseidon transcript) or by the MSM's input check (`from_xy`, EvmTranscript)."""
         tl, lay, m = self.tl, self.compiled.layout, len(proofs)
-        st = self._streams(instances, proofs)
-        ch = self.loader.evm_transcript_challenges(st.tobytes(), tl.total * 32, [32 * e for e in tl.seg_end], m)
+        st, words, lookup = self._parse(instances, proofs)
+        if self.transcript == "evm":
+            ch = self.loader.evm_transcript_challenges(st.tobytes(), tl.total * 32, [32 * e for e in tl.seg_end], m)
+        else:
+            ch = self.loader.poseidon_transcript_challenges(st.tobytes(), tl.total, list(tl.seg_end), m)
         ch = np.frombuffer(ch, dtype=np.uint8).reshape(m, len(tl.seg_end), 32)
-        words = st.reshape(m, tl.total, 32)[:, :, ::-1]                  # big-endian words -> little-endian
         n_inst, n_chal, n_eval = lay["challenges"], tl.n_challenges, len(self.protocol.evaluations)
         rows = np.zeros((m, lay["total"], 32), dtype=np.uint8)
         rows[:, :n_inst] = words[:, tl.instances:tl.instances + n_inst]
@@ -370,7 +400,7 @@ class PlonkBatchVerifier:
         self._require_canonical(ev, "evaluation")
         rows[:, lay["evaluations"]:lay["evaluations"] + n_eval] = ev
         rows[:, lay["pcs"]:] = ch[:, n_chal + 1:]
-        return rows, st, ch
+        return rows, lookup, ch
 
     @staticmethod
     def _require_canonical(words_le: np.ndarray, what: str):
@@ -382,10 +412,9 @@ class PlonkBatchVerifier:
             if int.from_bytes(row.tobytes(), "little") >= R_MODULUS:
                 raise TranscriptError("Invalid scalar encoding in proof (%s >= r)" % what)
 
-    def _points(self, st: np.ndarray, side: str) -> np.ndarray:
+    def _points(self, lookup, m: int, side: str) -> np.ndarray:
         """m x n_slots x 64 B little-endian affine points for the slots of one MSM side"""
-        tl, m = self.tl, st.shape[0]
-        words = st.reshape(m, tl.total, 32)[:, :, ::-1]
+        tl = self.tl
         slots = self._slots[side]
         out = np.zeros((m, len(slots), 64), dtype=np.uint8)
         for k, s in enumerate(slots):
@@ -394,9 +423,7 @@ class PlonkBatchVerifier:
             elif s[0] == "pre":
                 out[:, k] = np.frombuffer(self.protocol.preprocessed[s[1]], dtype=np.uint8)
             else:
-                w = {"wit": tl.witnesses, "quot": tl.quotients, "w": tl.ws}[s[0]][s[1]]
-                out[:, k, :32] = words[:, w]
-                out[:, k, 32:] = words[:, w + 1]
+                out[:, k] = lookup({"wit": tl.witnesses, "quot": tl.quotients, "w": tl.ws}[s[0]][s[1]])
         return out
 
     def old_accumulators(self, instances) -> List[KzgAccumulator]:
@@ -411,7 +438,7 @@ class PlonkBatchVerifier:
     def accumulate_new(self, instances, proofs, rho: int) -> KzgAccumulator:
         """sum_j rho^j (accumulator the multi-open verifier outputs for proof j): program + one fused MSM per side"""
         m = len(proofs)
-        rows, st, _ = self.read_proofs(instances, proofs)
+        rows, lookup, _ = self.read_proofs(instances, proofs)
         prog = self.compiled.msm.program
         out = self.loader.fr_program_eval(prog, rows.tobytes(), m)
         out = np.frombuffer(out, dtype=np.uint8).reshape(m, len(prog.outputs), 32)
@@ -419,7 +446,7 @@ class PlonkBatchVerifier:
         rho_b = (rho % R_MODULUS).to_bytes(32, "little")
         sides = []
         for side, sc in (("lhs", out[:, :nl]), ("rhs", out[:, nl:])):
-            pts = self._points(st, side)
+            pts = self._points(lookup, m, side)
             off = np.arange(m + 1, dtype=np.uint64) * pts.shape[1]
             sides.append(self.loader.msm_batch_rlc(np.ascontiguousarray(sc).reshape(-1), pts.reshape(-1), off, rho_b, flags=CHECK_INPUTS))
         return KzgAccumulator(sides[0], sides[1])
@@ -446,21 +473,26 @@ class PlonkBatchVerifier:
     def read_proof(self, instances, proof: bytes) -> PlonkProof:
         """PlonkProof::read for one proof, as host values (points validated with `from_xy`)"""
         tl = self.tl
-        rows, st, ch = self.read_proofs([instances], [proof])
-        w = _be_words(st[0].tobytes())
-        chal = [int.from_bytes(ch[0, i].tobytes(), "little") for i in range(ch.shape[1])]
-        pt = lambda o: _from_xy(w[o], w[o + 1])
+        rows, lookup, ch = self.read_proofs([instances], [proof])
+        lay = self.compiled.layout
+        val = lambda a: int.from_bytes(a.tobytes(), "little")
+        chal = [val(ch[0, i]) for i in range(ch.shape[1])]
+
+        def pt(o):
+            b = lookup(o)[0].tobytes()
+            return _from_xy(int.from_bytes(b[:32], "little"), int.from_bytes(b[32:], "little"))
+        evals = [val(rows[0, lay["evaluations"] + i]) for i in range(len(self.protocol.evaluations))]
         return PlonkProof([pt(o) for o in tl.witnesses], chal[:tl.n_challenges], [pt(o) for o in tl.quotients], chal[tl.n_challenges],
-                          w[tl.evaluations:tl.evaluations + len(self.protocol.evaluations)], chal[tl.n_challenges + 1:],
-                          [pt(o) for o in tl.ws], self.old_accumulators([instances]))
+                          evals, chal[tl.n_challenges + 1:], [pt(o) for o in tl.ws], self.old_accumulators([instances]))
 
 
 class PlonkVerifier:
     """verifier/plonk.rs:96-134: `verify(vk, protocol, instances, proof)` = succinct verification + `decide_all`; raises
     `AssertionFailure("e(lhs, g2)·e(rhs, -s_g2) == O")` like the reference returns it."""
 
-    def __init__(self, loader, kzg, svk_g: bytes, protocol: PlonkProtocol, scheme: str = "gwc19", limbs: Tuple[int, int] = (4, 68)):
-        self.batch = PlonkBatchVerifier(loader, kzg, svk_g, protocol, scheme, limbs)
+    def __init__(self, loader, kzg, svk_g: bytes, protocol: PlonkProtocol, scheme: str = "gwc19", limbs: Tuple[int, int] = (4, 68),
+                 transcript: str = "evm"):
+        self.batch = PlonkBatchVerifier(loader, kzg, svk_g, protocol, scheme, limbs, transcript)
 
     def read_proof(self, instances, proof: bytes) -> PlonkProof:
         return self.batch.read_proof(instances, proof)

@@ -16,6 +16,7 @@ import random
 import oracle
 from oracle import bn254_model as m
 from oracle.evm_transcript import EvmTranscript
+from oracle.poseidon_model import PoseidonTranscript
 from snark_verifier_b200 import pcs
 from snark_verifier_b200.plonk import MINUS_VANISHING_TIMES_QUOTIENT, WITHOUT_CONSTANT, PlonkProtocol, TranscriptLayout, simple_plonk_protocol
 from snark_verifier_b200.plonk_eval import Domain, Query, Rotation
@@ -89,19 +90,28 @@ def make_protocol(circ: Circuit, srs: Srs, variant=None, initial_state=0xC0DE, a
     return simple_plonk_protocol(circ.k, [srs.commit(f) for f in circ.fixed], len(circ.public), variant, initial_state, accumulator_indices)
 
 
-def prove(circ: Circuit, protocol: PlonkProtocol, srs: Srs, scheme="gwc19", tamper=None) -> bytes:
-    """Writes the proof exactly in the order PlonkProof::read consumes it.  `tamper`: None | "evaluation" | "witness" | "opening"."""
+def compress(pt: bytes) -> bytes:
+    """bn256 G1 `to_bytes` (halo2curves): x little-endian, bit 255 = parity of y (a proof never carries the identity)"""
+    x, y = xy(pt)
+    return (x | ((y & 1) << 255)).to_bytes(32, "little")
+
+
+def prove(circ: Circuit, protocol: PlonkProtocol, srs: Srs, scheme="gwc19", tamper=None, transcript="evm") -> bytes:
+    """Writes the proof exactly in the order PlonkProof::read consumes it.  `tamper`: None | "evaluation" | "witness" | "opening".
+    `transcript`: "evm" (Keccak EvmTranscript: 32-byte big-endian words, uncompressed points) | "poseidon" (PoseidonTranscript:
+    little-endian scalars, compressed points; system/halo2/transcript/halo2.rs:276-330)."""
     n, variant = circ.n, protocol.linearization
-    tr, out = EvmTranscript(), bytearray()
+    evm = transcript == "evm"
+    tr, out = (EvmTranscript() if evm else PoseidonTranscript()), bytearray()
 
     def write_point(pt):
         x, y = xy(pt)
         tr.common_ec_point(x, y)
-        out.extend(x.to_bytes(32, "big") + y.to_bytes(32, "big"))
+        out.extend(x.to_bytes(32, "big") + y.to_bytes(32, "big") if evm else compress(pt))
 
     def write_scalar(v):
         tr.common_scalar(v)
-        out.extend((v % R).to_bytes(32, "big"))
+        out.extend((v % R).to_bytes(32, "big" if evm else "little"))
 
     if protocol.transcript_initial_state is not None:
         tr.common_scalar(protocol.transcript_initial_state)
@@ -184,5 +194,5 @@ def prove(circ: Circuit, protocol: PlonkProtocol, srs: Srs, scheme="gwc19", tamp
             scale = coeff * zs1 % R * pow(p_eval(zs, z_prime), -1, R) % R
             big_l = p_add(big_l, p_scale(p_add(polys[poly], [(-p_eval(r_int, z_prime)) % R]), scale))
         write_point(srs.commit(p_divexact(big_l, [(-z_prime) % R, 1])))
-    assert len(out) == TranscriptLayout(protocol, scheme).proof_len()
+    assert len(out) == TranscriptLayout(protocol, scheme).proof_len(transcript)
     return bytes(out)

@@ -14,6 +14,7 @@ import oracle
 import snark_verifier_b200 as sv
 from oracle import bn254_model as m
 from oracle import evm_transcript as et
+from oracle import poseidon_model as pos
 from oracle.plonk_eval_model import run_program
 from snark_verifier_b200 import pcs, plonk
 from snark_verifier_b200.plonk import MINUS_VANISHING_TIMES_QUOTIENT, WITHOUT_CONSTANT
@@ -35,6 +36,28 @@ class OracleLoader:
         for j in range(mm):
             out += b"".join(le(c) for c in et.challenges_for_stream(streams[j * stream_len:(j + 1) * stream_len], seg_end))
         return out
+
+    def poseidon_transcript_challenges(self, elements, stream_len, seg_end, mm):
+        out = b""
+        for j in range(mm):
+            el = [int.from_bytes(elements[32 * (j * stream_len + i):32 * (j * stream_len + i + 1)], "little") for i in range(stream_len)]
+            out += b"".join(le(c) for c in pos.challenges_for_elements(el, seg_end))
+        return out
+
+    def g1_decompress(self, compressed, n, want_elements=True):
+        pts, els, valid = b"", b"", b""
+        for i in range(n):
+            v = int.from_bytes(compressed[32 * i:32 * i + 32], "little")
+            sign, ident, x = v >> 255, (v >> 254) & 1, v & ((1 << 254) - 1)
+            y = pow((x * x * x + 3) % m.P, (m.P + 1) // 4, m.P)
+            ok = not ident and x < m.P and y * y % m.P == (x * x * x + 3) % m.P
+            if ok and (y & 1) != sign:
+                y = (-y) % m.P
+            if not ok:
+                pts, els, valid = pts + bytes(64), els + bytes(64), valid + b"\x00"
+            else:
+                pts, els, valid = pts + le(x) + le(y), els + le(x % R) + le(y % R), valid + b"\x01"
+        return pts, els, valid
 
     def fr_program_eval(self, program, inputs, mm):
         out = b""
@@ -86,8 +109,8 @@ def circuit():
     return T.Circuit(4, 11, [5, 7])
 
 
-def cpu_verifier(srs, protocol, scheme):
-    return plonk.PlonkVerifier(OracleLoader(), OracleKzg(srs), T.GEN, protocol, scheme)
+def cpu_verifier(srs, protocol, scheme, transcript="evm"):
+    return plonk.PlonkVerifier(OracleLoader(), OracleKzg(srs), T.GEN, protocol, scheme, transcript=transcript)
 
 
 # ---- CPU ------------------------------------------------------------------------------------------------------------------------
@@ -106,6 +129,34 @@ def test_honest_proof_accepts_and_every_tampering_rejects(srs, circuit, variant,
     other = T.make_protocol(circuit, srs, variant, initial_state=0xBEEF)
     with pytest.raises(sv.AssertionFailure):                   # another transcript initial state (proof.rs:65-67)
         cpu_verifier(srs, other, scheme).verify(inst, T.prove(circuit, protocol, srs, scheme))
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+@pytest.mark.parametrize("variant", [None, WITHOUT_CONSTANT], ids=["no_linearization", "without_constant"])
+def test_poseidon_transcript_proofs_accept_and_reject(srs, circuit, variant, scheme):
+    """The same protocol over the native PoseidonTranscript (transcript/halo2.rs:201-274): compressed points, little-endian scalars."""
+    protocol = T.make_protocol(circuit, srs, variant)
+    v = cpu_verifier(srs, protocol, scheme, "poseidon")
+    inst = [circuit.public]
+    proof = T.prove(circuit, protocol, srs, scheme, transcript="poseidon")
+    assert len(proof) == 32 * len(v.batch.tl.items) < len(T.prove(circuit, protocol, srs, scheme))
+    v.verify(inst, proof)
+    for tamper in ("evaluation", "witness", "opening"):
+        with pytest.raises(sv.AssertionFailure):
+            v.verify(inst, T.prove(circuit, protocol, srs, scheme, tamper=tamper, transcript="poseidon"))
+    with pytest.raises(sv.AssertionFailure):                   # an EVM-transcript proof's challenges do not verify under Poseidon ...
+        cpu_verifier(srs, protocol, scheme, "evm").verify(inst, T.prove(circuit, protocol, srs, scheme, tamper="evaluation"))
+    bad = bytearray(proof)
+    bad[31] |= 0x40                                            # identity flag on a witness commitment (halo2.rs:226-241 rejects it)
+    with pytest.raises(plonk.TranscriptError, match="curve point"):
+        v.verify(inst, bytes(bad))
+    bad = bytearray(proof)
+    bad[0] ^= 1                                                # x with no square root of x^3 + 3 (or another point): reject or fail the pairing
+    with pytest.raises((plonk.TranscriptError, sv.AssertionFailure)):
+        v.verify(inst, bytes(bad))
+    p = v.read_proof(inst, proof)
+    q = cpu_verifier(srs, protocol, scheme, "evm").read_proof(inst, T.prove(circuit, protocol, srs, scheme))
+    assert p.witnesses == q.witnesses and p.challenges != q.challenges          # same commitments, other Fiat-Shamir
 
 
 def test_read_proof_matches_the_prover_transcript_and_error_behaviour(srs, circuit):
@@ -247,6 +298,36 @@ def test_device_verifier_accepts_rejects_and_equals_the_cpu_stand_in(gpu, srs, c
     bad[63] ^= 1                                               # off-curve witness: the device MSM's input check reports it
     with pytest.raises(sv.Error):
         v.verify(inst, bytes(bad))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_device_verifier_over_the_poseidon_transcript(gpu, srs, circuit, scheme):
+    """compressed points parsed and validated on the device, Poseidon challenges on the device, then the same program / MSMs / pairing"""
+    L, kz = gpu
+    protocol = T.make_protocol(circuit, srs)
+    v = plonk.PlonkVerifier(L, kz, T.GEN, protocol, scheme, transcript="poseidon")
+    ref = cpu_verifier(srs, protocol, scheme, "poseidon")
+    inst = [circuit.public]
+    proof = T.prove(circuit, protocol, srs, scheme, transcript="poseidon")
+    v.verify(inst, proof)
+    rows_d, _, ch_d = v.batch.read_proofs([inst], [proof])
+    rows_c, _, ch_c = ref.batch.read_proofs([inst], [proof])
+    assert rows_d.tobytes() == rows_c.tobytes() and ch_d.tobytes() == ch_c.tobytes()
+    got, exp = v.succinct_verify(inst, proof)[0], ref.succinct_verify(inst, proof)[0]
+    assert (got.lhs, got.rhs) == (exp.lhs, exp.rhs)
+    for tamper in ("evaluation", "witness", "opening"):
+        with pytest.raises(sv.AssertionFailure):
+            v.verify(inst, T.prove(circuit, protocol, srs, scheme, tamper=tamper, transcript="poseidon"))
+    bad = bytearray(proof)
+    bad[31] |= 0x40
+    with pytest.raises(plonk.TranscriptError):
+        v.verify(inst, bytes(bad))
+    mm = 300                                                   # a fused batch with one tampered proof
+    proofs = [proof] * mm
+    assert v.batch.verify_batch([inst] * mm, proofs, 0xABCDEF0123456789) is True
+    proofs[77] = T.prove(circuit, protocol, srs, scheme, tamper="opening", transcript="poseidon")
+    assert v.batch.verify_batch([inst] * mm, proofs, 0xABCDEF0123456789) is False
 
 
 @pytest.mark.gpu
