@@ -365,7 +365,7 @@ class Aux:
         # snark_verifier_b200.plonk.PlonkBatchVerifier: Keccak transcript challenges (device) -> per-proof program compiled from the
         # PlonkProtocol: common polynomials, instance + quotient evaluation, commitments, multi-open scalars (device) -> one fused MSM per
         # side with every proof point validated (device) -> one pairing.  Sharded by proof; verdict = AND over ranks.
-        def batch_verify_plonk(scheme):
+        def batch_verify_plonk(scheme, transcript="evm"):
             def body():
                 from snark_verifier_b200 import plonk
                 with open(os.path.join(ROOT, "tests", "golden", "plonk_proofs.json")) as f:
@@ -374,9 +374,10 @@ class Aux:
                 kz2 = sv.KzgAs(L, sv.KzgDecidingKey(Hx(fx["svk_g"]), Hx(fx["g2"]), Hx(fx["s_g2"])))
                 try:
                     protocol = plonk.simple_plonk_protocol(fx["k"], [Hx(p) for p in fx["preprocessed"]], fx["num_public"], None, fx["initial_state"])
-                    bv = plonk.PlonkBatchVerifier(L, kz2, Hx(fx["svk_g"]), protocol, scheme)
-                    good = [e for e in fx[scheme] if e["valid"]]
-                    bad = [e for e in fx[scheme] if not e["valid"]][0]
+                    bv = plonk.PlonkBatchVerifier(L, kz2, Hx(fx["svk_g"]), protocol, scheme, transcript=transcript)
+                    key = scheme if transcript == "evm" else scheme + "_" + transcript
+                    good = [e for e in fx[key] if e["valid"]]
+                    bad = [e for e in fx[key] if not e["valid"]][0]
                     pick = lambda e: ([[int(v) for v in col] for col in e["instances"]], Hx(e["proof"]))
                     mine = [pick(good[j % len(good)]) for j in my_proofs]
                     insts, proofs = [x[0] for x in mine], [x[1] for x in mine]
@@ -393,15 +394,17 @@ class Aux:
                 finally:
                     kz.__init__(L, kz.dk)                                   # restore the bench's deciding key on this context
                 prog = bv.compiled.msm.program
-                return ms, ok, {"proofs": m_proofs, "scheme": scheme, "proof_bytes": len(proofs[0]) if proofs else 0,
+                return ms, ok, {"proofs": m_proofs, "scheme": scheme, "transcript": transcript, "proof_bytes": len(proofs[0]) if proofs else 0,
                                 "program_instructions": len(prog.instrs), "lhs_terms_per_proof": len(bv.compiled.msm.lhs_slots),
-                                "what": "4096 REAL proofs (8 distinct, replicated) of a hand-built PLONK protocol, from proof bytes: device Keccak "
+                                "what": "4096 REAL proofs (8 distinct, replicated) of a hand-built PLONK protocol, from proof bytes: device Keccak / Poseidon "
                                         "transcript + protocol-compiled scalar program + two fused MSMs (points validated on the device) + one "
                                         "pairing, sharded by proof; a batch with one tampered proof is rejected; wall clock incl. H2D and host "
                                         "packing"}, m_proofs, "proofs_per_s"
             return body
         self.leg("batch_verify_plonk_gwc19", batch_verify_plonk("gwc19"))
         self.leg("batch_verify_plonk_shplonk", batch_verify_plonk("bdfg21"))
+        # the SDK's configuration: SHPLONK over the Poseidon transcript (compressed points parsed + validated on the device, Poseidon challenges on the device)
+        self.leg("batch_verify_plonk_shplonk_poseidon", batch_verify_plonk("bdfg21", "poseidon"))
 
         # BASELINE config 3, "independent mode": every proof keeps its own accumulator — 4096 separate 21-term / 3-term MSMs
         # (snarkv_g1_msm_batch: the literal per-proof `Msm::evaluate`, util/msm.rs:81-98 -> native.rs:61-71) + 4096 separate pairing

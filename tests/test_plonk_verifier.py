@@ -351,31 +351,31 @@ def test_device_batch_of_256_proofs_with_old_accumulators(gpu, srs, scheme):
 
 
 # ---- committed fixture (what bench.py's "real proofs" leg replicates) -----------------------------------------------------------
-def fixture_verifier(golden, loader, kzg_factory, scheme):
+def fixture_verifier(golden, loader, kzg_factory, scheme, transcript="evm"):
     fx = golden("plonk_proofs")
     H = bytes.fromhex
     protocol = plonk.simple_plonk_protocol(fx["k"], [H(p) for p in fx["preprocessed"]], fx["num_public"], None, fx["initial_state"])
-    bv = plonk.PlonkBatchVerifier(loader, kzg_factory(H(fx["svk_g"]), H(fx["g2"]), H(fx["s_g2"])), H(fx["svk_g"]), protocol, scheme)
-    entries = [([[int(v) for v in col] for col in e["instances"]], H(e["proof"]), e["valid"]) for e in fx[scheme]]
+    bv = plonk.PlonkBatchVerifier(loader, kzg_factory(H(fx["svk_g"]), H(fx["g2"]), H(fx["s_g2"])), H(fx["svk_g"]), protocol, scheme, transcript=transcript)
+    entries = [([[int(v) for v in col] for col in e["instances"]], H(e["proof"]), e["valid"]) for e in fx[scheme if transcript == "evm" else scheme + "_" + transcript]]
     return bv, entries
 
 
-@pytest.mark.parametrize("scheme", SCHEMES)
-def test_golden_proofs_fixture_on_cpu(golden, scheme):
+@pytest.mark.parametrize("scheme,transcript", [("gwc19", "evm"), ("bdfg21", "evm"), ("bdfg21", "poseidon")])
+def test_golden_proofs_fixture_on_cpu(golden, scheme, transcript):
     class Key:
         def __init__(self, g2, s_g2):
             self.g2, self.s_g2 = g2, s_g2
-    bv, entries = fixture_verifier(golden, OracleLoader(), lambda g, g2, s_g2: OracleKzg(Key(g2, s_g2)), scheme)
+    bv, entries = fixture_verifier(golden, OracleLoader(), lambda g, g2, s_g2: OracleKzg(Key(g2, s_g2)), scheme, transcript)
     for inst, proof, valid in entries[:2] + entries[-1:]:
         assert bv.verify_batch([inst], [proof], 1) is valid
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("scheme", SCHEMES)
-def test_golden_proofs_fixture_on_device(golden, scheme):
+@pytest.mark.parametrize("scheme,transcript", [("gwc19", "evm"), ("bdfg21", "evm"), ("bdfg21", "poseidon")])
+def test_golden_proofs_fixture_on_device(golden, scheme, transcript):
     L = sv.CudaLoader(0)
     try:
-        bv, entries = fixture_verifier(golden, L, lambda g, g2, s_g2: sv.KzgAs(L, sv.KzgDecidingKey(g, g2, s_g2)), scheme)
+        bv, entries = fixture_verifier(golden, L, lambda g, g2, s_g2: sv.KzgAs(L, sv.KzgDecidingKey(g, g2, s_g2)), scheme, transcript)
         for inst, proof, valid in entries:
             assert bv.verify_batch([inst], [proof], 1) is valid
         good = [e for e in entries if e[2]]
