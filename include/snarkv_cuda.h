@@ -263,6 +263,47 @@ int snarkv_multi_kzg_set_deciding_key(snarkv_multi* m, const uint8_t g1[64], con
 int snarkv_multi_kzg_decide_batch(snarkv_multi* m, const uint8_t* lhs, const uint8_t* rhs, size_t N, int format, uint8_t* accept,
                                   uint8_t* gt_out);
 
+/* ---- BASELINE config 3 in ONE call: m proofs of one PLONK protocol, from their absorbed byte streams to the fused accumulator ------
+ * Replaces, for a batch, PlonkProof::read (verifier/plonk/proof.rs:52-169), PlonkSuccinctVerifier::verify (verifier/plonk.rs:57-93: the
+ * per-proof Fr work, as the program snark_verifier_b200.plonk.compile_plonk_verifier emits for the protocol), the two `Msm::evaluate`
+ * calls of the multi-open verifier (util/msm.rs:81-98) fused by powers of rho (pcs/kzg/decider.rs:146-185) and, with `decide`, the
+ * pairing check (decider.rs:70-82).  Everything between the upload of the streams and the 128-byte result stays in HBM: transcript
+ * challenges, parsing (32-byte big-endian words -> scalars, rejected when >= r like `read_scalar`; points validated like `from_xy`),
+ * the scalar program, one Pippenger pass per side, one pairing.
+ * `streams`: m x stream_words x 32 B = what each proof's Keccak EvmTranscript absorbs, in order: [initial state] | instances | proof.
+ * Plan description (all arrays are copied): `seg_end[i]` = WORD offset after which challenge i is squeezed; `row_src[i]` >= 0: program
+ * input i is stream word row_src[i] (`row_check[i]` = 1: it is a proof scalar and must be canonical), < 0: challenge -(row_src[i] + 1);
+ * `lhs_src` / `rhs_src`[k] >= 0: base k of that MSM is the proof point at words src, src + 1 (x, y), < 0: constant point -(src + 1) of
+ * `const_points` (canonical little-endian x || y: SRS generator, preprocessed commitments); program outputs = lhs scalars then rhs scalars.
+ * Errors: SNARKV_ERR_BAD_SCALAR / SNARKV_ERR_BAD_POINT when any proof of the batch carries an invalid encoding (Error::Transcript). */
+typedef struct snarkv_plonk_plan snarkv_plonk_plan;
+typedef struct {
+    uint32_t transcript;   /* 0 = Keccak EvmTranscript */
+    uint32_t stream_words;
+    const uint32_t* seg_end;
+    uint32_t n_challenges;
+    const snarkv_fr_instr* program;
+    size_t n_instr;
+    uint32_t n_regs;
+    const uint8_t* consts; /* n_consts x 32 B canonical little-endian */
+    size_t n_consts;
+    uint32_t n_inputs;
+    const uint32_t* out_regs;
+    uint32_t n_out;
+    const int32_t* row_src;
+    const uint8_t* row_check;
+    uint32_t n_lhs, n_rhs;
+    const int32_t* lhs_src;
+    const int32_t* rhs_src;
+    const uint8_t* const_points;
+    uint32_t n_const_points;
+} snarkv_plonk_plan_desc;
+int snarkv_plonk_plan_create(snarkv_ctx* ctx, const snarkv_plonk_plan_desc* desc, snarkv_plonk_plan** out);
+void snarkv_plonk_plan_free(snarkv_ctx* ctx, snarkv_plonk_plan* plan);
+/* -> out_lhs / out_rhs (64 B canonical, may be NULL) = sum_j rho^j (accumulator of proof j); decide != 0: accept[0] = 1 iff it decides */
+int snarkv_plonk_accumulate_batch(snarkv_ctx* ctx, snarkv_plonk_plan* plan, const uint8_t* streams, size_t m, const uint8_t rho[32], int decide,
+                                  uint8_t out_lhs[64], uint8_t out_rhs[64], uint8_t* accept);
+
 /* ---- (next row f4) Pallas: the IPA decider and the large MSM behind it ---------------------------------------------------
  * The reference's only in-tree consumer of a 2^k-term MSM is `IpaAs::decide` over the Pasta curves (pcs/ipa/decider.rs:47-70):
  *     h = h_coeffs(&xi, 1)  (pcs/ipa.rs:401-417);   accept  <=>  u == util::msm::multi_scalar_multiplication(&h, &dk.g).to_affine()

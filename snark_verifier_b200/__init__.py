@@ -41,6 +41,19 @@ class CudaError(RuntimeError):
     """CUDA extension missing / no device / runtime failure.  Never swallowed, never replaced by a CPU path."""
 
 
+class _FrInstr(ctypes.Structure):
+    _fields_ = [("op", ctypes.c_uint32), ("dst", ctypes.c_uint32), ("a", ctypes.c_uint32), ("b", ctypes.c_uint32)]
+
+
+class _PlonkPlanDesc(ctypes.Structure):
+    """snarkv_plonk_plan_desc (include/snarkv_cuda.h)"""
+    _fields_ = [("transcript", ctypes.c_uint32), ("stream_words", ctypes.c_uint32), ("seg_end", ctypes.c_void_p), ("n_challenges", ctypes.c_uint32),
+                ("program", ctypes.c_void_p), ("n_instr", ctypes.c_size_t), ("n_regs", ctypes.c_uint32), ("consts", ctypes.c_void_p),
+                ("n_consts", ctypes.c_size_t), ("n_inputs", ctypes.c_uint32), ("out_regs", ctypes.c_void_p), ("n_out", ctypes.c_uint32),
+                ("row_src", ctypes.c_void_p), ("row_check", ctypes.c_void_p), ("n_lhs", ctypes.c_uint32), ("n_rhs", ctypes.c_uint32),
+                ("lhs_src", ctypes.c_void_p), ("rhs_src", ctypes.c_void_p), ("const_points", ctypes.c_void_p), ("n_const_points", ctypes.c_uint32)]
+
+
 class _StageTime(ctypes.Structure):
     _fields_ = [("name", ctypes.c_char_p), ("ms", ctypes.c_float), ("launches", ctypes.c_int)]
 
@@ -81,6 +94,9 @@ C_ABI = {
     "snarkv_fr_batch_invert": (_i, [_vp, _vp, _sz, _vp, _i]),
     "snarkv_fr_mul_vec": (_i, [_vp, _vp, _vp, _sz, _i, _vp]),
     "snarkv_evm_transcript_challenges": (_i, [_vp, _vp, _sz, _vp, _sz, _sz, _i, _vp]),
+    "snarkv_plonk_plan_create": (_i, [_vp, ctypes.POINTER(_PlonkPlanDesc), ctypes.POINTER(_vp)]),
+    "snarkv_plonk_plan_free": (None, [_vp, _vp]),
+    "snarkv_plonk_accumulate_batch": (_i, [_vp, _vp, _vp, _sz, _vp, _i, _vp, _vp, _vp]),
     "snarkv_poseidon_transcript_challenges": (_i, [_vp, _vp, _sz, _vp, _sz, _sz, _i, _vp]),
     "snarkv_g1_decompress_batch": (_i, [_vp, _vp, _sz, _i, _vp, _vp, _vp]),
     "snarkv_poseidon_permute": (_i, [_vp, _vp, _sz, _i, _vp]),
@@ -315,6 +331,34 @@ class CudaLoader:
         self._check(self.lib.snarkv_evm_transcript_challenges(self.h, _addr(streams) if stream_len else None, stream_len,
                                                               ctypes.cast(se, ctypes.c_void_p), k, m, self.fmt, out), "evm_transcript")
         return out.raw
+
+    def plonk_plan_create(self, stream_words, seg_end, program, row_src, row_check, lhs_src, rhs_src, const_points):
+        """snarkv_plonk_plan_create: the device-resident batch pipeline for one protocol (see include/snarkv_cuda.h) -> opaque plan"""
+        import numpy as np
+        from .plonk_eval import pack_program
+        assert self.fmt == CANONICAL
+        ins, consts, outs = pack_program(program)
+        keep = [np.ascontiguousarray(ins), np.asarray(seg_end, dtype=np.uint32), np.asarray(outs, dtype=np.uint32),
+                np.asarray(row_src, dtype=np.int32), np.asarray(row_check, dtype=np.uint8), np.asarray(lhs_src, dtype=np.int32),
+                np.asarray(rhs_src, dtype=np.int32), np.frombuffer(b"".join(const_points) or bytes(64), dtype=np.uint8),
+                np.frombuffer(consts or bytes(32), dtype=np.uint8)]
+        d = _PlonkPlanDesc(0, stream_words, keep[1].ctypes.data, len(seg_end), keep[0].ctypes.data, ins.shape[0], program.n_regs,
+                           keep[8].ctypes.data, len(program.consts), program.n_inputs, keep[2].ctypes.data, len(program.outputs),
+                           keep[3].ctypes.data, keep[4].ctypes.data, len(lhs_src), len(rhs_src), keep[5].ctypes.data, keep[6].ctypes.data,
+                           keep[7].ctypes.data, len(const_points))
+        plan = ctypes.c_void_p()
+        self._check(self.lib.snarkv_plonk_plan_create(self.h, ctypes.byref(d), ctypes.byref(plan)), "plonk_plan_create")
+        return plan
+
+    def plonk_plan_free(self, plan):
+        self.lib.snarkv_plonk_plan_free(self.h, plan)
+
+    def plonk_accumulate_batch(self, plan, streams, m, rho, decide=False):
+        """-> (lhs 64 B, rhs 64 B, accept | None)"""
+        lhs, rhs, acc = ctypes.create_string_buffer(64), ctypes.create_string_buffer(64), ctypes.create_string_buffer(1)
+        self._check(self.lib.snarkv_plonk_accumulate_batch(self.h, plan, _addr(streams), m, bytes(rho), 1 if decide else 0, lhs, rhs, acc),
+                    "plonk_accumulate_batch")
+        return lhs.raw, rhs.raw, (acc.raw == b"\x01" if decide else None)
 
     def poseidon_transcript_challenges(self, elements, stream_len, seg_end, m):
         """Poseidon transcript challenges (util/hash/poseidon.rs:117-203, transcript/halo2.rs:201-242) for m proofs sharing one

@@ -336,6 +336,81 @@ class PlonkBatchVerifier:
         self.tl = self.compiled.transcript
         self.encoding = LimbsEncoding(*limbs)
         self._slots = {"lhs": self.compiled.msm.lhs_slots, "rhs": self.compiled.msm.rhs_slots}
+        self._plan = None
+        self.use_device_plan = transcript == "evm" and hasattr(loader, "plonk_plan_create")   # the fused device-resident pipeline
+
+    def close(self):
+        if self._plan is not None:
+            self.loader.plonk_plan_free(self._plan)
+            self._plan = None
+
+    # -- the whole batch in ONE device call (csrc/plonk_batch.cu): streams up, fused accumulator (and verdict) down ------------------------
+    def _device_plan(self):
+        if self._plan is None:
+            tl, lay, pr = self.tl, self.compiled.layout, self.protocol
+            n_inst, n_chal, n_eval = lay["challenges"], tl.n_challenges, len(pr.evaluations)
+            row_src = [tl.instances + i for i in range(n_inst)] + [-(c + 1) for c in range(n_chal + 1)]          # instances | challenges, z
+            row_src += [tl.evaluations + i for i in range(n_eval)] + [-(c + 1) for c in range(n_chal + 1, len(tl.seg_end))]
+            row_check = [0] * (n_inst + n_chal + 1) + [1] * n_eval + [0] * (len(tl.seg_end) - n_chal - 1)          # read_scalar: evaluations < r
+            consts, index = [], {}
+
+            def const_slot(pt):
+                if pt not in index:
+                    index[pt] = len(consts)
+                    consts.append(pt)
+                return -(index[pt] + 1)
+            src = {}
+            for side in ("lhs", "rhs"):
+                src[side] = []
+                for s in self._slots[side]:
+                    if s == ("g",):
+                        src[side].append(const_slot(self.svk_g))
+                    elif s[0] == "pre":
+                        src[side].append(const_slot(pr.preprocessed[s[1]]))
+                    else:
+                        src[side].append({"wit": tl.witnesses, "quot": tl.quotients, "w": tl.ws}[s[0]][s[1]])
+            self._plan = self.loader.plonk_plan_create(tl.total, list(tl.seg_end), self.compiled.msm.program, row_src, row_check, src["lhs"], src["rhs"], consts)
+        return self._plan
+
+    def _streams_evm(self, instances, proofs) -> np.ndarray:
+        """m x (absorbed stream) bytes for the Keccak EvmTranscript: [initial state | instances | proof] as 32-byte big-endian words"""
+        tl, pr = self.tl, self.protocol
+        m, plen, shape = len(proofs), tl.proof_len("evm"), list(pr.num_instance)
+        if isinstance(proofs, np.ndarray):
+            if proofs.shape != (m, plen):
+                raise TranscriptError("proofs: %r, the protocol's transcript reads %d bytes per proof" % (proofs.shape, plen))
+        else:
+            for j, proof in enumerate(proofs):
+                if len(proof) != plen:
+                    raise TranscriptError("proof %d: %d bytes, the protocol's transcript reads %d" % (j, len(proof), plen))
+            proofs = np.frombuffer(b"".join(proofs), dtype=np.uint8).reshape(m, plen)
+        st = np.empty((m, tl.total * 32), dtype=np.uint8)
+        if tl.initial_state is not None:
+            st[:, :32] = np.frombuffer((pr.transcript_initial_state % R_MODULUS).to_bytes(32, "big"), dtype=np.uint8)
+        n_inst = sum(shape)
+        if isinstance(instances, np.ndarray):                     # m x n_inst x 32 B big-endian words, already packed by the caller
+            if instances.shape != (m, n_inst, 32):
+                raise InvalidInstances("instances: %r, expected %r" % (instances.shape, (m, n_inst, 32)))
+            st[:, 32 * tl.instances:32 * tl.proof_start] = instances.reshape(m, -1)
+        else:
+            for j, inst in enumerate(instances):
+                if [len(col) for col in inst] != shape:
+                    raise InvalidInstances("proof %d: instance column lengths %r != %r" % (j, [len(c) for c in inst], pr.num_instance))
+            if n_inst:
+                words = b"".join((v % R_MODULUS).to_bytes(32, "big") for inst in instances for col in inst for v in col)
+                st[:, 32 * tl.instances:32 * tl.proof_start] = np.frombuffer(words, dtype=np.uint8).reshape(m, 32 * n_inst)
+        st[:, 32 * tl.proof_start:] = proofs
+        return st
+
+    def _accumulate_new_device(self, instances, proofs, rho: int, decide: bool):
+        st = self._streams_evm(instances, proofs)
+        try:
+            lhs, rhs, ok = self.loader.plonk_accumulate_batch(self._device_plan(), st, st.shape[0], (rho % R_MODULUS).to_bytes(32, "little"), decide)
+        except Error as e:
+            if "Invalid" in str(e):                                # Error::Transcript(InvalidData, ..): a scalar >= r or a point off the curve
+                raise TranscriptError(str(e)) from None
+            raise
+        return KzgAccumulator(lhs, rhs), ok
 
     # -- PlonkProof::read for a batch (proof.rs:52-169) -------------------------------------------------------------------
     def _parse(self, instances: Sequence[Sequence[Sequence[int]]], proofs: Sequence[bytes]):
@@ -437,6 +512,8 @@ class PlonkBatchVerifier:
     # -- PlonkSuccinctVerifier::verify (plonk.rs:57-93) for the batch -------------------------------------------------------
     def accumulate_new(self, instances, proofs, rho: int) -> KzgAccumulator:
         """sum_j rho^j (accumulator the multi-open verifier outputs for proof j): program + one fused MSM per side"""
+        if self.use_device_plan:
+            return self._accumulate_new_device(instances, proofs, rho, False)[0]
         m = len(proofs)
         rows, lookup, _ = self.read_proofs(instances, proofs)
         prog = self.compiled.msm.program
@@ -465,6 +542,8 @@ class PlonkBatchVerifier:
 
     def verify_batch(self, instances, proofs, rho: int) -> bool:
         """True iff the fused accumulator passes `decide` (all proofs valid, up to the soundness error of the random `rho`)"""
+        if self.use_device_plan and not self.protocol.accumulator_indices:
+            return self._accumulate_new_device(instances, proofs, rho, True)[1]
         acc = self.accumulate(instances, proofs, rho)
         ok, _ = self.kzg.decide_batch(acc.lhs, acc.rhs, 1)
         return ok == b"\x01"

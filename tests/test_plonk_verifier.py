@@ -288,7 +288,14 @@ def test_device_verifier_accepts_rejects_and_equals_the_cpu_stand_in(gpu, srs, c
     v.verify(inst, proof)
     got, exp = v.succinct_verify(inst, proof)[0], ref.succinct_verify(inst, proof)[0]
     assert (got.lhs, got.rhs) == (exp.lhs, exp.rhs)
-    rows_d, _, ch_d = v.batch.read_proofs([inst], [proof])
+    assert v.batch.use_device_plan                              # ^ the ONE-call device pipeline (csrc/plonk_batch.cu); below: step by step
+    v.batch.use_device_plan = False
+    try:
+        step = v.succinct_verify(inst, proof)[0]
+        assert (step.lhs, step.rhs) == (exp.lhs, exp.rhs)
+        rows_d, _, ch_d = v.batch.read_proofs([inst], [proof])
+    finally:
+        v.batch.use_device_plan = True
     rows_c, _, ch_c = ref.batch.read_proofs([inst], [proof])
     assert rows_d.tobytes() == rows_c.tobytes() and ch_d.tobytes() == ch_c.tobytes()
     for tamper in ("evaluation", "witness", "opening"):
@@ -296,8 +303,15 @@ def test_device_verifier_accepts_rejects_and_equals_the_cpu_stand_in(gpu, srs, c
             v.verify(inst, T.prove(circuit, protocol, srs, scheme, tamper=tamper))
     bad = bytearray(proof)
     bad[63] ^= 1                                               # off-curve witness: the device MSM's input check reports it
-    with pytest.raises(sv.Error):
+    with pytest.raises(plonk.TranscriptError, match="curve point"):
         v.verify(inst, bytes(bad))
+    tl = v.batch.tl
+    bad = bytearray(proof)
+    o = 32 * (tl.evaluations - tl.proof_start)
+    bad[o:o + 32] = R.to_bytes(32, "big")                      # an evaluation >= r: read_scalar rejects it, on the device
+    with pytest.raises(plonk.TranscriptError, match="scalar"):
+        v.verify(inst, bytes(bad))
+    v.batch.close()
 
 
 @pytest.mark.gpu
