@@ -381,6 +381,12 @@ class Aux:
                     pick = lambda e: ([[int(v) for v in col] for col in e["instances"]], Hx(e["proof"]))
                     mine = [pick(good[j % len(good)]) for j in my_proofs]
                     insts, proofs = [x[0] for x in mine], [x[1] for x in mine]
+                    order = "big" if transcript == "evm" else "little"
+                    if mine:
+                        # the wire format of a batch: proofs and instances as contiguous byte arrays (32-byte words in the transcript's byte order)
+                        proofs = np.frombuffer(b"".join(proofs), dtype=np.uint8).reshape(len(mine), -1)
+                        insts = np.frombuffer(b"".join(v.to_bytes(32, order) for inst in insts for col in inst for v in col),
+                                              dtype=np.uint8).reshape(len(mine), -1, 32)
                     rho_i = int.from_bytes(rho, "little")
                     res = {}
 
@@ -390,11 +396,18 @@ class Aux:
                     ok = res["ok"] is True
                     if mine:                                                # one tampered proof in the batch must flip the verdict
                         bi, bp = pick(bad)
-                        ok = ok and bv.verify_batch(insts[:-1] + [bi], proofs[:-1] + [bp], rho_i) is False
+                        if isinstance(proofs, np.ndarray):
+                            p2, i2 = proofs.copy(), insts.copy()
+                            p2[-1] = np.frombuffer(bp, dtype=np.uint8)
+                            i2[-1] = np.frombuffer(b"".join(v.to_bytes(32, order) for col in bi for v in col), dtype=np.uint8).reshape(-1, 32)
+                            ok = ok and bv.verify_batch(i2, p2, rho_i) is False
+                        else:
+                            ok = ok and bv.verify_batch(insts[:-1] + [bi], proofs[:-1] + [bp], rho_i) is False
                 finally:
                     kz.__init__(L, kz.dk)                                   # restore the bench's deciding key on this context
                 prog = bv.compiled.msm.program
-                return ms, ok, {"proofs": m_proofs, "scheme": scheme, "transcript": transcript, "proof_bytes": len(proofs[0]) if proofs else 0,
+                bv.close()
+                return ms, ok, {"proofs": m_proofs, "scheme": scheme, "transcript": transcript, "proof_bytes": len(proofs[0]) if len(proofs) else 0,
                                 "program_instructions": len(prog.instrs), "lhs_terms_per_proof": len(bv.compiled.msm.lhs_slots),
                                 "what": "4096 REAL proofs (8 distinct, replicated) of a hand-built PLONK protocol, from proof bytes: device Keccak / Poseidon "
                                         "transcript + protocol-compiled scalar program + two fused MSMs (points validated on the device) + one "

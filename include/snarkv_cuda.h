@@ -275,10 +275,14 @@ int snarkv_multi_kzg_decide_batch(snarkv_multi* m, const uint8_t* lhs, const uin
  * input i is stream word row_src[i] (`row_check[i]` = 1: it is a proof scalar and must be canonical), < 0: challenge -(row_src[i] + 1);
  * `lhs_src` / `rhs_src`[k] >= 0: base k of that MSM is the proof point at words src, src + 1 (x, y), < 0: constant point -(src + 1) of
  * `const_points` (canonical little-endian x || y: SRS generator, preprocessed commitments); program outputs = lhs scalars then rhs scalars.
+ * transcript = 1 (native PoseidonTranscript, system/halo2/transcript/halo2.rs:201-274): `streams` = m x (n_pre + n_items) x 32 B — per proof n_pre
+ * little-endian scalars (initial state, instances) followed by the proof's n_items 32-byte items (little-endian scalar or compressed point).  Item i is a
+ * scalar absorbed as element item_off[i] >= 0, or a point (item_off[i] = -(off + 1): its two elements go to off, off + 1; item_pt[i] = its index among
+ * the proof's n_points points).  `stream_words` / `seg_end` / `row_src` count ELEMENTS, `lhs_src` / `rhs_src` >= 0 are point indices.
  * Errors: SNARKV_ERR_BAD_SCALAR / SNARKV_ERR_BAD_POINT when any proof of the batch carries an invalid encoding (Error::Transcript). */
 typedef struct snarkv_plonk_plan snarkv_plonk_plan;
 typedef struct {
-    uint32_t transcript;   /* 0 = Keccak EvmTranscript */
+    uint32_t transcript;   /* 0 = Keccak EvmTranscript, 1 = Poseidon transcript (T = 5, RATE = 4, R_F = 8, R_P = 60) */
     uint32_t stream_words;
     const uint32_t* seg_end;
     uint32_t n_challenges;
@@ -297,6 +301,11 @@ typedef struct {
     const int32_t* rhs_src;
     const uint8_t* const_points;
     uint32_t n_const_points;
+    /* transcript 1 only (see below): leading caller-supplied elements, proof items, item table, points per proof */
+    uint32_t n_pre, n_items;
+    const int32_t* item_off;
+    const int32_t* item_pt;
+    uint32_t n_points;
 } snarkv_plonk_plan_desc;
 int snarkv_plonk_plan_create(snarkv_ctx* ctx, const snarkv_plonk_plan_desc* desc, snarkv_plonk_plan** out);
 void snarkv_plonk_plan_free(snarkv_ctx* ctx, snarkv_plonk_plan* plan);

@@ -51,7 +51,9 @@ class _PlonkPlanDesc(ctypes.Structure):
                 ("program", ctypes.c_void_p), ("n_instr", ctypes.c_size_t), ("n_regs", ctypes.c_uint32), ("consts", ctypes.c_void_p),
                 ("n_consts", ctypes.c_size_t), ("n_inputs", ctypes.c_uint32), ("out_regs", ctypes.c_void_p), ("n_out", ctypes.c_uint32),
                 ("row_src", ctypes.c_void_p), ("row_check", ctypes.c_void_p), ("n_lhs", ctypes.c_uint32), ("n_rhs", ctypes.c_uint32),
-                ("lhs_src", ctypes.c_void_p), ("rhs_src", ctypes.c_void_p), ("const_points", ctypes.c_void_p), ("n_const_points", ctypes.c_uint32)]
+                ("lhs_src", ctypes.c_void_p), ("rhs_src", ctypes.c_void_p), ("const_points", ctypes.c_void_p), ("n_const_points", ctypes.c_uint32),
+                ("n_pre", ctypes.c_uint32), ("n_items", ctypes.c_uint32), ("item_off", ctypes.c_void_p), ("item_pt", ctypes.c_void_p),
+                ("n_points", ctypes.c_uint32)]
 
 
 class _StageTime(ctypes.Structure):
@@ -332,7 +334,7 @@ class CudaLoader:
                                                               ctypes.cast(se, ctypes.c_void_p), k, m, self.fmt, out), "evm_transcript")
         return out.raw
 
-    def plonk_plan_create(self, stream_words, seg_end, program, row_src, row_check, lhs_src, rhs_src, const_points):
+    def plonk_plan_create(self, stream_words, seg_end, program, row_src, row_check, lhs_src, rhs_src, const_points, poseidon=None):
         """snarkv_plonk_plan_create: the device-resident batch pipeline for one protocol (see include/snarkv_cuda.h) -> opaque plan"""
         import numpy as np
         from .plonk_eval import pack_program
@@ -345,7 +347,12 @@ class CudaLoader:
         d = _PlonkPlanDesc(0, stream_words, keep[1].ctypes.data, len(seg_end), keep[0].ctypes.data, ins.shape[0], program.n_regs,
                            keep[8].ctypes.data, len(program.consts), program.n_inputs, keep[2].ctypes.data, len(program.outputs),
                            keep[3].ctypes.data, keep[4].ctypes.data, len(lhs_src), len(rhs_src), keep[5].ctypes.data, keep[6].ctypes.data,
-                           keep[7].ctypes.data, len(const_points))
+                           keep[7].ctypes.data, len(const_points), 0, 0, None, None, 0)
+        if poseidon is not None:                                   # (n_pre, item_off, item_pt, n_points): the Poseidon transcript's item table
+            n_pre, item_off, item_pt, n_points = poseidon
+            keep += [np.asarray(item_off, dtype=np.int32), np.asarray(item_pt, dtype=np.int32)]
+            d.transcript, d.n_pre, d.n_items, d.n_points = 1, n_pre, len(item_off), n_points
+            d.item_off, d.item_pt = keep[-2].ctypes.data, keep[-1].ctypes.data
         plan = ctypes.c_void_p()
         self._check(self.lib.snarkv_plonk_plan_create(self.h, ctypes.byref(d), ctypes.byref(plan)), "plonk_plan_create")
         return plan

@@ -209,6 +209,10 @@ int fr_mul_vec_device(snarkv_ctx* ctx, const void* d_a, const void* d_b, size_t 
 int fr_from_mont_device(snarkv_ctx* ctx, void* d_v, size_t n);
 int evm_transcript_device(snarkv_ctx* ctx, const void* d_streams, size_t stream_len, const void* d_seg_end, size_t k, size_t m, int format,
                           void* d_out);
+int poseidon_transcript_device(snarkv_ctx* ctx, const void* d_elements, size_t stream_len, const void* d_seg_end, size_t k, size_t m, int format,
+                               void* d_out);
+int plonk_poseidon_expand_device(snarkv_ctx* ctx, const void* d_proofs, uint32_t n_items, const void* d_item_off, const void* d_item_pt, uint32_t stream_len,
+                                 uint32_t n_points, size_t m, void* d_elements, void* d_points, void* d_status, uint32_t in_stride, uint32_t in_base);
 int fr_powers_device(snarkv_ctx* ctx, const void* d_r, int format, size_t n, void* d_out_mont, uint64_t first = 0);
 int field_op_device(snarkv_ctx* ctx, int field, int op, const void* d_a, const void* d_b, size_t n, void* d_out);
 int synth_scalars_device(snarkv_ctx* ctx, uint64_t seed, uint64_t start, size_t n, int format, void* d_out);

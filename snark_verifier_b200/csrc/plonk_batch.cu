@@ -17,6 +17,8 @@
 
 struct snarkv_plonk_plan {
     int device = 0;
+    uint32_t transcript = 0, n_pre = 0, n_items = 0, n_points = 0;   // Poseidon: caller-supplied leading elements, proof items, points per proof
+    int32_t *d_item_off = nullptr, *d_item_pt = nullptr;
     uint32_t stream_words = 0, n_challenges = 0, n_instr = 0, n_regs = 0, n_consts = 0, n_inputs = 0, n_out = 0, n_lhs = 0, n_rhs = 0;
     // device tables (one allocation)
     uint8_t* d_tables = nullptr;
@@ -45,7 +47,8 @@ __device__ __forceinline__ Fr load_be_word(const uint8_t* p) {
 // program input rows: rows[j][i] = the proof's word row_src[i] (little-endian) or its challenge -(row_src[i] + 1)
 __global__ void __launch_bounds__(256) k_plonk_rows(const uint8_t* __restrict__ streams, uint32_t stream_words, const uint8_t* __restrict__ challenges,
                                                     uint32_t n_challenges, const int32_t* __restrict__ row_src, const uint8_t* __restrict__ row_check,
-                                                    uint32_t n_inputs, size_t m, uint8_t* __restrict__ rows, int* __restrict__ status) {
+                                                    uint32_t n_inputs, size_t m, int little_endian, uint8_t* __restrict__ rows,
+                                                    int* __restrict__ status) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= m * n_inputs) return;
     const size_t j = t / n_inputs;
@@ -53,7 +56,8 @@ __global__ void __launch_bounds__(256) k_plonk_rows(const uint8_t* __restrict__ 
     const int32_t src = row_src[i];
     Fr v;
     if (src >= 0) {
-        v = load_be_word(streams + (j * stream_words + (uint32_t)src) * 32);
+        const uint8_t* w = streams + (j * stream_words + (uint32_t)src) * 32;
+        v = little_endian ? fp_load<FR>(w) : load_be_word(w);     // Poseidon element stream: already little-endian scalars
         if (row_check[i] && !fp_is_canonical(v)) atomicCAS(status, 0, SNARKV_ERR_BAD_SCALAR);   // read_scalar: "Invalid scalar encoding in proof"
     } else {
         v = fp_load<FR>(challenges + (j * n_challenges + (uint32_t)(-(src + 1))) * 32);
@@ -64,14 +68,19 @@ __global__ void __launch_bounds__(256) k_plonk_rows(const uint8_t* __restrict__ 
 // bases of one MSM side: pts[j][k] = constant point -(src[k] + 1) or the proof's point at words src[k], src[k] + 1; scal[j][k] = outputs[j][first + k]
 __global__ void __launch_bounds__(256) k_plonk_side(const uint8_t* __restrict__ streams, uint32_t stream_words, const uint8_t* __restrict__ const_points,
                                                     const int32_t* __restrict__ src, uint32_t n_slots, const uint8_t* __restrict__ outputs,
-                                                    uint32_t n_out, uint32_t first, size_t m, uint8_t* __restrict__ pts, uint8_t* __restrict__ scal) {
+                                                    uint32_t n_out, uint32_t first, size_t m, const uint8_t* __restrict__ parsed_points,
+                                                    uint32_t n_points, uint8_t* __restrict__ pts, uint8_t* __restrict__ scal) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= m * n_slots) return;
     const size_t j = t / n_slots;
     const uint32_t k = (uint32_t)(t - j * n_slots);
     const int32_t s = src[k];
     Fr x, y;
-    if (s >= 0) {
+    if (s >= 0 && parsed_points) {                                 // Poseidon transcript: the proof's points were decompressed into an array
+        const uint8_t* w = parsed_points + (j * n_points + (uint32_t)s) * 64;
+        x = fp_load<FR>(w);
+        y = fp_load<FR>(w + 32);
+    } else if (s >= 0) {
         const uint8_t* w = streams + (j * stream_words + (uint32_t)s) * 32;
         x = load_be_word(w);
         y = load_be_word(w + 32);
@@ -110,7 +119,19 @@ int snarkv_plonk_plan_create(snarkv_ctx* ctx, const snarkv_plonk_plan_desc* d, s
     BCTX_GUARD(ctx);
     if (!d || !out) return ctx->fail(SNARKV_ERR_USAGE, "snarkv_plonk_plan_create: bad argument");
     *out = nullptr;
-    if (d->transcript != 0) return ctx->fail(SNARKV_ERR_USAGE, "snarkv_plonk_plan_create: transcript 0 (Keccak EvmTranscript) only");
+    if (d->transcript > 1) return ctx->fail(SNARKV_ERR_USAGE, "snarkv_plonk_plan_create: transcript 0 (Keccak EvmTranscript) or 1 (Poseidon)");
+    const bool pos = d->transcript == 1;
+    if (pos && (!d->item_off || !d->item_pt || d->n_items == 0 || d->n_pre + d->n_items == 0))
+        return ctx->fail(SNARKV_ERR_USAGE, "snarkv_plonk_plan_create: the Poseidon transcript needs the proof item table");
+    if (pos) {
+        for (uint32_t i = 0; i < d->n_items; ++i) {
+            const int32_t o = d->item_off[i];
+            const uint32_t off = o >= 0 ? (uint32_t)o : (uint32_t)(-(o + 1)) + 1;
+            if (off >= d->stream_words || (o < 0 && (d->item_pt[i] < 0 || (uint32_t)d->item_pt[i] >= d->n_points)))
+                return ctx->fail(SNARKV_ERR_USAGE, "snarkv_plonk_plan_create: proof item out of range");
+        }
+        if (d->n_pre > d->stream_words) return ctx->fail(SNARKV_ERR_USAGE, "snarkv_plonk_plan_create: n_pre exceeds the stream");
+    }
     if (!d->seg_end || d->n_challenges == 0 || !d->program || d->n_instr == 0 || d->n_regs == 0 || !d->out_regs || d->n_out == 0 || !d->row_src ||
         !d->row_check || d->n_inputs == 0 || d->n_lhs + d->n_rhs != d->n_out || d->n_lhs == 0 || d->n_rhs == 0 || !d->lhs_src || !d->rhs_src ||
         (d->n_consts && !d->consts) || (d->n_const_points && !d->const_points) || d->stream_words == 0)
@@ -129,7 +150,8 @@ int snarkv_plonk_plan_create(snarkv_ctx* ctx, const snarkv_plonk_plan_desc* d, s
         const uint32_t n = side ? d->n_rhs : d->n_lhs;
         for (uint32_t k = 0; k < n; ++k) {
             const int32_t s = src[k];
-            if (s >= 0 ? (uint32_t)s + 1 >= d->stream_words : (uint32_t)(-(s + 1)) >= d->n_const_points) return ctx->fail(SNARKV_ERR_USAGE, "point source out of range");
+            if (s >= 0 ? (pos ? (uint32_t)s >= d->n_points : (uint32_t)s + 1 >= d->stream_words) : (uint32_t)(-(s + 1)) >= d->n_const_points)
+                return ctx->fail(SNARKV_ERR_USAGE, "point source out of range");
         }
     }
     // instruction validation as in snarkv_fr_program_eval_batch: opcodes, operand ranges, no read before write
@@ -154,12 +176,13 @@ int snarkv_plonk_plan_create(snarkv_ctx* ctx, const snarkv_plonk_plan_desc* d, s
     }
     snarkv_plonk_plan* p = new snarkv_plonk_plan();
     p->device = ctx->device;
+    p->transcript = d->transcript; p->n_pre = pos ? d->n_pre : 0; p->n_items = pos ? d->n_items : 0; p->n_points = pos ? d->n_points : 0;
     p->stream_words = d->stream_words; p->n_challenges = d->n_challenges; p->n_instr = (uint32_t)d->n_instr; p->n_regs = d->n_regs;
     p->n_consts = (uint32_t)d->n_consts; p->n_inputs = d->n_inputs; p->n_out = d->n_out; p->n_lhs = d->n_lhs; p->n_rhs = d->n_rhs;
     const size_t b_seg = al256(d->n_challenges * 4), b_prog = al256(d->n_instr * sizeof(snarkv_fr_instr)), b_consts = al256(d->n_consts * 32 + 32),
                  b_outr = al256(d->n_out * 4), b_rows = al256(d->n_inputs * 4), b_chk = al256(d->n_inputs), b_l = al256(d->n_lhs * 4), b_r = al256(d->n_rhs * 4),
-                 b_cp = al256(d->n_const_points * 64 + 64);
-    const size_t total = b_seg + b_prog + 2 * b_consts + b_outr + b_rows + b_chk + b_l + b_r + b_cp;
+                 b_cp = al256(d->n_const_points * 64 + 64), b_items = pos ? al256(d->n_items * 4) : 0;
+    const size_t total = 2 * b_items + b_seg + b_prog + 2 * b_consts + b_outr + b_rows + b_chk + b_l + b_r + b_cp;
     cudaError_t ce = cudaMalloc(&p->d_tables, total);
     if (ce != cudaSuccess) { delete p; return ctx->fail(SNARKV_ERR_CUDA, "cudaMalloc(plan tables)", ce); }
     std::vector<uint8_t> host(total, 0);
@@ -167,7 +190,7 @@ int snarkv_plonk_plan_create(snarkv_ctx* ctx, const snarkv_plonk_plan_desc* d, s
     auto put = [&](const void* src, size_t bytes, size_t slot) { uint8_t* dev = p->d_tables + o; if (bytes) memcpy(host.data() + o, src, bytes); o += slot; return dev; };
     {
         std::vector<uint32_t> seg_bytes(d->seg_end, d->seg_end + d->n_challenges);   // the transcript kernel cuts the stream at byte offsets
-        for (auto& e : seg_bytes) e *= 32;
+        if (!pos) for (auto& e : seg_bytes) e *= 32;             // Poseidon: element offsets as they are
         p->d_seg_end = (uint32_t*)put(seg_bytes.data(), d->n_challenges * 4, b_seg);
     }
     p->d_prog = put(d->program, d->n_instr * sizeof(snarkv_fr_instr), b_prog);
@@ -179,6 +202,10 @@ int snarkv_plonk_plan_create(snarkv_ctx* ctx, const snarkv_plonk_plan_desc* d, s
     p->d_lhs_src = (int32_t*)put(d->lhs_src, d->n_lhs * 4, b_l);
     p->d_rhs_src = (int32_t*)put(d->rhs_src, d->n_rhs * 4, b_r);
     p->d_const_points = put(d->const_points, d->n_const_points * 64, b_cp);
+    if (pos) {
+        p->d_item_off = (int32_t*)put(d->item_off, d->n_items * 4, b_items);
+        p->d_item_pt = (int32_t*)put(d->item_pt, d->n_items * 4, b_items);
+    }
     ce = cudaMemcpy(p->d_tables, host.data(), total, cudaMemcpyHostToDevice);
     if (ce != cudaSuccess) { cudaFree(p->d_tables); delete p; return ctx->fail(SNARKV_ERR_CUDA, "cudaMemcpy(plan tables)", ce); }
     *out = p;
@@ -205,13 +232,18 @@ int snarkv_plonk_accumulate_batch(snarkv_ctx* ctx, snarkv_plonk_plan* p, const u
     const size_t b_st = al256(m * sw * 32), b_ch = al256(m * p->n_challenges * 32), b_rows = al256(m * p->n_inputs * 32 + 32), b_out = al256(m * p->n_out * 32),
                  b_lp = al256(m * nl * 64), b_ls = al256(m * nl * 32), b_rp = al256(m * nr * 64), b_rs = al256(m * nr * 32), b_off = al256((m + 1) * 8),
                  b_pow = al256(m * 32), b_misc = 1024;
-    const size_t need = b_st + b_ch + b_rows + b_out + b_lp + 2 * b_ls + b_rp + 2 * b_rs + 2 * b_off + b_pow + b_misc;
+    const bool pos = p->transcript == 1;
+    const size_t in_words = pos ? (size_t)p->n_pre + p->n_items : sw;         // what the caller uploads per proof
+    const size_t b_in = pos ? al256(m * in_words * 32) : 0, b_pts = pos ? al256(m * (size_t)p->n_points * 64 + 64) : 0;
+    const size_t need = b_in + b_pts + b_st + b_ch + b_rows + b_out + b_lp + 2 * b_ls + b_rp + 2 * b_rs + 2 * b_off + b_pow + b_misc;
     if (need > p->work_bytes) {
         if (p->d_work) { cudaStreamSynchronize(ctx->stream); cudaFree(p->d_work); p->d_work = nullptr; p->work_bytes = 0; }
         SNARKV_CUDA_TRY(ctx, cudaMalloc(&p->d_work, need + need / 4));
         p->work_bytes = need + need / 4;
     }
     uint8_t* w = p->d_work;
+    uint8_t* d_in = w; w += b_in;
+    uint8_t* d_pts = pos ? w : nullptr; w += b_pts;
     uint8_t* d_st = w; w += b_st;
     uint8_t* d_ch = w; w += b_ch;
     uint8_t* d_rows = w; w += b_rows;
@@ -227,17 +259,28 @@ int snarkv_plonk_accumulate_batch(snarkv_ctx* ctx, snarkv_plonk_plan* p, const u
     uint8_t* d_pow = w; w += b_pow;
     uint8_t* d_misc = w;                                   // [rho 32 | lhs 64 | rhs 64 | accept 1 @192 | status words @256..]
     cudaStream_t st = ctx->stream;
-    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_st, streams, m * sw * 32, cudaMemcpyHostToDevice, st));
+    SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(pos ? d_in : d_st, streams, m * in_words * 32, cudaMemcpyHostToDevice, st));
     SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_misc, rho, 32, cudaMemcpyHostToDevice, st));
     SNARKV_CUDA_TRY(ctx, cudaMemsetAsync(d_misc + 256, 0, 64, st));
-    int* d_status = (int*)(d_misc + 256);                  // [0]: rows; [2..3]: lhs rlc + msm; [4..5]: rhs rlc + msm
-    int rc = evm_transcript_device(ctx, d_st, sw * 32, p->d_seg_end, p->n_challenges, m, SNARKV_CANONICAL, d_ch);   // seg_end kept as BYTE offsets
+    int* d_status = (int*)(d_misc + 256);                  // [0]: rows / parsing; [2..3]: lhs rlc + msm; [4..5]: rhs rlc + msm
+    int rc;
+    if (pos) {
+        // element stream = [caller's leading elements | what every proof item absorbs]; compressed points are decompressed + validated here
+        if (p->n_pre)
+            SNARKV_CUDA_TRY(ctx, cudaMemcpy2DAsync(d_st, sw * 32, d_in, in_words * 32, (size_t)p->n_pre * 32, m, cudaMemcpyDeviceToDevice, st));
+        rc = plonk_poseidon_expand_device(ctx, d_in, p->n_items, p->d_item_off, p->d_item_pt, (uint32_t)sw, p->n_points, m, d_st, d_pts, d_status,
+                                          (uint32_t)in_words, p->n_pre);
+        if (rc) return rc;
+        rc = poseidon_transcript_device(ctx, d_st, sw, p->d_seg_end, p->n_challenges, m, SNARKV_CANONICAL, d_ch);      // seg_end: ELEMENT offsets
+    } else {
+        rc = evm_transcript_device(ctx, d_st, sw * 32, p->d_seg_end, p->n_challenges, m, SNARKV_CANONICAL, d_ch);      // seg_end: BYTE offsets
+    }
     if (rc) return rc;
     {
         Stage sg(ctx, "plonk_parse_rows");
         const size_t n = m * p->n_inputs;
         k_plonk_rows<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_st, (uint32_t)sw, d_ch, p->n_challenges, p->d_row_src, p->d_row_check, p->n_inputs, m,
-                                                                 d_rows, d_status);
+                                                                 pos ? 1 : 0, d_rows, d_status);
         SNARKV_LAUNCH_CHECK(ctx, "k_plonk_rows");
         sg.launched();
     }
@@ -247,9 +290,9 @@ int snarkv_plonk_accumulate_batch(snarkv_ctx* ctx, snarkv_plonk_plan* p, const u
     if (rc) return rc;
     {
         Stage sg(ctx, "plonk_parse_points");
-        k_plonk_side<<<(unsigned)((m * nl + 255) / 256), 256, 0, st>>>(d_st, (uint32_t)sw, p->d_const_points, p->d_lhs_src, (uint32_t)nl, d_out, p->n_out, 0, m, d_lp, d_ls);
+        k_plonk_side<<<(unsigned)((m * nl + 255) / 256), 256, 0, st>>>(d_st, (uint32_t)sw, p->d_const_points, p->d_lhs_src, (uint32_t)nl, d_out, p->n_out, 0, m, d_pts, p->n_points, d_lp, d_ls);
         SNARKV_LAUNCH_CHECK(ctx, "k_plonk_side");
-        k_plonk_side<<<(unsigned)((m * nr + 255) / 256), 256, 0, st>>>(d_st, (uint32_t)sw, p->d_const_points, p->d_rhs_src, (uint32_t)nr, d_out, p->n_out, (uint32_t)nl, m, d_rp, d_rs);
+        k_plonk_side<<<(unsigned)((m * nr + 255) / 256), 256, 0, st>>>(d_st, (uint32_t)sw, p->d_const_points, p->d_rhs_src, (uint32_t)nr, d_out, p->n_out, (uint32_t)nl, m, d_pts, p->n_points, d_rp, d_rs);
         SNARKV_LAUNCH_CHECK(ctx, "k_plonk_side");
         k_plonk_offsets<<<(unsigned)((m + 256) / 256), 256, 0, st>>>(d_loff, m, (uint32_t)nl);
         k_plonk_offsets<<<(unsigned)((m + 256) / 256), 256, 0, st>>>(d_roff, m, (uint32_t)nr);
@@ -268,7 +311,7 @@ int snarkv_plonk_accumulate_batch(snarkv_ctx* ctx, snarkv_plonk_plan* p, const u
     SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(host, d_misc, sizeof host, cudaMemcpyDeviceToHost, st));
     SNARKV_CUDA_TRY(ctx, cudaStreamSynchronize(st));
     const int* hs = (const int*)(host + 256);
-    if (hs[0]) return ctx->fail(hs[0], "Invalid scalar encoding in proof");
+    if (hs[0]) return ctx->fail(hs[0], hs[0] == SNARKV_ERR_BAD_POINT ? "Invalid elliptic curve point encoding in proof" : "Invalid scalar encoding in proof");
     for (int k = 2; k < 6; ++k)
         if (hs[k]) return ctx->fail(hs[k], hs[k] == SNARKV_ERR_BAD_SCALAR ? "scalar is not a canonical Fr" : "Invalid elliptic curve point encoding in proof");
     if (out_lhs) memcpy(out_lhs, host + 32, 64);

@@ -98,6 +98,75 @@ __global__ void __launch_bounds__(64) k_poseidon_transcript(const uint8_t* __res
     }
 }
 
+// The same transcript with the state spread over lanes: one proof per group of 8 lanes, lane g < 5 holds state[g].  A round costs 3
+// multiplications of latency for the S-box (every lane; in a partial round only lane 0 keeps its result) + 5 for its MDS row,
+// instead of 15 (3) + 25 in one thread: ~3x shorter critical path, which is what bounds a batch of a few thousand proofs
+// (one thread per proof leaves the SMs almost idle: measured 11 ms for 4096 proofs of ~60 elements).
+__device__ __forceinline__ Fr fr_shfl8(const Fr& a, int src) {
+    Fr r;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r.v[k] = __shfl_sync(0xffffffffu, a.v[k], src, 8);
+    return r;
+}
+__device__ void poseidon_permute_lanes(Fr& s, uint32_t g) {
+    constexpr int T = SNARKV_POSEIDON_T, RF = SNARKV_POSEIDON_RF, RP = SNARKV_POSEIDON_RP;
+    const uint32_t gi = g < (uint32_t)T ? g : 0u;           // lanes 5..7 mirror lane 0's constants and discard everything
+#pragma unroll 1
+    for (int r = 0; r < RF + RP; ++r) {
+        s = fp_add(s, fr_const(POSEIDON_RC[r * T + gi]));
+        const Fr p5 = fr_pow5(s);
+        if (r < RF / 2 || r >= RF / 2 + RP || g == 0) s = p5;
+        Fr acc = fp_mul(fr_const(POSEIDON_MDS[gi * T]), fr_shfl8(s, 0));
+#pragma unroll
+        for (int j = 1; j < T; ++j) acc = fp_add(acc, fp_mul(fr_const(POSEIDON_MDS[gi * T + j]), fr_shfl8(s, j)));
+        s = acc;
+    }
+}
+__global__ void __launch_bounds__(128) k_poseidon_transcript_lanes(const uint8_t* __restrict__ elements, size_t stream_len,
+                                                                   const uint32_t* __restrict__ seg_end, uint32_t k, size_t m, int format,
+                                                                   uint8_t* __restrict__ out) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t jj = t >> 3;
+    const uint32_t g = (uint32_t)(t & 7u);
+    const size_t j = jj < m ? jj : m - 1;                  // surplus groups of the last warp replay the last proof (shuffles need every lane)
+    constexpr uint32_t RATE = SNARKV_POSEIDON_T - 1;
+    const uint8_t* st = elements + j * stream_len * 32;
+    Fr s = fp_zero<FR>();
+    if (g == 0) {
+        constexpr uint32_t cap[8] = SNARKV_POSEIDON_CAPACITY;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s.v[i] = cap[i];
+    }
+    uint32_t prev = 0;
+    for (uint32_t i = 0; i < k; ++i) {
+        const uint32_t e = seg_end[i];
+        // chunks of RATE elements, then one empty chunk when the count is a multiple of RATE (incl. zero)
+        const uint32_t len = e - prev, chunks = len / RATE + 1;
+        for (uint32_t c = 0; c < chunks; ++c) {
+            const uint32_t pos = prev + c * RATE, cnt = min(RATE, e - pos);
+            if (c == chunks - 1 && len % RATE != 0 && cnt == 0) break;
+            if (c == chunks - 1 && len % RATE == 0) {
+                if (g == 1) s = fp_add(s, fp_one<FR>());                            // the `exact` permutation on an empty chunk
+            } else if (g >= 1 && g <= RATE) {
+                if (g - 1 < cnt) {
+                    Fr v = fp_load<FR>(st + (size_t)(pos + g - 1) * 32);
+                    if (format == SNARKV_CANONICAL) v = fp_to_mont(v);
+                    s = fp_add(s, v);
+                } else if (g - 1 == cnt) {
+                    s = fp_add(s, fp_one<FR>());
+                }
+            }
+            poseidon_permute_lanes(s, g);
+        }
+        prev = e;
+        if (g == 1 && jj < m) {
+            Fr c = s;
+            if (format == SNARKV_CANONICAL) c = fp_from_mont(c);
+            fp_store<FR>(out + (j * k + i) * 32, c);
+        }
+    }
+}
+
 // parity entry: m states of T elements -> permuted states
 __global__ void __launch_bounds__(64) k_poseidon_permute(const uint8_t* __restrict__ in, size_t m, int format, uint8_t* __restrict__ out) {
     const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -122,16 +191,14 @@ __global__ void __launch_bounds__(64) k_poseidon_permute(const uint8_t* __restri
 // transcript rejects it one line later (`coordinates()` of the identity is None, halo2.rs:226-241) — so the two historical
 // layouts of the identity (all zeros / flag bit) need not be told apart.  points: affine (x, y) in `format`;
 // elements (optional): x mod r, y mod r in `format` — what common_ec_point absorbs (fe_to_fe).
-__global__ void __launch_bounds__(128) k_g1_decompress(const uint8_t* __restrict__ compressed, size_t n, int format, uint8_t* __restrict__ points,
-                                                       uint8_t* __restrict__ elements, uint8_t* __restrict__ valid) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    Fq x = fp_load<FQ>(compressed + i * 32);
+// one compressed point -> (ok, canonical x / y, Montgomery x / y)
+__device__ bool g1_decompress_one(const uint8_t* compressed, Fq& xc, Fq& yc, Fq& xm, Fq& y) {
+    Fq x = fp_load<FQ>(compressed);
     const uint32_t sign = x.v[7] >> 31, ident = (x.v[7] >> 30) & 1u;
     x.v[7] &= 0x3fffffffu;
     bool ok = !ident && fp_is_canonical(x);
-    const Fq xc = x;
-    Fq xm = fp_to_mont(x);
+    xc = x;
+    xm = fp_to_mont(x);
     Fq b = fp_one<FQ>();
 #pragma unroll
     for (int k = 1; k < SNARKV_CURVE_B; ++k) b = fp_add(b, fp_one<FQ>());
@@ -148,19 +215,44 @@ __global__ void __launch_bounds__(128) k_g1_decompress(const uint8_t* __restrict
 #pragma unroll
     for (int k = 0; k < 7; ++k) e[k] = (e[k] >> 2) | (e[k + 1] << 30);
     e[7] >>= 2;
-    Fq y = fp_one<FQ>();
+    y = fp_one<FQ>();
 #pragma unroll 1
     for (int bit = 253; bit >= 0; --bit) {
         y = fp_sqr(y);
         if ((e[bit >> 5] >> (bit & 31)) & 1u) y = fp_mul(y, rhs);
     }
     ok = ok && fp_eq(fp_sqr(y), rhs);
-    Fq yc = fp_from_mont(y);
+    yc = fp_from_mont(y);
     if ((yc.v[0] & 1u) != sign) {
         y = fp_neg(y);
         yc = fp_from_mont(y);
     }
-    ok = ok && !(fp_is_zero(yc) && sign);                        // y = 0 has no odd twin
+    return ok && !(fp_is_zero(yc) && sign);                      // y = 0 has no odd twin
+}
+// fe_to_fe: a canonical base-field value reduced into the scalar field (p < 2 r: one conditional subtraction), in `format`
+__device__ __forceinline__ Fr fq_to_fr_element(const Fq& c, int format) {
+    Fr v;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v.v[k] = c.v[k];
+    if (!fp_is_canonical(v)) {
+        uint32_t borrow = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint64_t d = (uint64_t)v.v[k] - fp_mod_limb<FR>(k) - borrow;
+            v.v[k] = (uint32_t)d;
+            borrow = (uint32_t)(d >> 63);
+        }
+    }
+    if (format == SNARKV_MONTGOMERY) v = fp_to_mont(v);
+    return v;
+}
+
+__global__ void __launch_bounds__(128) k_g1_decompress(const uint8_t* __restrict__ compressed, size_t n, int format, uint8_t* __restrict__ points,
+                                                       uint8_t* __restrict__ elements, uint8_t* __restrict__ valid) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fq xc, yc, xm, y;
+    const bool ok = g1_decompress_one(compressed + i * 32, xc, yc, xm, y);
     if (!ok) {
         valid[i] = 0;
         fp_store<FQ>(points + i * 64, fp_zero<FQ>());
@@ -175,28 +267,68 @@ __global__ void __launch_bounds__(128) k_g1_decompress(const uint8_t* __restrict
     fp_store<FQ>(points + i * 64, format == SNARKV_CANONICAL ? xc : xm);
     fp_store<FQ>(points + i * 64 + 32, format == SNARKV_CANONICAL ? yc : y);
     if (elements) {
-        // fe_to_fe: reduce the base-field coordinate into the scalar field (p < 2 r: one conditional subtraction)
-        Fr ex, ey;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { ex.v[k] = xc.v[k]; ey.v[k] = yc.v[k]; }
-        Fr* both[2] = {&ex, &ey};
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            Fr& v = *both[h];
-            if (!fp_is_canonical(v)) {
-                uint32_t borrow = 0;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const uint64_t d = (uint64_t)v.v[k] - fp_mod_limb<FR>(k) - borrow;
-                    v.v[k] = (uint32_t)d;
-                    borrow = (uint32_t)(d >> 63);
-                }
-            }
-            if (format == SNARKV_MONTGOMERY) v = fp_to_mont(v);
-        }
-        fp_store<FR>(elements + i * 64, ex);
-        fp_store<FR>(elements + i * 64 + 32, ey);
+        fp_store<FR>(elements + i * 64, fq_to_fr_element(xc, format));
+        fp_store<FR>(elements + i * 64 + 32, fq_to_fr_element(yc, format));
     }
+}
+
+// PlonkProof::read over the Poseidon transcript for a batch (plonk_batch.cu): item i of proof j (32 bytes) is a little-endian scalar
+// (copied to element `off`, rejected when >= r) or a compressed point (decompressed: the two elements it absorbs go to `off`, `off + 1`,
+// the affine point to slot pt_index of the proof's point array).  item_off[i] < 0 marks a point: off = -(item_off[i] + 1).
+__global__ void __launch_bounds__(128) k_plonk_poseidon_expand(const uint8_t* __restrict__ proofs, uint32_t n_items, const int32_t* __restrict__ item_off,
+                                                               const int32_t* __restrict__ item_pt, uint32_t stream_len, uint32_t n_points, size_t m,
+                                                               uint8_t* __restrict__ elements, uint8_t* __restrict__ points, int* __restrict__ status,
+                                                               uint32_t in_stride, uint32_t in_base) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m * n_items) return;
+    const size_t j = t / n_items;
+    const uint32_t i = (uint32_t)(t - j * n_items);
+    const uint8_t* src = proofs + (j * in_stride + in_base + i) * 32;   // proof j's items follow its in_base caller-supplied elements
+    const int32_t o = item_off[i];
+    if (o >= 0) {
+        const Fr v = fp_load<FR>(src);
+        if (!fp_is_canonical(v)) atomicCAS(status, 0, SNARKV_ERR_BAD_SCALAR);       // "Invalid scalar encoding in proof"
+        fp_store<FR>(elements + (j * stream_len + (uint32_t)o) * 32, v);
+        return;
+    }
+    const uint32_t off = (uint32_t)(-(o + 1));
+    Fq xc, yc, xm, y;
+    if (!g1_decompress_one(src, xc, yc, xm, y)) {
+        atomicCAS(status, 0, SNARKV_ERR_BAD_POINT);                                // "Invalid elliptic curve point encoding in proof"
+        xc = fp_zero<FQ>();
+        yc = fp_zero<FQ>();
+    }
+    fp_store<FR>(elements + (j * stream_len + off) * 32, fq_to_fr_element(xc, SNARKV_CANONICAL));
+    fp_store<FR>(elements + (j * stream_len + off + 1) * 32, fq_to_fr_element(yc, SNARKV_CANONICAL));
+    uint8_t* dst = points + (j * n_points + (uint32_t)item_pt[i]) * 64;
+    fp_store<FQ>(dst, xc);
+    fp_store<FQ>(dst + 32, yc);
+}
+
+int plonk_poseidon_expand_device(snarkv_ctx* ctx, const void* d_proofs, uint32_t n_items, const void* d_item_off, const void* d_item_pt, uint32_t stream_len,
+                                 uint32_t n_points, size_t m, void* d_elements, void* d_points, void* d_status, uint32_t in_stride, uint32_t in_base) {
+    Stage sg(ctx, "plonk_poseidon_expand");
+    const size_t n = m * n_items;
+    k_plonk_poseidon_expand<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((const uint8_t*)d_proofs, n_items, (const int32_t*)d_item_off,
+                                                                                 (const int32_t*)d_item_pt, stream_len, n_points, m, (uint8_t*)d_elements,
+                                                                                 (uint8_t*)d_points, (int*)d_status, in_stride, in_base);
+    SNARKV_LAUNCH_CHECK(ctx, "k_plonk_poseidon_expand");
+    sg.launched();
+    return SNARKV_OK;
+}
+
+int poseidon_transcript_device(snarkv_ctx* ctx, const void* d_elements, size_t stream_len, const void* d_seg_end, size_t k, size_t m, int format, void* d_out) {
+    Stage sg(ctx, "poseidon_transcript");
+    // small and medium batches: one proof per 8 lanes (latency); huge batches: one proof per thread (throughput)
+    if (m <= ((size_t)1 << 16))
+        k_poseidon_transcript_lanes<<<(unsigned)((m * 8 + 127) / 128), 128, 0, ctx->stream>>>((const uint8_t*)d_elements, stream_len, (const uint32_t*)d_seg_end,
+                                                                                            (uint32_t)k, m, format, (uint8_t*)d_out);
+    else
+        k_poseidon_transcript<<<(unsigned)((m + 63) / 64), 64, 0, ctx->stream>>>((const uint8_t*)d_elements, stream_len, (const uint32_t*)d_seg_end, (uint32_t)k, m,
+                                                                               format, (uint8_t*)d_out);
+    SNARKV_LAUNCH_CHECK(ctx, "k_poseidon_transcript");
+    sg.launched();
+    return SNARKV_OK;
 }
 
 }  // namespace snarkv
@@ -234,10 +366,8 @@ int snarkv_poseidon_transcript_challenges(snarkv_ctx* ctx, const uint8_t* elemen
     if (stream_len) SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_st, elements, m * stream_len * 32, cudaMemcpyHostToDevice, st));
     SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(d_seg, seg_end, k * 4, cudaMemcpyHostToDevice, st));
     {
-        Stage sg(ctx, "poseidon_transcript");
-        k_poseidon_transcript<<<(unsigned)((m + 63) / 64), 64, 0, st>>>(d_st, stream_len, (const uint32_t*)d_seg, (uint32_t)k, m, format, d_out);
-        SNARKV_LAUNCH_CHECK(ctx, "k_poseidon_transcript");
-        sg.launched();
+        int rc = poseidon_transcript_device(ctx, d_st, stream_len, d_seg, k, m, format, d_out);
+        if (rc) return rc;
     }
     SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(challenges, d_out, m * k * 32, cudaMemcpyDeviceToHost, st));
     SNARKV_CUDA_TRY(ctx, cudaStreamSynchronize(st));

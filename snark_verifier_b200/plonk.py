@@ -337,7 +337,7 @@ class PlonkBatchVerifier:
         self.encoding = LimbsEncoding(*limbs)
         self._slots = {"lhs": self.compiled.msm.lhs_slots, "rhs": self.compiled.msm.rhs_slots}
         self._plan = None
-        self.use_device_plan = transcript == "evm" and hasattr(loader, "plonk_plan_create")   # the fused device-resident pipeline
+        self.use_device_plan = hasattr(loader, "plonk_plan_create")   # the fused device-resident pipeline (csrc/plonk_batch.cu)
 
     def close(self):
         if self._plan is not None:
@@ -359,6 +359,14 @@ class PlonkBatchVerifier:
                     index[pt] = len(consts)
                     consts.append(pt)
                 return -(index[pt] + 1)
+            poseidon = None
+            point_src = {o: o for o in tl.witnesses + tl.quotients + tl.ws}          # EvmTranscript: a point is addressed by its word offset
+            if self.transcript == "poseidon":
+                pt_offsets = [off for kind, off in tl.items if kind == "point"]
+                point_src = {off: k for k, off in enumerate(pt_offsets)}             # Poseidon: by its index among the decompressed points
+                item_off = [off if kind == "scalar" else -(off + 1) for kind, off in tl.items]
+                item_pt = [point_src[off] if kind == "point" else -1 for kind, off in tl.items]
+                poseidon = (tl.proof_start, item_off, item_pt, len(pt_offsets))
             src = {}
             for side in ("lhs", "rhs"):
                 src[side] = []
@@ -368,14 +376,17 @@ class PlonkBatchVerifier:
                     elif s[0] == "pre":
                         src[side].append(const_slot(pr.preprocessed[s[1]]))
                     else:
-                        src[side].append({"wit": tl.witnesses, "quot": tl.quotients, "w": tl.ws}[s[0]][s[1]])
-            self._plan = self.loader.plonk_plan_create(tl.total, list(tl.seg_end), self.compiled.msm.program, row_src, row_check, src["lhs"], src["rhs"], consts)
+                        src[side].append(point_src[{"wit": tl.witnesses, "quot": tl.quotients, "w": tl.ws}[s[0]][s[1]]])
+            self._plan = self.loader.plonk_plan_create(tl.total, list(tl.seg_end), self.compiled.msm.program, row_src, row_check, src["lhs"], src["rhs"], consts,
+                                                       poseidon)
         return self._plan
 
-    def _streams_evm(self, instances, proofs) -> np.ndarray:
-        """m x (absorbed stream) bytes for the Keccak EvmTranscript: [initial state | instances | proof] as 32-byte big-endian words"""
+    def _streams_wire(self, instances, proofs) -> np.ndarray:
+        """m x bytes handed to the device plan: [initial state | instances | proof].  EvmTranscript: 32-byte big-endian words (this IS the
+        absorbed stream); Poseidon: little-endian scalars followed by the proof's 32-byte items (compressed points / little-endian scalars)"""
         tl, pr = self.tl, self.protocol
-        m, plen, shape = len(proofs), tl.proof_len("evm"), list(pr.num_instance)
+        order = "big" if self.transcript == "evm" else "little"
+        m, plen, shape = len(proofs), tl.proof_len(self.transcript), list(pr.num_instance)
         if isinstance(proofs, np.ndarray):
             if proofs.shape != (m, plen):
                 raise TranscriptError("proofs: %r, the protocol's transcript reads %d bytes per proof" % (proofs.shape, plen))
@@ -384,11 +395,11 @@ class PlonkBatchVerifier:
                 if len(proof) != plen:
                     raise TranscriptError("proof %d: %d bytes, the protocol's transcript reads %d" % (j, len(proof), plen))
             proofs = np.frombuffer(b"".join(proofs), dtype=np.uint8).reshape(m, plen)
-        st = np.empty((m, tl.total * 32), dtype=np.uint8)
+        st = np.empty((m, 32 * tl.proof_start + plen), dtype=np.uint8)
         if tl.initial_state is not None:
-            st[:, :32] = np.frombuffer((pr.transcript_initial_state % R_MODULUS).to_bytes(32, "big"), dtype=np.uint8)
+            st[:, :32] = np.frombuffer((pr.transcript_initial_state % R_MODULUS).to_bytes(32, order), dtype=np.uint8)
         n_inst = sum(shape)
-        if isinstance(instances, np.ndarray):                     # m x n_inst x 32 B big-endian words, already packed by the caller
+        if isinstance(instances, np.ndarray):                     # m x n_inst x 32 B words in the transcript's byte order, packed by the caller
             if instances.shape != (m, n_inst, 32):
                 raise InvalidInstances("instances: %r, expected %r" % (instances.shape, (m, n_inst, 32)))
             st[:, 32 * tl.instances:32 * tl.proof_start] = instances.reshape(m, -1)
@@ -397,13 +408,13 @@ class PlonkBatchVerifier:
                 if [len(col) for col in inst] != shape:
                     raise InvalidInstances("proof %d: instance column lengths %r != %r" % (j, [len(c) for c in inst], pr.num_instance))
             if n_inst:
-                words = b"".join((v % R_MODULUS).to_bytes(32, "big") for inst in instances for col in inst for v in col)
+                words = b"".join((v % R_MODULUS).to_bytes(32, order) for inst in instances for col in inst for v in col)
                 st[:, 32 * tl.instances:32 * tl.proof_start] = np.frombuffer(words, dtype=np.uint8).reshape(m, 32 * n_inst)
         st[:, 32 * tl.proof_start:] = proofs
         return st
 
     def _accumulate_new_device(self, instances, proofs, rho: int, decide: bool):
-        st = self._streams_evm(instances, proofs)
+        st = self._streams_wire(instances, proofs)
         try:
             lhs, rhs, ok = self.loader.plonk_accumulate_batch(self._device_plan(), st, st.shape[0], (rho % R_MODULUS).to_bytes(32, "little"), decide)
         except Error as e:

@@ -102,3 +102,18 @@ def test_compressed_points_from_bytes(loader):
     assert list(valid[n:]) == [0, 1 if zero_is_point else 0, 0, 0, 0]
     assert points[64 * n:64 * n + 64] == bytes(64)
     # (a coordinate in [r, p) would be absorbed reduced — fe_to_fe — but p - r ~ 2^127: no such point can be found to test with)
+
+
+def test_huge_batch_uses_the_thread_per_proof_kernel(loader):
+    """above 2^16 proofs the transcript runs one proof per thread instead of one per 8 lanes: same challenges"""
+    import numpy as np
+    if loader.fmt != sv.CANONICAL:
+        pytest.skip("one format is enough for the dispatch test")
+    mm, ln, seg_end = (1 << 16) + 37, 6, [2, 6]
+    rng = np.random.default_rng(3)
+    st = rng.integers(0, 256, size=(mm, ln, 32), dtype=np.uint8)
+    st[:, :, 31] &= 0x1F                                        # < 2^253 < r
+    got = loader.poseidon_transcript_challenges(st.tobytes(), ln, seg_end, mm)
+    for j in (0, 1, 4095, 65535, mm - 1):
+        el = [int.from_bytes(st[j, i].tobytes(), "little") for i in range(ln)]
+        assert [int.from_bytes(got[32 * (2 * j + i):32 * (2 * j + i + 1)], "little") for i in range(2)] == pos.challenges_for_elements(el, seg_end)

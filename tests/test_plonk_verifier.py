@@ -328,14 +328,27 @@ def test_device_verifier_over_the_poseidon_transcript(gpu, srs, circuit, scheme)
     rows_d, _, ch_d = v.batch.read_proofs([inst], [proof])
     rows_c, _, ch_c = ref.batch.read_proofs([inst], [proof])
     assert rows_d.tobytes() == rows_c.tobytes() and ch_d.tobytes() == ch_c.tobytes()
-    got, exp = v.succinct_verify(inst, proof)[0], ref.succinct_verify(inst, proof)[0]
-    assert (got.lhs, got.rhs) == (exp.lhs, exp.rhs)
+    exp = ref.succinct_verify(inst, proof)[0]
+    for _ in range(2):                                          # the one-call device pipeline (twice: plan state must not leak between calls)
+        got = v.succinct_verify(inst, proof)[0]
+        assert v.batch.use_device_plan and (got.lhs, got.rhs) == (exp.lhs, exp.rhs)
+    v.batch.use_device_plan = False                             # ... and step by step through the separate entry points
+    try:
+        step = v.succinct_verify(inst, proof)[0]
+        assert (step.lhs, step.rhs) == (exp.lhs, exp.rhs)
+    finally:
+        v.batch.use_device_plan = True
     for tamper in ("evaluation", "witness", "opening"):
         with pytest.raises(sv.AssertionFailure):
             v.verify(inst, T.prove(circuit, protocol, srs, scheme, tamper=tamper, transcript="poseidon"))
     bad = bytearray(proof)
     bad[31] |= 0x40
-    with pytest.raises(plonk.TranscriptError):
+    with pytest.raises(plonk.TranscriptError, match="curve point"):
+        v.verify(inst, bytes(bad))
+    o = 32 * [i for i, (kind, _) in enumerate(v.batch.tl.items) if kind == "scalar"][0]
+    bad = bytearray(proof)
+    bad[o:o + 32] = R.to_bytes(32, "little")                   # an evaluation >= r
+    with pytest.raises(plonk.TranscriptError, match="scalar"):
         v.verify(inst, bytes(bad))
     mm = 300                                                   # a fused batch with one tampered proof
     proofs = [proof] * mm
