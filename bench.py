@@ -483,6 +483,29 @@ class Aux:
                               "what": "StandardPlonk-shaped quotient evaluation (protocol.rs:211-283, 336-392; proof.rs:298-349) as one straight-line Fr "
                                       "program, one thread per proof, sharded by proof, operands resident in HBM"}, m_proofs, "proofs_per_s"
         self.leg("plonk_scalar_eval", plonk_scalar_eval)
+
+        # the IPA decider over Pallas (pcs/ipa/decider.rs:47-70) — h_coeffs on the device + a 2^20-term Pallas MSM against the
+        # resident committing key + comparison with u.  A single decision does not shard: replicas (every rank decides its own accumulators).
+        def ipa_decide():
+            from snark_verifier_b200 import pasta
+            k = 20
+            n = 1 << k
+            PL = pasta.PallasLoader(L)
+            with torch.cuda.stream(stream):
+                dp = torch.empty(n * 64, dtype=torch.uint8, device=dev)
+                PL.synth_points_device(SEED + 9, 0, n, dp.data_ptr())
+            stream.synchronize()
+            g = dp.cpu().numpy().tobytes()
+            ipa = pasta.IpaAs(L, pasta.IpaDecidingKey(g))                     # uploads + validates the key once
+            xi = [((7919 * (i + 1) + rank) % 65521 + 2).to_bytes(32, "little") for i in range(k)]
+            u = PL.msm(PL.h_coeffs(b"".join(xi), k), g, n)                     # an accumulator that decides (outside the timed region)
+            good = pasta.IpaAccumulator(xi, u)
+            bad = pasta.IpaAccumulator(xi, pasta.PALLAS_GENERATOR)
+            ok = ipa.decide_batch([good, bad]) == b"\x01\x00"
+            ms = self.timed_wall(lambda: ipa.decide(good), 5)
+            return ms, ok, {"k": k, "what": "IpaAs::decide over Pallas at k = 20 (h_coeffs + 2^20-term MSM against the resident key + compare); replicas: "
+                                            "every rank decides its own accumulator; ms = latency of one decision incl. H2D of (xi, u)"}, world, "decisions_per_s"
+        self.leg("ipa_decide_pallas_k20", ipa_decide)
         return self.out
 
 
