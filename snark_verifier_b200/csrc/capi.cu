@@ -111,6 +111,8 @@ int snarkv_init(int device, snarkv_ctx** out) {
     c->ba_pairs_min = env_int("SNARKV_BA_PAIRS_MIN", 1, 1 << 20, c->ba_pairs_min);
     c->ba_q = env_int("SNARKV_BA_Q", 1, 4, c->ba_q);
     c->host_chunks = env_int("SNARKV_HOST_CHUNKS", 2, 7, c->host_chunks);
+    c->sort_blocks_per_sm = env_int("SNARKV_SORT_BLOCKS", 0, 16, 0);
+    c->sort_tile = env_int("SNARKV_SORT_TILE", 4096, 8192, c->sort_tile) == 8192 ? 8192 : 4096;
     c->host_chunk_min_log_n = env_int("SNARKV_HOST_CHUNK_MIN", 16, 30, c->host_chunk_min_log_n);
     c->host_chunks_small = env_int("SNARKV_HOST_CHUNKS_SMALL", 2, 7, c->host_chunks_small);
     c->host_chunk_ratio_pct = env_int("SNARKV_HOST_RATIO", 100, 400, c->host_chunk_ratio_pct);

@@ -77,7 +77,9 @@ struct snarkv_ctx {
     int window_bits = 0;
     int glv_mode = 0;       // 0 = GLV for n < 2^22 (default), 1 = always, 2 = never
     int pairing_mode = 0;   // 0 = choose from N, 1 = one thread per check, 2 = one block per check
-    int host_chunk_min_log_n = 22, host_chunks_small = 3;   // SNARKV_HOST_CHUNK_MIN / SNARKV_HOST_CHUNKS_SMALL: chunk pipeline for inputs of 2^min .. 2^22 terms
+    int sort_blocks_per_sm = 0;   // SNARKV_SORT_BLOCKS: resident k_partition blocks per SM (0 = default)
+    int sort_tile = 8192;   // SNARKV_SORT_TILE: digits per k_partition work item (4096 | 8192); measured at 2^24: 1.30 vs 1.20 ms (profiles/r02_sort_tile_probe.txt)
+    int host_chunk_min_log_n = 20, host_chunks_small = 3;   // SNARKV_HOST_CHUNK_MIN / SNARKV_HOST_CHUNKS_SMALL: chunk pipeline for inputs of 2^min .. 2^22 terms
     int host_chunks = 7, host_chunk_ratio_pct = 160;   // host entry pipeline: term-chunks of geometrically growing size (SNARKV_HOST_CHUNKS <= 7, SNARKV_HOST_RATIO in percent)
     int accumulate_mode = 0;   // 0 = choose from the bucket load, 1 = XYZZ, 2 = batched affine (tree), 3 = XYZZ + tree + task-level self-check, 4 = chained batched affine
     int ba_blocks_per_sm = 0;  // occupancy of k_bucket_accumulate_affine (queried once)

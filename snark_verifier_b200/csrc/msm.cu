@@ -705,12 +705,14 @@ static int msm_sort_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* d_scal
             k_part_scan<<<pl.W < 64 ? pl.W : 64, 1024, 0, st>>>(wk.part_count, wk.part_off, wk.part_cursor, pl.W, P);
             SNARKV_LAUNCH_CHECK(ctx, "k_part_scan");
             sg.launched();
-            const size_t smem = (size_t)3 * P * 4 + (size_t)SNARKV_SORT_TILE * 8;
-            SNARKV_CUDA_TRY(ctx, cudaFuncSetAttribute(k_partition, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            const size_t items = ((nvt + SNARKV_SORT_TILE - 1) / SNARKV_SORT_TILE) * pl.W;
-            const size_t want_b = items, cap_b = (size_t)ctx->sm_count * 4;
-            k_partition<<<(unsigned)(want_b < cap_b ? want_b : cap_b), SNARKV_SORT_THREADS, smem, st>>>(wk.digits, nvt, pl.W, P, lo, wk.part_off,
-                                                                                                       wk.part_cursor, wk.rec_idx, wk.rec_lo);
+            const int tile = ctx->sort_tile;                    // digits per work item: 4096 (256 threads) or 8192 (512 threads)
+            const size_t smem = (size_t)3 * P * 4 + (size_t)tile * 8;
+            auto kp = tile == 8192 ? k_partition<512> : k_partition<256>;
+            SNARKV_CUDA_TRY(ctx, cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const size_t items = ((nvt + tile - 1) / tile) * pl.W;
+            const size_t want_b = items, cap_b = (size_t)ctx->sm_count * (ctx->sort_blocks_per_sm > 0 ? ctx->sort_blocks_per_sm : 4);
+            kp<<<(unsigned)(want_b < cap_b ? want_b : cap_b), tile / SNARKV_SORT_PER_THREAD, smem, st>>>(wk.digits, nvt, pl.W, P, lo, wk.part_off,
+                                                                                                   wk.part_cursor, wk.rec_idx, wk.rec_lo);
             SNARKV_LAUNCH_CHECK(ctx, "k_partition");
             sg.launched();
         }
@@ -982,10 +984,10 @@ int msm_run_host(snarkv_ctx* ctx, const uint8_t* scalars, const uint8_t* points,
     uint8_t* d_o = (uint8_t*)ctx->wsget(WS_OUT, 1024);   // [affine 64 | pad | status K x 4 @512]
     if (!d_s || !d_p || !d_o) return SNARKV_ERR_CUDA;
     cudaStream_t st = ctx->stream;
-    // measured: below 2^22 terms the per-chunk fixed costs (scan, merges, launches) eat the copy/compute overlap (2^21: 12.1 ms
-    // chunked vs 11.9 ms in one pass), so smaller inputs keep the single-pass path
-    // (SNARKV_HOST_CHUNK_MIN lowers the threshold: when several GPUs of one box copy at the same time the host side of PCIe is the
-    // bottleneck and a short pipeline pays earlier)
+    // Chunk pipeline: >= 2^22 terms in host_chunks (7) geometrically growing chunks; 2^20 .. 2^22 terms in 3.  On one GPU the short
+    // pipeline is neutral at 2^21 terms (12.1 ms chunked vs 11.9 ms in one pass: per-chunk scans and merges eat the overlap), but when
+    // the 8 GPUs of a box copy at the same time the host side of PCIe is the bottleneck and it pays: e2e of the 2^24-term MSM at
+    // N = 8 (2^21 terms per rank) 1086 -> 1220 M/s (profiles/r02_bench_n8*.json).  SNARKV_HOST_CHUNK_MIN / _CHUNKS_SMALL override.
     const int K = n >= ((size_t)1 << ctx->host_chunk_min_log_n) ? (n >= ((size_t)1 << 22) ? ctx->host_chunks : ctx->host_chunks_small) : 1;
     int status[SNARKV_HOST_CHUNKS_MAX] = {};
     int* d_status = (int*)(d_o + 512);

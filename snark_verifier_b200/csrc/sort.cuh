@@ -111,7 +111,8 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_smem(uint32_t* a, uint3
 }
 
 // K3: coarse partition.  Dynamic shared memory: hist[P] | loff[P] | gbase[P] | stage_idx[TILE] | stage_lo[TILE] (u16) | stage_p[TILE] (u16)
-__global__ void __launch_bounds__(SNARKV_SORT_THREADS) k_partition(const uint32_t* __restrict__ digits, size_t nv, uint32_t W, uint32_t P,
+template <int THREADS>   // tile = THREADS x SNARKV_SORT_PER_THREAD digits
+__global__ void __launch_bounds__(THREADS) k_partition(const uint32_t* __restrict__ digits, size_t nv, uint32_t W, uint32_t P,
                                                                    uint32_t lo_bits, const uint32_t* __restrict__ part_off,
                                                                    uint32_t* __restrict__ part_cursor, uint32_t* __restrict__ rec_idx,
                                                                    uint16_t* __restrict__ rec_lo) {
@@ -121,22 +122,22 @@ __global__ void __launch_bounds__(SNARKV_SORT_THREADS) k_partition(const uint32_
     uint32_t* loff = hist + P;
     uint32_t* gbase = loff + P;
     uint32_t* stage_idx = gbase + P;
-    uint16_t* stage_lo = reinterpret_cast<uint16_t*>(stage_idx + SNARKV_SORT_TILE);
-    uint16_t* stage_p = stage_lo + SNARKV_SORT_TILE;
+    uint16_t* stage_lo = reinterpret_cast<uint16_t*>(stage_idx + (THREADS * SNARKV_SORT_PER_THREAD));
+    uint16_t* stage_p = stage_lo + (THREADS * SNARKV_SORT_PER_THREAD);
     const uint32_t t = threadIdx.x;
-    const size_t ntiles = (nv + SNARKV_SORT_TILE - 1) / SNARKV_SORT_TILE;
+    const size_t ntiles = (nv + (THREADS * SNARKV_SORT_PER_THREAD) - 1) / (THREADS * SNARKV_SORT_PER_THREAD);
     const size_t items = ntiles * W;
     const uint32_t lo_mask = (1u << lo_bits) - 1u;
     for (size_t item = blockIdx.x; item < items; item += gridDim.x) {
         const uint32_t w = (uint32_t)(item / ntiles);          // window-major: neighbouring blocks share a window's cursors
-        const size_t first = (item - (size_t)w * ntiles) * SNARKV_SORT_TILE;
+        const size_t first = (item - (size_t)w * ntiles) * (THREADS * SNARKV_SORT_PER_THREAD);
         const uint32_t* dg = digits + (size_t)w * nv;
-        for (uint32_t k = t; k < P; k += SNARKV_SORT_THREADS) hist[k] = 0;
+        for (uint32_t k = t; k < P; k += THREADS) hist[k] = 0;
         __syncthreads();
         uint32_t e[SNARKV_SORT_PER_THREAD], rank[SNARKV_SORT_PER_THREAD];
 #pragma unroll
         for (int k = 0; k < SNARKV_SORT_PER_THREAD; ++k) {
-            const size_t i = first + (size_t)k * SNARKV_SORT_THREADS + t;
+            const size_t i = first + (size_t)k * THREADS + t;
             e[k] = i < nv ? dg[i] : 0u;
         }
 #pragma unroll
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(SNARKV_SORT_THREADS) k_partition(const uint32_
         }
         __syncthreads();
         // counts -> exclusive offsets inside the tile (loff) and the global run reserved for this tile (gbase)
-        for (uint32_t k = t; k < P; k += SNARKV_SORT_THREADS) {
+        for (uint32_t k = t; k < P; k += THREADS) {
             const uint32_t c = hist[k];
             loff[k] = c;
             gbase[k] = c ? part_off[w * P + k] + atomicAdd(&part_cursor[w * P + k], c) : 0u;
@@ -159,7 +160,7 @@ __global__ void __launch_bounds__(SNARKV_SORT_THREADS) k_partition(const uint32_
             if (d == 0) continue;
             const uint32_t b = d - 1u, p = b >> lo_bits;
             const uint32_t slot = loff[p] + rank[k];
-            const size_t i = first + (size_t)k * SNARKV_SORT_THREADS + t;
+            const size_t i = first + (size_t)k * THREADS + t;
             stage_idx[slot] = (uint32_t)i | (e[k] & 0x80000000u);
             stage_lo[slot] = (uint16_t)(b & lo_mask);
             stage_p[slot] = (uint16_t)p;
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(SNARKV_SORT_THREADS) k_partition(const uint32_
         __syncthreads();
         uint32_t* out_idx = rec_idx + (size_t)w * nv;
         uint16_t* out_lo = rec_lo + (size_t)w * nv;
-        for (uint32_t slot = t; slot < total; slot += SNARKV_SORT_THREADS) {
+        for (uint32_t slot = t; slot < total; slot += THREADS) {
             const uint32_t p = stage_p[slot];
             const uint32_t pos = gbase[p] + (slot - loff[p]);
             out_idx[pos] = stage_idx[slot];

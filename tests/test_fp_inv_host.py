@@ -39,10 +39,11 @@ def test_binary_gcd_inverse_matches_python(tmp_path):
 
 def test_generated_ptx_blocks_pass_cpu_emulation():
     out = subprocess.run([sys.executable, os.path.join(CSRC, "gen_field_ptx.py"), "--selftest"], capture_output=True, text=True)
-    assert out.returncode == 0 and out.stdout.count("ok") == 2, out.stdout + out.stderr
+    assert out.returncode == 0 and out.stdout.count("ok") == 4, out.stdout + out.stderr   # BN254 Fq / Fr + Pallas base / scalar field
 
 
 def test_committed_generated_headers_are_current():
-    for gen, inc in (("gen_field_ptx.py", "fp_ptx.inc"), ("gen_pairing_consts.py", "pairing_consts.inc")):
-        out = subprocess.run([sys.executable, os.path.join(CSRC, gen)], capture_output=True, text=True, check=True).stdout
+    for gen, inc, args in (("gen_field_ptx.py", "fp_ptx.inc", []), ("gen_field_ptx.py", "fp_ptx_pallas.inc", ["--curve=pallas"]),
+                           ("gen_pairing_consts.py", "pairing_consts.inc", []), ("gen_poseidon_consts.py", "poseidon_consts.inc", [])):
+        out = subprocess.run([sys.executable, os.path.join(CSRC, gen)] + args, capture_output=True, text=True, check=True).stdout
         assert out == open(os.path.join(CSRC, inc)).read(), inc + " is stale: regenerate"
