@@ -121,6 +121,7 @@ int snarkv_init(int device, snarkv_ctx** out) {
     if (c->bc_r != 8 && c->bc_r != 12) c->bc_r = 16;
     c->bc_auto = env_int("SNARKV_BC_AUTO", 0, 1, c->bc_auto);
     c->bc_min_load = env_int("SNARKV_BC_MIN_LOAD", 1, 1 << 20, c->bc_min_load);
+    c->pf_max_per_sm = env_int("SNARKV_PAIRING_FAST_MAX", 0, 1 << 20, c->pf_max_per_sm);
     *out = c;
     return SNARKV_OK;
 }
@@ -162,7 +163,7 @@ int snarkv_set_glv_mode(snarkv_ctx* ctx, int mode) {
 }
 
 int snarkv_set_pairing_mode(snarkv_ctx* ctx, int mode) {
-    if (!ctx || mode < 0 || mode > 4) return SNARKV_ERR_USAGE;
+    if (!ctx || mode < 0 || mode > 5) return SNARKV_ERR_USAGE;
     ctx->pairing_mode = mode;
     return SNARKV_OK;
 }

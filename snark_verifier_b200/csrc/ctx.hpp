@@ -76,7 +76,7 @@ struct snarkv_ctx {
     std::string err;
     int window_bits = 0;
     int glv_mode = 0;       // 0 = GLV for n < 2^22 (default), 1 = always, 2 = never
-    int pairing_mode = 0;   // 0 = choose from N, 1 = one thread per check, 2 = one block per check
+    int pairing_mode = 0;   // 0 = choose from N, 1 = one thread per check, 2 = first cooperative kernels (block or warp per check by N), 3 = block (160 threads), 4 = warp, 5 = latency kernel (pairing_fast.cu)
     int sort_blocks_per_sm = 0;   // SNARKV_SORT_BLOCKS: resident k_partition blocks per SM (0 = default)
     int sort_tile = 8192;   // SNARKV_SORT_TILE: digits per k_partition work item (4096 | 8192); measured at 2^24: 1.30 vs 1.20 ms (profiles/r02_sort_tile_probe.txt)
     int host_chunk_min_log_n = 20, host_chunks_small = 3;   // SNARKV_HOST_CHUNK_MIN / SNARKV_HOST_CHUNKS_SMALL: chunk pipeline for inputs of 2^min .. 2^22 terms
@@ -104,6 +104,9 @@ struct snarkv_ctx {
     bool has_key = false;
     void* d_key_coeffs = nullptr;   // 2 x NUM_COEFFS x 3 x Fq2 line coefficients (Montgomery)
     int key_num_coeffs = 0;
+    void* d_key_tables = nullptr;   // merged two-pair line constants per Miller step (pairing_fast.cu): 3 x NUM_COEFFS x 32 Fq words
+    int pf_blocks_per_sm = 0;       // occupancy of k_kzg_decide_fast (queried once)
+    int pf_max_per_sm = 2;          // SNARKV_PAIRING_FAST_MAX: automatic mode gives a check a whole block up to this many checks per SM
     uint8_t key_g1[64] = {};
 
     int fail(int code, const char* what, cudaError_t ce = cudaSuccess) {
@@ -222,6 +225,8 @@ int synth_points_device(snarkv_ctx* ctx, uint64_t seed, uint64_t start, size_t n
 int kzg_set_key(snarkv_ctx* ctx, const uint8_t g1[64], const uint8_t g2[128], const uint8_t s_g2[128]);
 int kzg_decide_device(snarkv_ctx* ctx, const void* d_lhs, const void* d_rhs, size_t N, int format, void* d_accept, void* d_gt);
 int kzg_decide_coop_device(snarkv_ctx* ctx, const void* d_lhs, const void* d_rhs, size_t N, int format, void* d_accept, void* d_gt);
+int kzg_decide_fast_device(snarkv_ctx* ctx, const void* d_lhs, const void* d_rhs, size_t N, int format, void* d_accept, void* d_gt);
+int kzg_build_pair_tables(snarkv_ctx* ctx);
 void kzg_free_key(snarkv_ctx* ctx);
 
 }  // namespace snarkv

@@ -217,6 +217,8 @@ __global__ void __launch_bounds__(64) k_final_exp(const Fq12* __restrict__ f_in,
 void kzg_free_key(snarkv_ctx* ctx) {
     if (ctx->d_key_coeffs) cudaFree(ctx->d_key_coeffs);
     ctx->d_key_coeffs = nullptr;
+    if (ctx->d_key_tables) cudaFree(ctx->d_key_tables);
+    ctx->d_key_tables = nullptr;
     ctx->has_key = false;
 }
 
@@ -238,6 +240,10 @@ int kzg_set_key(snarkv_ctx* ctx, const uint8_t g1[64], const uint8_t g2[128], co
     k_g2_prepare<<<1, 32, 0, st>>>(d_stage, base, d_inf, d_status);
     SNARKV_LAUNCH_CHECK(ctx, "k_g2_prepare");
     ctx->launches++;
+    {   // merged two-pair line constants for the latency kernel (pairing_fast.cu); rows of a key at infinity are never read
+        const int rc = kzg_build_pair_tables(ctx);
+        if (rc) return rc;
+    }
     int status = 0;
     SNARKV_CUDA_TRY(ctx, cudaMemcpyAsync(&status, d_status, 4, cudaMemcpyDeviceToHost, st));
     SNARKV_CUDA_TRY(ctx, cudaStreamSynchronize(st));
@@ -253,6 +259,9 @@ int kzg_decide_device(snarkv_ctx* ctx, const void* d_lhs, const void* d_rhs, siz
     // a whole thread block instead (pairing_coop.cu).  Very large batches fill the machine either way; keep the leaner kernel.
     // modes: 0 auto, 1 thread per check, 2 cooperative (block or warp per check by N), 3 block per check, 4 warp per check
     // measured crossover on B200 (profiles/r01_pairing_modes.txt): warp-per-check 395 K checks/s vs thread-per-check 13.9 ms flat
+    // mode 5 / small N: the latency kernel (pairing_fast.cu) — one 256-thread block per check
+    if (ctx->pairing_mode == 5 || (ctx->pairing_mode == 0 && N <= (size_t)ctx->sm_count * ctx->pf_max_per_sm))
+        return kzg_decide_fast_device(ctx, d_lhs, d_rhs, N, format, d_accept, d_gt);
     const bool coop = ctx->pairing_mode >= 2 || (ctx->pairing_mode == 0 && N <= (size_t)ctx->sm_count * 37);
     if (coop) return kzg_decide_coop_device(ctx, d_lhs, d_rhs, N, format, d_accept, d_gt);
     Fq12* f = (Fq12*)ctx->wsget(WS_PAIR_A, N * sizeof(Fq12));

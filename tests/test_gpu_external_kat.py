@@ -38,7 +38,7 @@ def test_eip196_scalar_mul_and_add_on_device(loader, golden):
         assert loader.msm(le(1) * 2, a + b, 2) == exp, v["name"]
 
 
-@pytest.mark.parametrize("mode", [1, 3, 4], ids=["thread_per_check", "block_per_check", "warp_per_check"])
+@pytest.mark.parametrize("mode", [1, 3, 4, 5], ids=["thread_per_check", "block_per_check", "warp_per_check", "latency_kernel"])
 def test_eip197_pairing_vectors_on_device(golden, mode):
     """e(P1, Q1) e(P2, Q2) = 1 as a KZG decision with g2 = Q1, s_g2 = -Q2 (decider.rs:74-78); arbitrary G2 keys exercise
     k_g2_prepare on operands that are not multiples chosen by this repository.  Reject twin: P2 negated."""

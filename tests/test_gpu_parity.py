@@ -266,7 +266,7 @@ def kzg(loader, golden):
     return sv.KzgAs(loader, dk)
 
 
-@pytest.fixture(params=[1, 3, 4], ids=["thread_per_check", "block_per_check", "warp_per_check"])
+@pytest.fixture(params=[1, 3, 4, 5], ids=["thread_per_check", "block_per_check", "warp_per_check", "latency_kernel"])
 def pairing_mode(request, loader):
     loader.set_pairing_mode(request.param)
     yield request.param
@@ -321,6 +321,34 @@ def test_decide_batch_vs_oracle_random_mix(kzg, golden, pairing_mode):
 def test_decide_rejects_off_curve_accumulator(kzg, pairing_mode):
     acc, _ = kzg.decide_batch(le(1) + le(3), m.g1_to_bytes(m.G1_GEN), 1)
     assert acc == b"\x00"
+
+
+def test_latency_kernel_dead_pairs_and_grid_stride(kzg, golden, loader):
+    """pairing_fast.cu against the thread-per-check kernels: identity on either side (the merged-line tables have one row set per
+    live-pair case), both sides identity, and more checks than resident blocks (grid-stride reuse of the shared-memory state)."""
+    g = golden("pairing")
+    s = int.from_bytes(H(g["s"]), "little")
+    gen = m.g1_to_bytes(m.G1_GEN)
+    n = 700
+    lhs, rhs = [], []
+    for i in range(n):
+        a = 1000003 * i + 17
+        l = oracle.g1_mul(gen, le((a * s + (1 if i % 5 == 2 else 0)) % m.R))
+        r = oracle.g1_mul(gen, le(a))
+        if i % 7 == 3: l = bytes(64)
+        if i % 11 == 4: r = bytes(64)
+        lhs.append(l); rhs.append(r)
+    lhs, rhs = b"".join(lhs), b"".join(rhs)
+    loader.set_pairing_mode(1)
+    acc1, gt1 = kzg.decide_batch(lhs, rhs, n, want_gt=True)
+    loader.set_pairing_mode(5)
+    acc5, gt5 = kzg.decide_batch(lhs, rhs, n, want_gt=True)
+    loader.set_pairing_mode(0)
+    assert acc5 == acc1 and gt5 == gt1
+    both = [i for i in range(n) if i % 7 == 3 and i % 11 == 4]
+    assert both and all(acc5[i] == 1 for i in both)            # e(O, .) e(O, .) = 1
+    oacc, ogt = oracle.kzg_decide_batch(lhs[:64 * 48], rhs[:64 * 48], 48, H(g["g2_generator"]), H(g["s_g2"]), threads=8, hoist=0, want_gt=True)
+    assert acc5[:48] == oacc and gt5[:384 * 48] == ogt
 
 
 def test_decide_needs_key():
@@ -504,7 +532,7 @@ def test_decide_and_accumulate_in_montgomery_layout(mont_loader, golden):
     kz = sv.KzgAs(mont_loader, sv.KzgDecidingKey(m.g1_to_bytes(m.G1_GEN), H(g["g2_generator"]), H(g["s_g2"])))   # key is always canonical
     checks = g["checks"]
     lhs = to_mont_pts(b"".join(H(c["lhs"]) for c in checks)); rhs = to_mont_pts(b"".join(H(c["rhs"]) for c in checks))
-    for mode in (1, 3, 4):
+    for mode in (1, 3, 4, 5):
         mont_loader.set_pairing_mode(mode)
         acc, gt = kz.decide_batch(lhs, rhs, len(checks), want_gt=True)
         assert list(acc) == [int(c["accept"]) for c in checks]

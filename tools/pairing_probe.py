@@ -11,9 +11,10 @@ n = 1 << 17
 pts = torch.empty(n * 64, dtype=torch.uint8, device="cuda"); acc = torch.zeros(n, dtype=torch.uint8, device="cuda")
 L.synth_points_device(7, 0, n, pts.data_ptr())
 L.profile(True)
-for mode, name in ((1, "thread"), (3, "block"), (4, "warp"), (0, "auto")):
+for mode, name in ((5, "fast"), (1, "thread"), (3, "block"), (4, "warp"), (0, "auto")):
     L.set_pairing_mode(mode)
-    for cnt in (1, 444, 1024, 2368, 4096, 1 << 14, 1 << 16, 1 << 17):
+    for cnt in (1, 148, 296, 444, 1024, 2368, 4096, 1 << 14, 1 << 16, 1 << 17):
+        if mode in (3, 5) and cnt > 16384: continue
         if mode == 3 and cnt > 4096: continue
         for _ in range(2):
             kz.decide_batch_device(pts.data_ptr(), pts.data_ptr(), cnt, acc.data_ptr()); torch.cuda.synchronize()
