@@ -69,6 +69,36 @@ int msm_batch_rlc_host(snarkv_ctx* ctx, const uint8_t* scalars, const uint8_t* p
     if (out_affine) memcpy(out_affine, host, 64);
     return SNARKV_OK;
 }
+
+// Child context for a second concurrent MSM: own stream, own (grow-only) workspace, same device and tuning knobs.
+snarkv_ctx* ctx_aux(snarkv_ctx* ctx) {
+    if (ctx->aux) {
+        snarkv_ctx* a = ctx->aux;   // knobs may have been changed through the C ABI since the child was made
+        a->window_bits = ctx->window_bits; a->glv_mode = ctx->glv_mode; a->accumulate_mode = ctx->accumulate_mode;
+        return a;
+    }
+    snarkv_ctx* a = new (std::nothrow) snarkv_ctx();
+    if (!a) { ctx->fail(SNARKV_ERR_CUDA, "child context allocation"); return nullptr; }
+    a->device = ctx->device;
+    a->sm_count = ctx->sm_count;
+    cudaError_t ce = cudaStreamCreateWithFlags(&a->own_stream, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&ctx->join_ev, cudaEventDisableTiming);
+    if (ce != cudaSuccess) {
+        if (a->own_stream) cudaStreamDestroy(a->own_stream);
+        if (ctx->fork_ev) { cudaEventDestroy(ctx->fork_ev); ctx->fork_ev = nullptr; }
+        delete a;
+        ctx->fail(SNARKV_ERR_CUDA, "child context stream / events", ce);
+        return nullptr;
+    }
+    a->stream = a->own_stream;
+    a->window_bits = ctx->window_bits; a->glv_mode = ctx->glv_mode; a->accumulate_mode = ctx->accumulate_mode;
+    a->sort_blocks_per_sm = ctx->sort_blocks_per_sm; a->sort_tile = ctx->sort_tile;
+    a->ba_k = ctx->ba_k; a->ba_pairs_min = ctx->ba_pairs_min; a->ba_q = ctx->ba_q; a->ba_min_load = ctx->ba_min_load;
+    a->bc_r = ctx->bc_r; a->bc_auto = ctx->bc_auto; a->bc_min_load = ctx->bc_min_load;
+    ctx->aux = a;
+    return a;
+}
 }  // namespace snarkv
 
 extern "C" {
@@ -122,6 +152,7 @@ int snarkv_init(int device, snarkv_ctx** out) {
     c->bc_auto = env_int("SNARKV_BC_AUTO", 0, 1, c->bc_auto);
     c->bc_min_load = env_int("SNARKV_BC_MIN_LOAD", 1, 1 << 20, c->bc_min_load);
     c->pf_max_per_sm = env_int("SNARKV_PAIRING_FAST_MAX", 0, 1 << 20, c->pf_max_per_sm);
+    c->overlap_msms = env_int("SNARKV_OVERLAP_MSMS", 0, 1, c->overlap_msms);
     *out = c;
     return SNARKV_OK;
 }
@@ -131,6 +162,16 @@ void snarkv_destroy(snarkv_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     kzg_free_key(ctx);
+    if (ctx->aux) {
+        for (int i = 0; i < WS_SLOTS; ++i)
+            if (ctx->aux->ws[i]) cudaFree(ctx->aux->ws[i]);
+        for (cudaEvent_t e : ctx->aux->event_pool) cudaEventDestroy(e);
+        if (ctx->aux->own_stream) cudaStreamDestroy(ctx->aux->own_stream);
+        delete ctx->aux;
+        ctx->aux = nullptr;
+    }
+    if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
+    if (ctx->join_ev) cudaEventDestroy(ctx->join_ev);
     if (ctx->d_ipa_g) cudaFree(ctx->d_ipa_g);
     for (int i = 0; i < WS_SLOTS; ++i)
         if (ctx->ws[i]) cudaFree(ctx->ws[i]);

@@ -100,6 +100,12 @@ struct snarkv_ctx {
     void* d_ipa_g = nullptr;
     size_t ipa_n = 0;
 
+    // Child context: its own stream and workspace slots, so that a second, independent MSM can run concurrently with one on this
+    // context (the lhs / rhs MSMs of the fused PLONK batch, plonk_batch.cu).  Created on first use by ctx_aux(), tuning knobs copied.
+    snarkv_ctx* aux = nullptr;
+    cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+    int overlap_msms = 1;   // SNARKV_OVERLAP_MSMS: 0 = run the two MSMs of the fused PLONK batch one after the other
+
     // KZG deciding key (pairing.cu)
     bool has_key = false;
     void* d_key_coeffs = nullptr;   // 2 x NUM_COEFFS x 3 x Fq2 line coefficients (Montgomery)
@@ -227,6 +233,7 @@ int kzg_decide_device(snarkv_ctx* ctx, const void* d_lhs, const void* d_rhs, siz
 int kzg_decide_coop_device(snarkv_ctx* ctx, const void* d_lhs, const void* d_rhs, size_t N, int format, void* d_accept, void* d_gt);
 int kzg_decide_fast_device(snarkv_ctx* ctx, const void* d_lhs, const void* d_rhs, size_t N, int format, void* d_accept, void* d_gt);
 int kzg_build_pair_tables(snarkv_ctx* ctx);
+snarkv_ctx* ctx_aux(snarkv_ctx* ctx);   // capi.cu: the child context (nullptr + ctx->err on failure)
 void kzg_free_key(snarkv_ctx* ctx);
 
 }  // namespace snarkv
