@@ -23,7 +23,7 @@
 //     + one Fq inversion instead of ~100 serial multiplications.
 //
 // The index arithmetic of this file (term map, Frobenius signs, line slots, digit chains) is emulated thread by thread over
-// exact integers in oracle/pairing_fast_model.py and checked against the independent pairing model (tests/test_pairing_fast_model.py).
+// exact integers by the test-side model pairing_fast_model.py and checked against the independent pairing model (tests/test_pairing_fast_model.py).
 #include "ctx.hpp"
 #include "g1.cuh"
 #define SNARKV_TOWER_SERIAL_INV 1
