@@ -32,6 +32,13 @@ def test_decomposition_matches_identity_and_bounds(tmp_path):
     rnd = random.Random(9)
     cases = [0, 1, 2, 3, m.R - 1, m.R - 2, LAMBDA, m.R - LAMBDA, (m.R - 1) // 2, 1 << 253, (1 << 128) - 1, 1 << 128]
     cases += [rnd.randrange(m.R) for _ in range(20000)]
+    # adversarial: scalars whose quotients k b2 / r, k |b1| / r sit next to a rounding boundary (largest residuals)
+    B2, B1ABS = 0x6F4D8248EEB859FD0BE4E1541221250B, 0x89D3256894D213E3
+    for den in (B2, B1ABS):
+        for _ in range(2000):
+            j = rnd.randrange(den)
+            k0 = ((2 * j + 1) * m.R) // (2 * den)
+            cases += [(k0 + d) % m.R for d in (-1, 0, 1)]
     worst = 0
     for k in cases:
         out = (ctypes.c_uint32 * 12)()
