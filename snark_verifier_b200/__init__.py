@@ -18,7 +18,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsnarkv_cuda.so")
+# SNARKV_LIB_VARIANT=<name> (developer knob, tools/ A/B probes): load libsnarkv_cuda_<name>.so built by `make variant V=<name> DEFS=...`
+LIB_PATH = os.path.join(_HERE, "libsnarkv_cuda%s.so" % ("_" + os.environ["SNARKV_LIB_VARIANT"] if os.environ.get("SNARKV_LIB_VARIANT") else ""))
 
 CANONICAL, MONTGOMERY = 0, 1
 CHECK_INPUTS = 1

@@ -35,6 +35,11 @@ enum Field : int { FQ = 0, FR = 1 };
     : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),    \
       "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7])
 
+#define SNARKV_FP_OPS1(r, a)                                                                                     \
+    : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]),          \
+      "=r"(r.v[7])                                                                                               \
+    : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7])
+
 template <Field F>
 struct alignas(16) Fp {
     uint32_t v[8];
@@ -125,10 +130,13 @@ template <Field F> __device__ __forceinline__ bool fp_eq(const Fp<F>& a, const F
 }
 // canonical integer (< m) -> Montgomery form, and back
 template <Field F> __device__ __forceinline__ Fp<F> fp_to_mont(const Fp<F>& a) { return fp_mul(a, fp_r2<F>()); }
+// a / 2^256 mod m: the Montgomery reduction alone (generated FROM_MONT block: the products by the constant 1 are moves / carry
+// chains, half the multiplier work of fp_mul(a, 1) — k_digits converts every scalar of a Montgomery-format MSM with it)
 template <Field F> __device__ __forceinline__ Fp<F> fp_from_mont(const Fp<F>& a) {
-    Fp<F> one = fp_zero<F>();
-    one.v[0] = 1;
-    return fp_mul(a, one);
+    Fp<F> r;
+    if constexpr (F == FQ) asm(SNARKV_PTX_FQ_FROM_MONT SNARKV_FP_OPS1(r, a));
+    else asm(SNARKV_PTX_FR_FROM_MONT SNARKV_FP_OPS1(r, a));
+    return r;
 }
 // true iff the raw 256-bit value is a canonical residue (< m) — `PrimeField::from_repr` acceptance test
 template <Field F> __device__ __forceinline__ bool fp_is_canonical(const Fp<F>& a) {

@@ -111,24 +111,39 @@ class Prog:
         return env
 
 
-def gen_mont_mul(mod, a="a", b="b", out="r", reduce_final=True):
-    """r = a * b / 2^256 mod m  (fully reduced if reduce_final, else < 2m)."""
+def gen_mont_mul(mod, a="a", b="b", out="r", reduce_final=True, b_const=None):
+    """r = a * b / 2^256 mod m  (fully reduced if reduce_final, else < 2m).
+    b_const: list of 8 limbs, each 0 or 1 — b is that CONSTANT and every product by it degenerates to a move / an add-with-carry
+    (used for b = 1: r = a / 2^256 mod m, the conversion out of Montgomery form, at half the products of a multiplication)."""
     M = limbs(mod)
     m0inv = (-pow(mod, -1, 1 << 32)) & MASK
     p = Prog()
     A = [a + str(i) for i in range(8)]
-    B = [b + str(i) for i in range(8)]
+    B = [b + str(i) for i in range(8)] if b_const is None else list(b_const)
+    assert all(isinstance(x, str) or x in (0, 1) for x in B)
     E = [p.tmp("e%d" % i) for i in range(8)]
     O = [p.tmp("o%d" % i) for i in range(8)]
     mi = p.tmp("mi")
 
     def mul_n(acc, src_off, bi, src=A):
         for j in range(0, 8, 2):
+            if isinstance(bi, int):          # constant 0 / 1
+                if bi:
+                    p.emit("mov.u32", acc[j], src[j + src_off])
+                else:
+                    p.emit("mov.u32", acc[j], 0)
+                p.emit("mov.u32", acc[j + 1], 0)
+                continue
             p.emit("mul.lo.u32", acc[j], src[j + src_off], bi)
             p.emit("mul.hi.u32", acc[j + 1], src[j + src_off], bi)
 
     def cmad_n(acc, srcs, bi, carry_out=True):
         # acc(64-bit columns) += srcs[0,2,4,6] * bi, one carry chain; CF left set on exit iff carry_out
+        if isinstance(bi, int) and bi == 0:
+            if carry_out:                     # nothing to add: the chain only has to leave CF = 0
+                p.emit("add.cc.u32", acc[0], acc[0], 0)
+            return
+        assert not isinstance(bi, int)
         for k, j in enumerate(range(0, 8, 2)):
             p.emit("mad.lo.cc.u32" if k == 0 else "madc.lo.cc.u32", acc[j], bi, srcs[j], acc[j])
             last = (j == 6) and not carry_out
@@ -136,6 +151,13 @@ def gen_mont_mul(mod, a="a", b="b", out="r", reduce_final=True):
 
     def madc_n_rshift(odd, bi):
         # odd <- (odd >> 64) + A[1,3,5,7] * bi + CF
+        if isinstance(bi, int) and bi == 0:
+            for j in range(0, 6):
+                p.emit("addc.cc.u32", odd[j], odd[j + 2], 0)
+            p.emit("addc.cc.u32", odd[6], 0, 0)
+            p.emit("addc.u32", odd[7], 0, 0)
+            return
+        assert not isinstance(bi, int)
         for j in range(0, 6, 2):
             p.emit("madc.lo.cc.u32", odd[j], A[j + 1], bi, odd[j + 2])
             p.emit("madc.hi.cc.u32", odd[j + 1], A[j + 1], bi, odd[j + 3])
@@ -269,6 +291,7 @@ def selftest(iters=2000):
         pl, _, _, OUTL = gen_mont_mul(mod, reduce_final=False)
         pa, _, _, OA = gen_add_mod(mod)
         ps, _, _, OS = gen_sub_mod(mod)
+        pf, _, _, OF = gen_mont_mul(mod, b_const=[1, 0, 0, 0, 0, 0, 0, 0])
         edge = [0, 1, mod - 1, mod - 2, (1 << 254) % mod, Rm % mod]
         cases = [(x, y) for x in edge for y in edge] + [(rnd.randrange(mod), rnd.randrange(mod)) for _ in range(iters)]
         for x, y in cases:
@@ -277,6 +300,7 @@ def selftest(iters=2000):
             assert val_of(_emul(pm, env), OUT) == x * y * Rinv % mod, (name, "mul", hex(x), hex(y))
             assert val_of(_emul(pa, env), OA) == (x + y) % mod, (name, "add")
             assert val_of(_emul(ps, env), OS) == (x - y) % mod, (name, "sub")
+            assert val_of(_emul(pf, env), OF) == x * Rinv % mod, (name, "from_mont", hex(x))
         # lazy variant: inputs anywhere below 2m, output < 2m and congruent (BN254 only: needs m < 2^254)
         for _ in range(iters if mod < (1 << 254) else 0):
             x, y = rnd.randrange(2 * mod), rnd.randrange(2 * mod)
@@ -284,7 +308,7 @@ def selftest(iters=2000):
             env.update(env_of("a", x)); env.update(env_of("b", y))
             got = val_of(_emul(pl, env), OUTL)
             assert got < 2 * mod and got % mod == x * y * Rinv % mod, (name, "lazy mul")
-        print("selftest %s: %d mul/add/sub cases ok (%d PTX instructions per mul)" % (name, len(cases), len(pm.ins)))
+        print("selftest %s: %d mul/add/sub/from_mont cases ok (%d PTX instructions per mul, %d per from_mont)" % (name, len(cases), len(pm.ins), len(pf.ins)))
 
 
 def c_macro(name, lines):
@@ -313,6 +337,9 @@ def main():
             ops.insert(1, ("MUL_LAZY", gen_mont_mul(mod, reduce_final=False)))
         for tag, (p, A, B, OUT) in ops:
             out.append(c_macro("SNARKV_PTX_%s_%s" % (name, tag), _strip(p).render(OUT, A + B)))
+        # r = a / 2^256 mod m (out of Montgomery form): operands %0..%7 = r, %8..%15 = a
+        p, A, _, OUT = gen_mont_mul(mod, b_const=[1, 0, 0, 0, 0, 0, 0, 0])
+        out.append(c_macro("SNARKV_PTX_%s_FROM_MONT" % name, _strip(p).render(OUT, A)))
     sys.stdout.write("\n".join(out))
 
 
