@@ -41,6 +41,36 @@ TRAFFIC_JSON = os.path.join("profiles", "r02_traffic.json")
 KERNEL_SOURCES = ("msm.cu", "bucket_affine.cuh", "sort.cuh", "g1.cuh", "fp.cuh", "fp_ptx.inc")
 
 
+_saved_affinity = None
+
+
+def gpu_local_affinity(device_index):
+    """device_index = int: bind this process to the CPU cores NVML reports as local to that GPU (its NUMA node) and return a note for
+    the bench line; None: restore the affinity saved by the previous call.  Best effort: any failure leaves the process as it was."""
+    global _saved_affinity
+    try:
+        if device_index is None:
+            if _saved_affinity is not None:
+                os.sched_setaffinity(0, _saved_affinity)
+                _saved_affinity = None
+            return None
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        ncpu = os.cpu_count() or 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, v in enumerate(words) for b in range(64) if (int(v) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus:
+            return "no GPU-local cores reported"
+        _saved_affinity = allowed
+        os.sched_setaffinity(0, cpus)
+        return "pinned buffers first-touched on %d GPU-local cores of %d" % (len(cpus), len(allowed))
+    except Exception as e:  # noqa: BLE001 — NVML / affinity not available: measure as is
+        return "unavailable (%s)" % type(e).__name__
+
+
 def workload_name(log_n):
     """The ONE description of the workload both arms (--impl cuda / reference) print in config.workload."""
     return "BN254 G1 MSM, 2^%d uniformly random scalars x points [t_i]G (seed %d)" % (log_n, SEED)
@@ -718,10 +748,14 @@ def main():
         acc_kernel, acc_ms, acc_mulmods = "k_bucket_accumulate", stages.get("msm_bucket_accumulate", float("nan")), MADD_MULMODS
 
     # ---- end to end: pinned host buffers through the C-ABI host entry points ------------------------------------------
+    # The pinned buffers are allocated (first-touched) from the CPU cores next to this rank's GPU, so that with several ranks per
+    # box every H2D copy reads the memory of its own socket; the process affinity is restored right after.
+    numa_note = gpu_local_affinity(local_rank)
     h_s = torch.empty(n_local * 32, dtype=torch.uint8).pin_memory()
     h_p = torch.empty(n_local * 64, dtype=torch.uint8).pin_memory()
-    h_s.copy_(d_s); h_p.copy_(d_p)
     h_out = torch.empty(64, dtype=torch.uint8).pin_memory()
+    gpu_local_affinity(None)
+    h_s.copy_(d_s); h_p.copy_(d_p)
     torch.cuda.synchronize()
 
     def step_e2e():
@@ -792,6 +826,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Mscalar-mults/s", "h2d_bytes_per_step": n_local * 96 * world, "d2h_bytes_per_step": 64 * world,
                     "api": "snarkv_g1_msm (N=1) / snarkv_g1_msm_partial + all_gather + fold (N>1), pinned host buffers",
+                    "host_numa": numa_note,
                     "result_matches_device_path": res_e2e == res_dev},
             "gpu_launches": int(launches),
             "roofline": {"kernel": acc_kernel, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",

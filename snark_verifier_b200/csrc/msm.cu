@@ -42,8 +42,8 @@ struct MsmPlan {
 };
 // With GLV the pipeline sees nv = 2 n "virtual terms" (index i < n: P_i with k1, index n + i: phi(P_i) with k2) whose scalars
 // have 128 bits, so W = ceil(130 / c) windows instead of ceil(255 / c): the additions are the same in number, but the Horner
-// chain, the bucket reduction and the window sums are halved.  Worth it while those fixed costs matter and the window is 16 bits either way (n < 2^23); above, a
-// larger window (c = 17, 15 windows) saves more additions than GLV saves tail.
+// chain, the bucket reduction and the window sums are halved.  Worth it while those fixed costs matter (n < 2^22); above, a
+// larger window (c = 17, 15 windows) with long enough bucket lists for the batched-affine kernel saves more than GLV saves tail.
 static inline size_t plan_virtual_terms(const MsmPlan& p, size_t n) { return p.glv ? 2 * n : n; }
 
 static int choose_window_bits(size_t n, bool glv) {
@@ -60,13 +60,15 @@ static int choose_window_bits(size_t n, bool glv) {
     if (n < (1u << 12)) return 8;
     if (n < (1u << 17)) return 13;
     if (n < (1u << 20)) return 15;
-    if (n < (1u << 23)) return 16;
+    if (n < (1u << 22)) return 16;
     return 17;
 }
 
 static MsmPlan make_plan(size_t n_terms, int c_override, int glv_mode) {
     MsmPlan p;
-    p.glv = (glv_mode == 1 || (glv_mode == 0 && n_terms < ((size_t)1 << 23))) ? 1u : 0u;
+    // measured plan table (tools/plan_sweep.py, profiles/r02_plan_sweep.txt): GLV wins up to 2^21 terms; from 2^22 on the plain
+    // c = 17 plan with the batched-affine kernel is faster (2^22: 12.0 vs 12.5 ms)
+    p.glv = (glv_mode == 1 || (glv_mode == 0 && n_terms < ((size_t)1 << 22))) ? 1u : 0u;
 #ifdef SNARKV_CURVE_PALLAS
     p.glv = 0;   // glv.cuh holds BN254's lattice; the Pallas build runs the plain pipeline
 #endif
