@@ -98,37 +98,68 @@ __global__ void __launch_bounds__(64) k_poseidon_transcript(const uint8_t* __res
     }
 }
 
-// The same transcript with the state spread over lanes: one proof per group of 8 lanes, lane g < 5 holds state[g].  A round costs 3
-// multiplications of latency for the S-box (every lane; in a partial round only lane 0 keeps its result) + 5 for its MDS row,
-// instead of 15 (3) + 25 in one thread: ~3x shorter critical path, which is what bounds a batch of a few thousand proofs
-// (one thread per proof leaves the SMs almost idle: measured 11 ms for 4096 proofs of ~60 elements).
-__device__ __forceinline__ Fr fr_shfl8(const Fr& a, int src) {
+// The same transcript with the state spread over lanes: one proof per group of FIVE lanes (six proofs per warp, lanes 30 / 31 shadow
+// lanes 25 / 26), lane g holds state[g].  One thread per proof leaves the SMs almost idle at a few thousand proofs (11 ms for 4096 proofs
+// of ~60 elements); the first lane version (groups of 8, S-box on every lane, one MDS row per lane: 8 multiplication steps per round)
+// took 4.1 ms and was bound by the multiplier SLOTS it occupies (8 lanes x 8 steps x 68 rounds per permutation).  Here a full round is
+// still 3 (S-box) + 5 (MDS row) steps, but a PARTIAL round — 60 of the 68 — takes 6: while lane 0 runs its S-box (x^2, x^4, x^5), lanes
+// 1..4 multiply what does not depend on it — lane j first the entry M[0][j] x_j of lane 0's row, then M[j][1..4] x_1..4 of its own —
+// and one last step multiplies column 0 by the fresh x_0^5 on every lane: 5 lanes x (60 x 6 + 8 x 8) slots per permutation, 2.05 x fewer.
+__device__ __forceinline__ Fr fr_shfl(const Fr& a, int src) {
     Fr r;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) r.v[k] = __shfl_sync(0xffffffffu, a.v[k], src, 8);
+    for (int k = 0; k < 8; ++k) r.v[k] = __shfl_sync(0xffffffffu, a.v[k], src);
     return r;
 }
-__device__ void poseidon_permute_lanes(Fr& s, uint32_t g) {
+__device__ __forceinline__ Fr fr_sel(bool c, const Fr& a, const Fr& b) {
+    Fr r;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r.v[k] = c ? a.v[k] : b.v[k];
+    return r;
+}
+__device__ void poseidon_permute_lanes(Fr& s, uint32_t g, int base) {
     constexpr int T = SNARKV_POSEIDON_T, RF = SNARKV_POSEIDON_RF, RP = SNARKV_POSEIDON_RP;
-    const uint32_t gi = g < (uint32_t)T ? g : 0u;           // lanes 5..7 mirror lane 0's constants and discard everything
+    const bool z = g == 0;
 #pragma unroll 1
     for (int r = 0; r < RF + RP; ++r) {
-        s = fp_add(s, fr_const(POSEIDON_RC[r * T + gi]));
-        const Fr p5 = fr_pow5(s);
-        if (r < RF / 2 || r >= RF / 2 + RP || g == 0) s = p5;
-        Fr acc = fp_mul(fr_const(POSEIDON_MDS[gi * T]), fr_shfl8(s, 0));
+        const Fr x = fp_add(s, fr_const(POSEIDON_RC[r * T + g]));
+        if (r < RF / 2 || r >= RF / 2 + RP) {   // full round (warp-uniform)
+            const Fr y = fr_pow5(x);
+            Fr acc = fp_mul(fr_const(POSEIDON_MDS[g * T]), fr_shfl(y, base));
 #pragma unroll
-        for (int j = 1; j < T; ++j) acc = fp_add(acc, fp_mul(fr_const(POSEIDON_MDS[gi * T + j]), fr_shfl8(s, j)));
-        s = acc;
+            for (int j = 1; j < T; ++j) acc = fp_add(acc, fp_mul(fr_const(POSEIDON_MDS[g * T + j]), fr_shfl(y, base + j)));
+            s = acc;
+        } else {                                // partial round: only x_0 goes through the S-box
+            const Fr x1 = fr_shfl(x, base + 1), x2 = fr_shfl(x, base + 2), x3 = fr_shfl(x, base + 3), x4 = fr_shfl(x, base + 4);
+            // step 1   lane 0: x^2            lane j: M[0][j] x_j  (an entry of lane 0's row)
+            const Fr t1 = fp_mul(fr_sel(z, x, fr_const(POSEIDON_MDS[g])), x);
+            // step 2   lane 0: x^4            lane j: M[j][1] x_1
+            const Fr t2 = fp_mul(fr_sel(z, t1, fr_const(POSEIDON_MDS[g * T + 1])), fr_sel(z, t1, x1));
+            // step 3   lane 0: x^5            lane j: M[j][2] x_2
+            const Fr t3 = fp_mul(fr_sel(z, t2, fr_const(POSEIDON_MDS[g * T + 2])), fr_sel(z, x, x2));
+            // steps 4, 5   lane j: M[j][3] x_3, M[j][4] x_4  (lane 0 idles along)
+            const Fr t4 = fp_mul(fr_const(POSEIDON_MDS[g * T + 3]), x3);
+            const Fr t5 = fp_mul(fr_const(POSEIDON_MDS[g * T + 4]), x4);
+            // step 6   every lane: M[g][0] x_0^5
+            const Fr q = fp_mul(fr_const(POSEIDON_MDS[g * T]), fr_shfl(t3, base));
+            const Fr row0 = fp_add(fp_add(fr_shfl(t1, base + 1), fr_shfl(t1, base + 2)), fp_add(fr_shfl(t1, base + 3), fr_shfl(t1, base + 4)));
+            const Fr own = fp_add(fp_add(t2, t3), fp_add(t4, t5));
+            s = fp_add(q, fr_sel(z, row0, own));
+        }
     }
 }
+#define SNARKV_POSEIDON_GROUPS_PER_WARP 6
 __global__ void __launch_bounds__(128) k_poseidon_transcript_lanes(const uint8_t* __restrict__ elements, size_t stream_len,
                                                                    const uint32_t* __restrict__ seg_end, uint32_t k, size_t m, int format,
                                                                    uint8_t* __restrict__ out) {
-    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t jj = t >> 3;
-    const uint32_t g = (uint32_t)(t & 7u);
-    const size_t j = jj < m ? jj : m - 1;                  // surplus groups of the last warp replay the last proof (shuffles need every lane)
+    const uint32_t lane = threadIdx.x & 31u;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const bool shadow = lane >= 30u;                          // lanes 30, 31 replay lanes 25, 26 (shuffles need every lane) and store nothing
+    const uint32_t grp = shadow ? 5u : lane / 5u;
+    const uint32_t g = shadow ? lane - 30u : lane - grp * 5u;
+    const int base = (int)(grp * 5u);
+    const size_t jj = warp * SNARKV_POSEIDON_GROUPS_PER_WARP + grp;
+    const size_t j = jj < m ? jj : m - 1;                     // surplus groups of the last warp replay the last proof
     constexpr uint32_t RATE = SNARKV_POSEIDON_T - 1;
     const uint8_t* st = elements + j * stream_len * 32;
     Fr s = fp_zero<FR>();
@@ -147,7 +178,7 @@ __global__ void __launch_bounds__(128) k_poseidon_transcript_lanes(const uint8_t
             if (c == chunks - 1 && len % RATE != 0 && cnt == 0) break;
             if (c == chunks - 1 && len % RATE == 0) {
                 if (g == 1) s = fp_add(s, fp_one<FR>());                            // the `exact` permutation on an empty chunk
-            } else if (g >= 1 && g <= RATE) {
+            } else if (g >= 1) {
                 if (g - 1 < cnt) {
                     Fr v = fp_load<FR>(st + (size_t)(pos + g - 1) * 32);
                     if (format == SNARKV_CANONICAL) v = fp_to_mont(v);
@@ -156,10 +187,10 @@ __global__ void __launch_bounds__(128) k_poseidon_transcript_lanes(const uint8_t
                     s = fp_add(s, fp_one<FR>());
                 }
             }
-            poseidon_permute_lanes(s, g);
+            poseidon_permute_lanes(s, g, base);
         }
         prev = e;
-        if (g == 1 && jj < m) {
+        if (g == 1 && !shadow && jj < m) {
             Fr c = s;
             if (format == SNARKV_CANONICAL) c = fp_from_mont(c);
             fp_store<FR>(out + (j * k + i) * 32, c);
@@ -319,9 +350,9 @@ int plonk_poseidon_expand_device(snarkv_ctx* ctx, const void* d_proofs, uint32_t
 
 int poseidon_transcript_device(snarkv_ctx* ctx, const void* d_elements, size_t stream_len, const void* d_seg_end, size_t k, size_t m, int format, void* d_out) {
     Stage sg(ctx, "poseidon_transcript");
-    // small and medium batches: one proof per 8 lanes (latency); huge batches: one proof per thread (throughput)
+    // small and medium batches: one proof per 5 lanes (latency); huge batches: one proof per thread (throughput)
     if (m <= ((size_t)1 << 16))
-        k_poseidon_transcript_lanes<<<(unsigned)((m * 8 + 127) / 128), 128, 0, ctx->stream>>>((const uint8_t*)d_elements, stream_len, (const uint32_t*)d_seg_end,
+        k_poseidon_transcript_lanes<<<(unsigned)((m + 4 * SNARKV_POSEIDON_GROUPS_PER_WARP - 1) / (4 * SNARKV_POSEIDON_GROUPS_PER_WARP)), 128, 0, ctx->stream>>>((const uint8_t*)d_elements, stream_len, (const uint32_t*)d_seg_end,
                                                                                             (uint32_t)k, m, format, (uint8_t*)d_out);
     else
         k_poseidon_transcript<<<(unsigned)((m + 63) / 64), 64, 0, ctx->stream>>>((const uint8_t*)d_elements, stream_len, (const uint32_t*)d_seg_end, (uint32_t)k, m,
