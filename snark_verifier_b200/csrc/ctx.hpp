@@ -83,7 +83,7 @@ struct snarkv_ctx {
     int host_chunks = 7, host_chunk_ratio_pct = 160;   // host entry pipeline: term-chunks of geometrically growing size (SNARKV_HOST_CHUNKS <= 7, SNARKV_HOST_RATIO in percent)
     int accumulate_mode = 0;   // 0 = choose from the bucket load, 1 = XYZZ, 2 = batched affine (tree), 3 = XYZZ + tree + task-level self-check, 4 = chained batched affine
     int ba_blocks_per_sm = 0;  // occupancy of k_bucket_accumulate_affine (queried once)
-    int ba_k = 128, ba_pairs_min = 12, ba_q = 4, ba_min_load = 48;   // batched-affine tuning (developer knobs: SNARKV_BA_K, _PAIRS_MIN, _Q, _MIN_LOAD)
+    int ba_k = 128, ba_pairs_min = 12, ba_q = 4, ba_min_load = 96;   // batched-affine tuning (developer knobs: SNARKV_BA_K, _PAIRS_MIN, _Q, _MIN_LOAD)
     int bc_r = 16, bc_blocks_per_sm = 0, bc_blocks_r = 0, bc_auto = 0, bc_min_load = 32;   // chained batched-affine kernel (SNARKV_BC_R in {8, 12, 16}, SNARKV_BC_AUTO, SNARKV_BC_MIN_LOAD)
     uint64_t launches = 0;
     int sm_count = 148;

@@ -72,7 +72,7 @@ static __device__ __noinline__ G1Xyzz xyzz_dbl_affine(const Fq& x, const Fq& y) 
     Fq xx = fp_sqr(x);
     Fq m = fp_add(fp_dbl(xx), xx);
     r.x = fp_sub(fp_sqr(m), fp_dbl(s));
-    r.y = fp_sub(fp_mul(m, fp_sub(s, r.x)), fp_mul(w, y));
+    r.y = fp_mul2add(m, fp_sub(s, r.x), fp_neg(w), y);   // m (s - x3) - w y under one reduction
     r.zz = v;
     r.zzz = w;
     return r;
@@ -89,13 +89,14 @@ __device__ __forceinline__ G1Xyzz xyzz_dbl(const G1Xyzz& p) {
     Fq xx = fp_sqr(p.x);
     Fq m = fp_add(fp_dbl(xx), xx);
     r.x = fp_sub(fp_sqr(m), fp_dbl(s));
-    r.y = fp_sub(fp_mul(m, fp_sub(s, r.x)), fp_mul(w, p.y));
+    r.y = fp_mul2add(m, fp_sub(s, r.x), fp_neg(w), p.y);
     r.zz = fp_mul(v, p.zz);
     r.zzz = fp_mul(w, p.zzz);
     return r;
 }
 
-// acc += (x2, y2), (x2, y2) affine and NOT the identity (madd-2008-s): 8M + 2S on the common path.
+// acc += (x2, y2), (x2, y2) affine and NOT the identity (madd-2008-s): 8M + 2S on the common path; the two squarings are the
+// dedicated SQR block and y3 is one dual-product block (fp_mul2add), i.e. 8.3 multiplications' worth of partial products.
 // Exceptional cases (empty accumulator, equal points, opposite points) are handled exactly.
 __device__ __forceinline__ void xyzz_madd(G1Xyzz& acc, const Fq& x2, const Fq& y2) {
     if (xyzz_is_identity(acc)) {
@@ -115,7 +116,7 @@ __device__ __forceinline__ void xyzz_madd(G1Xyzz& acc, const Fq& x2, const Fq& y
     Fq ppp = fp_mul(p, pp);
     Fq q = fp_mul(acc.x, pp);
     Fq x3 = fp_sub(fp_sub(fp_sqr(r), ppp), fp_dbl(q));
-    acc.y = fp_sub(fp_mul(r, fp_sub(q, x3)), fp_mul(acc.y, ppp));
+    acc.y = fp_mul2add(r, fp_sub(q, x3), fp_neg(acc.y), ppp);   // r (q - x3) - y1 ppp: two products, one reduction
     acc.x = x3;
     acc.zz = fp_mul(acc.zz, pp);
     acc.zzz = fp_mul(acc.zzz, ppp);
@@ -144,7 +145,7 @@ __device__ __forceinline__ G1Xyzz xyzz_add(const G1Xyzz& a, const G1Xyzz& b) {
     Fq q = fp_mul(u1, pp);
     G1Xyzz o;
     o.x = fp_sub(fp_sub(fp_sqr(r), ppp), fp_dbl(q));
-    o.y = fp_sub(fp_mul(r, fp_sub(q, o.x)), fp_mul(s1, ppp));
+    o.y = fp_mul2add(r, fp_sub(q, o.x), fp_neg(s1), ppp);
     o.zz = fp_mul(fp_mul(a.zz, b.zz), pp);
     o.zzz = fp_mul(fp_mul(a.zzz, b.zzz), ppp);
     return o;

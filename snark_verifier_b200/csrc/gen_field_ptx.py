@@ -99,6 +99,13 @@ class Prog:
             elif base == "and":
                 env[dst] = s[0] & s[1]
                 continue
+            elif base == "shl":
+                env[dst] = (s[0] << s[1]) & MASK
+                continue
+            elif base == "shf":       # shf.l.wrap.b32 d, lo, hi, n : high word of (hi:lo) << n
+                assert op == "shf.l.wrap.b32"
+                env[dst] = ((((s[1] << 32) | s[0]) << (s[2] & 31)) >> 32) & MASK
+                continue
             else:
                 raise ValueError(op)
             env[dst] = t & MASK
@@ -111,10 +118,12 @@ class Prog:
         return env
 
 
-def gen_mont_mul(mod, a="a", b="b", out="r", reduce_final=True, b_const=None):
+def gen_mont_mul(mod, a="a", b="b", out="r", reduce_final=True, b_const=None, second=None):
     """r = a * b / 2^256 mod m  (fully reduced if reduce_final, else < 2m).
     b_const: list of 8 limbs, each 0 or 1 — b is that CONSTANT and every product by it degenerates to a move / an add-with-carry
-    (used for b = 1: r = a / 2^256 mod m, the conversion out of Montgomery form, at half the products of a multiplication)."""
+    (used for b = 1: r = a / 2^256 mod m, the conversion out of Montgomery form, at half the products of a multiplication).
+    second = (c, d): r = (a * b + c * d) / 2^256 mod m — two products under ONE reduction (128 + 64 partial products instead of 256);
+    inputs must be fully reduced (< m < 2^254) for the row sums to stay below 2^288 (asserted by the emulator)."""
     M = limbs(mod)
     m0inv = (-pow(mod, -1, 1 << 32)) & MASK
     p = Prog()
@@ -164,6 +173,8 @@ def gen_mont_mul(mod, a="a", b="b", out="r", reduce_final=True, b_const=None):
         p.emit("madc.lo.cc.u32", odd[6], A[7], bi, 0)
         p.emit("madc.hi.u32", odd[7], A[7], bi, 0)
 
+    C2 = [second[0] + str(i) for i in range(8)] if second else None
+    D2 = [second[1] + str(i) for i in range(8)] if second else None
     even, odd = E, O
     for i in range(8):
         bi = B[i]
@@ -174,6 +185,12 @@ def gen_mont_mul(mod, a="a", b="b", out="r", reduce_final=True, b_const=None):
             p.emit("add.cc.u32", even[0], even[0], odd[1])
             madc_n_rshift(odd, bi)
             cmad_n(even, A, bi)
+            p.emit("addc.u32", odd[7], odd[7], 0)
+        if second:
+            # + c * d_i into the same window: odd limbs of c on the odd columns (cannot carry out of the window), even limbs on the
+            # even columns with the carry landing in odd[7]
+            cmad_n(odd, C2[1:] + [0], D2[i], carry_out=False)
+            cmad_n(even, C2, D2[i])
             p.emit("addc.u32", odd[7], odd[7], 0)
         p.emit("mul.lo.u32", mi, even[0], m0inv)
         # columns (1,2),(3,4),(5,6),(7,8): m1, m3, m5, m7; this chain cannot carry out (total < 2^288) — the
@@ -194,7 +211,111 @@ def gen_mont_mul(mod, a="a", b="b", out="r", reduce_final=True, b_const=None):
     else:
         for k in range(8):
             p.emit("mov.u32", OUT[k], Rr[k])
+    if second:
+        return p, A, B, C2, D2, OUT
     return p, A, B, OUT
+
+
+def gen_mont_sqr(mod, a="a", out="r", reduce_final=True):
+    """r = a * a / 2^256 mod m with 36 + 64 instead of 64 + 64 partial products (inputs < 2m < 2^255).
+    Same interleaved operand scanning as gen_mont_mul, with every unordered pair of limbs assigned to the EARLIER row: row i multiplies
+    a_i by C_i = a_i 2^(32 i) + 2 (a_{i+1} 2^(32 (i+1)) + ... + a_7 2^(32 7)), whose limbs are a_i, a_{i+1} << 1, then the limbs of 2a
+    (d_j = a_j << 1 | a_{j-1} >> 31); limbs below i are zero and their products become carry propagation.  Row sums stay below 2^288
+    (the emulator asserts that no carry is ever dropped)."""
+    M = limbs(mod)
+    m0inv = (-pow(mod, -1, 1 << 32)) & MASK
+    p = Prog()
+    A = [a + str(i) for i in range(8)]
+    E = [p.tmp("e%d" % i) for i in range(8)]
+    O = [p.tmp("o%d" % i) for i in range(8)]
+    D = [None] + [p.tmp("d%d" % i) for i in range(1, 8)]     # limbs of 2a (d_8 = a_7 >> 31 = 0 for a < 2^255)
+    S = [None] + [p.tmp("h%d" % i) for i in range(1, 8)]     # a_j << 1 (the limb right above a_i in C_i)
+    mi = p.tmp("mi")
+    for j in range(1, 8):
+        p.emit("shf.l.wrap.b32", D[j], A[j - 1], A[j], 1)
+        p.emit("shl.b32", S[j], A[j], 1)
+
+    def row_vec(i):
+        v = [0] * 8
+        v[i] = A[i]
+        if i + 1 < 8:
+            v[i + 1] = S[i + 1]
+        for j in range(i + 2, 8):
+            v[j] = D[j]
+        return v
+
+    def cmad_sparse(acc, srcs, bi, carry_out=True):
+        # acc(64-bit columns at limbs (0,1),(2,3),(4,5),(6,7)) += srcs[0,2,4,6] * bi; zero entries only pass the carry on
+        started = False
+        for j in range(0, 8, 2):
+            last = (j == 6) and not carry_out
+            if isinstance(srcs[j], int):
+                assert srcs[j] == 0
+                if started:
+                    p.emit("addc.cc.u32", acc[j], acc[j], 0)
+                    p.emit("addc.u32" if last else "addc.cc.u32", acc[j + 1], acc[j + 1], 0)
+                continue
+            p.emit("madc.lo.cc.u32" if started else "mad.lo.cc.u32", acc[j], bi, srcs[j], acc[j])
+            p.emit("madc.hi.u32" if last else "madc.hi.cc.u32", acc[j + 1], bi, srcs[j], acc[j + 1])
+            started = True
+        if not started and carry_out:
+            p.emit("add.cc.u32", acc[0], acc[0], 0)          # leave CF = 0 for the addc that follows
+
+    def cmad_const(acc, consts, bi, carry_out=True):
+        for k, j in enumerate(range(0, 8, 2)):
+            p.emit("mad.lo.cc.u32" if k == 0 else "madc.lo.cc.u32", acc[j], bi, consts[j], acc[j])
+            last = (j == 6) and not carry_out
+            p.emit("madc.hi.u32" if last else "madc.hi.cc.u32", acc[j + 1], bi, consts[j], acc[j + 1])
+
+    def rshift_mad_sparse(odd, srcs, bi):
+        # odd <- (odd >> 64) + srcs[1,3,5,7] * bi + CF
+        for j in range(0, 6, 2):
+            if isinstance(srcs[j + 1], int):
+                p.emit("addc.cc.u32", odd[j], odd[j + 2], 0)
+                p.emit("addc.cc.u32", odd[j + 1], odd[j + 3], 0)
+            else:
+                p.emit("madc.lo.cc.u32", odd[j], srcs[j + 1], bi, odd[j + 2])
+                p.emit("madc.hi.cc.u32", odd[j + 1], srcs[j + 1], bi, odd[j + 3])
+        if isinstance(srcs[7], int):
+            p.emit("addc.cc.u32", odd[6], 0, 0)
+            p.emit("addc.u32", odd[7], 0, 0)
+        else:
+            p.emit("madc.lo.cc.u32", odd[6], srcs[7], bi, 0)
+            p.emit("madc.hi.u32", odd[7], srcs[7], bi, 0)
+
+    even, odd = E, O
+    for i in range(8):
+        bi = A[i]
+        v = row_vec(i)
+        if i == 0:
+            for j in range(0, 8, 2):
+                p.emit("mul.lo.u32", odd[j], v[j + 1], bi)
+                p.emit("mul.hi.u32", odd[j + 1], v[j + 1], bi)
+            for j in range(0, 8, 2):
+                p.emit("mul.lo.u32", even[j], v[j], bi)
+                p.emit("mul.hi.u32", even[j + 1], v[j], bi)
+        else:
+            p.emit("add.cc.u32", even[0], even[0], odd[1])
+            rshift_mad_sparse(odd, v, bi)
+            cmad_sparse(even, v, bi)
+            p.emit("addc.u32", odd[7], odd[7], 0)
+        p.emit("mul.lo.u32", mi, even[0], m0inv)
+        cmad_const(odd, M[1:] + [0], mi, carry_out=False)
+        cmad_const(even, M, mi)
+        p.emit("addc.u32", odd[7], odd[7], 0)
+        even, odd = odd, even
+    Rr = [p.tmp("t%d" % i) for i in range(8)]
+    p.emit("add.cc.u32", Rr[0], even[0], odd[1])
+    for k in range(1, 7):
+        p.emit("addc.cc.u32", Rr[k], even[k], odd[k + 1])
+    p.emit("addc.u32", Rr[7], even[7], 0)
+    OUT = [out + str(i) for i in range(8)]
+    if reduce_final:
+        emit_cond_sub(p, Rr, M, OUT)
+    else:
+        for k in range(8):
+            p.emit("mov.u32", OUT[k], Rr[k])
+    return p, A, OUT
 
 
 def emit_cond_sub(p, X, M, OUT):
@@ -292,6 +413,8 @@ def selftest(iters=2000):
         pa, _, _, OA = gen_add_mod(mod)
         ps, _, _, OS = gen_sub_mod(mod)
         pf, _, _, OF = gen_mont_mul(mod, b_const=[1, 0, 0, 0, 0, 0, 0, 0])
+        pq, _, OQ = gen_mont_sqr(mod)
+        p2, _, _, _, _, O2 = gen_mont_mul(mod, second=("c", "d"))
         edge = [0, 1, mod - 1, mod - 2, (1 << 254) % mod, Rm % mod]
         cases = [(x, y) for x in edge for y in edge] + [(rnd.randrange(mod), rnd.randrange(mod)) for _ in range(iters)]
         for x, y in cases:
@@ -301,14 +424,25 @@ def selftest(iters=2000):
             assert val_of(_emul(pa, env), OA) == (x + y) % mod, (name, "add")
             assert val_of(_emul(ps, env), OS) == (x - y) % mod, (name, "sub")
             assert val_of(_emul(pf, env), OF) == x * Rinv % mod, (name, "from_mont", hex(x))
+            assert val_of(_emul(pq, env), OQ) == x * x * Rinv % mod, (name, "sqr", hex(x))
+            if mod < (1 << 254):      # two products under one reduction (BN254 only: the row sums need m < 2^254)
+                for u, w in ((y, x), (mod - 1, mod - 1), (rnd.randrange(mod), rnd.randrange(mod))):
+                    env2 = dict(env); env2.update(env_of("c", u)); env2.update(env_of("d", w))
+                    assert val_of(_emul(p2, env2), O2) == (x * y + u * w) * Rinv % mod, (name, "mul2add")
         # lazy variant: inputs anywhere below 2m, output < 2m and congruent (BN254 only: needs m < 2^254)
+        pql, _, OQL = gen_mont_sqr(mod, reduce_final=False)
+        for _ in range(iters if mod < (1 << 254) else 0):
+            x = rnd.randrange(2 * mod)
+            got = val_of(_emul(pql, env_of("a", x)), OQL)
+            assert got < 2 * mod and got % mod == x * x * Rinv % mod, (name, "lazy sqr")
         for _ in range(iters if mod < (1 << 254) else 0):
             x, y = rnd.randrange(2 * mod), rnd.randrange(2 * mod)
             env = {}
             env.update(env_of("a", x)); env.update(env_of("b", y))
             got = val_of(_emul(pl, env), OUTL)
             assert got < 2 * mod and got % mod == x * y * Rinv % mod, (name, "lazy mul")
-        print("selftest %s: %d mul/add/sub/from_mont cases ok (%d PTX instructions per mul, %d per from_mont)" % (name, len(cases), len(pm.ins), len(pf.ins)))
+        print("selftest %s: %d mul/sqr/add/sub/from_mont cases ok (%d PTX instructions per mul, %d per sqr, %d per from_mont)"
+              % (name, len(cases), len(pm.ins), len(pq.ins), len(pf.ins)))
 
 
 def c_macro(name, lines):
@@ -340,6 +474,13 @@ def main():
         # r = a / 2^256 mod m (out of Montgomery form): operands %0..%7 = r, %8..%15 = a
         p, A, _, OUT = gen_mont_mul(mod, b_const=[1, 0, 0, 0, 0, 0, 0, 0])
         out.append(c_macro("SNARKV_PTX_%s_FROM_MONT" % name, _strip(p).render(OUT, A)))
+        if not pallas:
+            # r = (a * b + c * d) / 2^256 mod m, one reduction: operands %0..%7 = r, %8..%15 = a, %16..%23 = b, %24..%31 = c, %32..%39 = d
+            p, A, B, C2, D2, OUT = gen_mont_mul(mod, second=("c", "d"))
+            out.append(c_macro("SNARKV_PTX_%s_MUL2ADD" % name, _strip(p).render(OUT, A + B + C2 + D2)))
+        # r = a * a / 2^256 mod m with 36 + 64 partial products: operands %0..%7 = r, %8..%15 = a
+        p, A, OUT = gen_mont_sqr(mod)
+        out.append(c_macro("SNARKV_PTX_%s_SQR" % name, _strip(p).render(OUT, A)))
     sys.stdout.write("\n".join(out))
 
 

@@ -794,12 +794,11 @@ static int msm_accumulate_phase(snarkv_ctx* ctx, const MsmWork& wk, const void* 
             if (cz) pts[z] = cz;
         }
     }
-    // accumulate mode.  Batched affine (6 instead of 10 multiplications per addition, but one inversion per batch, prefix traffic
-    // and whole 32-task units of work per warp) pays once the bucket lists are long and there are enough of them to keep every
-    // warp busy for several rounds — measured on B200 (tools/accumulate_probe.py): mean load 256 at 2^22 terms 10.5 vs 11.3 ms,
-    // 128 at 2^23 18.3 vs 20.6 ms, 256 at 2^24 33.9 vs 41.2 ms; mean load 128 at 2^21 or 64 at 2^20 lose (6.1 vs 5.6, 3.4 vs 2.9 ms).
-    // With >= 2^19 buckets (c = 17, or c = 16 without GLV: the term-chunks of the host entry point) it wins from a mean load of
-    // ~48 on (64 at 2^22 terms, c = 17: 10.5 vs 11.8 ms; e2e 2^24 from host memory 53.1 -> 51.5 ms).
+    // accumulate mode.  Batched affine (6 instead of ~8.3 multiplications' worth of products per addition, but one inversion per
+    // batch, a DRAM-bound forward pass, prefix traffic and whole 32-task units of work per warp) pays once the bucket lists are long.
+    // Measured on B200 (tools/accumulate_probe.py) after the XYZZ addition got its dedicated squarings and the dual-product y3:
+    // mean load 256 at 2^24 terms 33.5 vs 36.7 ms, 128 at 2^23 17.9 vs 18.3 ms; mean load 64 at 2^22 (c = 17) loses, 9.43 vs 9.13 ms,
+    // and so do 128 at 2^21 (GLV) and every shorter list.  ba_min_load = 96 is the crossover for plans with >= 2^19 buckets.
     const int mode = ctx->accumulate_mode;
     const size_t mean_load = nv / pl.NB;
     bool affine = mode == 2 || mode == 3 || (mode == 0 && (mean_load >= 256 || (mean_load >= (size_t)ctx->ba_min_load && nbk >= ((size_t)1 << 19))));
