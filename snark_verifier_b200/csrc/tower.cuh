@@ -34,12 +34,18 @@ __device__ __forceinline__ Fq2 fq2_sub(const Fq2& a, const Fq2& b) { return {fp_
 __device__ __forceinline__ Fq2 fq2_neg(const Fq2& a) { return {fp_neg(a.c0), fp_neg(a.c1)}; }
 __device__ __forceinline__ Fq2 fq2_dbl(const Fq2& a) { return {fp_dbl(a.c0), fp_dbl(a.c1)}; }
 __device__ __forceinline__ Fq2 fq2_conj(const Fq2& a) { return {a.c0, fp_neg(a.c1)}; }
-// Karatsuba: 3 Montgomery multiplications
+// (a0 b0 - a1 b1) + (a0 b1 + a1 b0) i.  Default: two dual-product blocks (each two products under one reduction: 4 x 64 + 2 x 64
+// partial products — the same as Karatsuba's 3 x 128 — but one negation instead of five modular additions / subtractions around
+// them); SNARKV_FQ2_KARATSUBA restores the three-multiplication form.
 static __device__ __noinline__ Fq2 fq2_mul(const Fq2& a, const Fq2& b) {
+#if defined(SNARKV_FQ2_KARATSUBA) || !defined(SNARKV_PTX_FQ_MUL2ADD)
     Fq t0 = fp_mul(a.c0, b.c0);
     Fq t1 = fp_mul(a.c1, b.c1);
     Fq t2 = fp_mul(fp_add(a.c0, a.c1), fp_add(b.c0, b.c1));
     return {fp_sub(t0, t1), fp_sub(fp_sub(t2, t0), t1)};
+#else
+    return {fp_mul2add(a.c0, b.c0, fp_neg(a.c1), b.c1), fp_mul2add(a.c0, b.c1, a.c1, b.c0)};
+#endif
 }
 // (c0 + c1)(c0 - c1), 2 c0 c1: 2 Montgomery multiplications
 static __device__ __noinline__ Fq2 fq2_sqr(const Fq2& a) {
