@@ -56,3 +56,37 @@ def test_generated_device_constants_match_the_model():
     words = [int(w, 16) for w in re.findall(r"0x([0-9a-f]{8})u", body)]
     want = [l for row in rc for v in row for l in limbs(v)] + [l for row in mds for v in row for l in limbs(v)]
     assert words == want
+
+
+def test_lane_schedule_of_the_device_permutation_matches_the_plain_rounds():
+    """csrc/poseidon.cu poseidon_permute_lanes: one proof per group of five lanes, lane g holds state[g].  A partial round is six
+    multiplication steps — lane 0: x^2, x^4, x^5; lanes j >= 1: M[0][j] x_j (an entry of lane 0's row), then M[j][1..4] x_1..4; last step
+    every lane M[g][0] x_0^5; lane 0 sums the four row-0 entries it is handed, lanes j their own four.  Emulated lane by lane over
+    exact integers (every value a lane reads from another lane goes through `shfl`) against the textbook rounds."""
+    T, RF, RP = 5, 8, 60
+    rc, mds = pm.generate(T, RF, RP)
+
+    def permute_lanes(state):
+        s = list(state)                                   # s[g] = register of lane g
+        for r in range(RF + RP):
+            x = [(s[g] + rc[r][g]) % R for g in range(T)]
+            shfl = lambda v, lane: v[lane]                # noqa: E731 — a value read from another lane of the group
+            if r < RF // 2 or r >= RF // 2 + RP:
+                y = [pow(x[g], 5, R) for g in range(T)]
+                s = [sum(mds[g][j] * shfl(y, j) for j in range(T)) % R for g in range(T)]
+                continue
+            t1, t2, t3, t4, t5 = [0] * T, [0] * T, [0] * T, [0] * T, [0] * T
+            for g in range(T):
+                z = g == 0
+                t1[g] = (x[g] if z else mds[0][g]) * x[g] % R                                   # step 1
+                t2[g] = (t1[g] if z else mds[g][1]) * (t1[g] if z else shfl(x, 1)) % R          # step 2
+                t3[g] = (t2[g] if z else mds[g][2]) * (x[g] if z else shfl(x, 2)) % R           # step 3
+                t4[g] = mds[g][3] * shfl(x, 3) % R                                              # steps 4, 5 (lane 0 idles along)
+                t5[g] = mds[g][4] * shfl(x, 4) % R
+            q = [mds[g][0] * shfl(t3, 0) % R for g in range(T)]                                 # step 6
+            row0 = (shfl(t1, 1) + shfl(t1, 2) + shfl(t1, 3) + shfl(t1, 4)) % R
+            s = [(q[g] + (row0 if g == 0 else t2[g] + t3[g] + t4[g] + t5[g])) % R for g in range(T)]
+        return s
+
+    for state in ([0, 1, 2, 3, 4], [R - 1, 0, 12345, 1 << 200, 7]):
+        assert permute_lanes(state) == pm.permute(list(state), rc, mds, RF, RP)
