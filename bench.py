@@ -35,7 +35,7 @@ LOG_N_DEFAULT = 24
 SEED = 2024
 ALG_BYTES_PER_TERM = 96            # 64 B affine point + 32 B scalar, each read once
 MADD_MULMODS = 10                  # XYZZ mixed addition: 8M + 2S (csrc/g1.cuh); the 2S are SQR blocks and y3 one MUL2ADD block, i.e.
-                                   # ~8.3 multiplications' worth of partial products — the count below stays the formula's
+                                   # ~9.1 multiplications' worth of partial products (1160 instead of 1280) — the count below stays the formula's
 AFFINE_MULMODS = 6                 # batched-affine addition: 3 for the shared inversion + 1M + 1S + 1M (csrc/bucket_affine.cuh)
 IMAD_PER_MULMOD = 136              # FMA-pipe instructions per Montgomery multiplication (cuobjdump: 120 IMAD.WIDE + 8 IMAD + 8 IMAD.HI;
                                    # in the batched-affine kernel ptxas adds ~13 IMAD.X per call)
